@@ -64,7 +64,7 @@ def test_anatomask_steps_match_reference(golden_dir, name):
         loss, mask, recon = tr.anatomask_step(inp, s['mask1'], s['epoch'])
         assert torch.allclose(recon, s['teacher_loss'], rtol=1e-4, atol=1e-6)
         assert torch.equal(mask, s['mask']), f'hard mask differs at step {it}'       # bit-exact
-        assert loss == pytest.approx(s['loss'], rel=1e-4)
+        assert loss == pytest.approx(s['loss'], rel=1e-4 if it == 0 else 2e-3)   # later steps inherit Adam jitter
     # Post-step state.  Conv biases that feed a pooled norm have analytically-zero gradients (the reference shows
     # 1e-8..1e-10 noise); Adam normalises that noise into ±lr steps of arbitrary sign, so those
     # entries are only bounded by n_steps·lr, and everything downstream inherits ~1e-4 of jitter.
