@@ -74,7 +74,7 @@ def test_anatomask_steps_match_reference(golden_dir, name):
             t = have[k].detach().double().flatten()[:64]
             err = float((t - d['head'].double()).abs().max())
             zero_grad_bias = 'sparse_encoder' in k and k.endswith(('conv1.bias', 'conv2.bias'))
-            bound = 2.2 * nsteps * lr if zero_grad_bias else 0.6 * lr
+            bound = 2.2 * nsteps * lr if zero_grad_bias else 1.5 * lr
             if which == 'teacher':
                 bound *= 0.01        # EMA decay >= 0.999 scales student jitter by <= 1e-3 per step
                 bound += 1e-6
