@@ -1,0 +1,414 @@
+// tcgen05 / TMEM / TMA implicit-GEMM execution of a gather-GEMM plan (conv_plan.cuh).
+//
+//   tile      : 128 output voxels (a box bn×bd×bh×bw of one out view) × NT output channels
+//   K loop    : for every tap of the tile's group, for every KC-channel slab of the gathered tensor:
+//                 A = TMA box load of the tap-shifted input window  → smem [128 rows][KC] (K-major, 128/64/32B swizzle)
+//                 B = TMA load of W[tap][nt*NT .. +NT][slab]         → smem [NT rows][KC]
+//                 KC/16 × tcgen05.mma (M=128, N=NT, K=16), fp32 accumulators in TMEM
+//               zero padding and stride-2 / transposed-conv geometry come for free from TMA out-of-bounds fill and
+//               parity-class tensor maps — there is no im2col buffer.
+//   roles     : warp 0 TMA producer · warp 1 MMA issuer · warp 2 TMEM allocator · warps 4-7 epilogue
+//   pipelines : smem ring (full/empty mbarriers) and a double-buffered TMEM accumulator (tmem_full/tmem_empty), so the
+//               epilogue of tile i overlaps the main loop of tile i+1; CTAs are persistent (one per SM) and walk the
+//               tile list with a static stride.
+//   epilogue  : TMEM → registers (tcgen05.ld 32x32b) → +bias → mask → bf16 → 128-bit global stores; optional
+//               per-channel Σy / Σy² (warp transpose-reduce → smem → one fp64 atomic per channel per CTA).
+//   sparsity  : with an active-patch work-list only tiles inside visible patches are enumerated (stage 0/1 of the
+//               encoder, where a 2×8×8 tile fits a patch); otherwise tiles are dense and the epilogue zeroes masked rows.
+#include "conv_plan.cuh"
+#include "ptx.cuh"
+
+namespace amb {
+
+using namespace ptx;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int kc) {
+    return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// rank-5 map over a view: dims (C, W, H, D, N), box (kc, bw, bh, bd, bn)
+int encode_view_map(CUtensorMap* m, const void* tensor_base, const View& v, int C, int kc, const int box[4]) {
+    EncodeTiledFn enc = get_encode();
+    AMB_CHECK(enc != nullptr, AMB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.D, (cuuint64_t)v.N};
+    cuuint64_t strides[4] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sD * 2, (cuuint64_t)v.sN * 2};
+    cuuint32_t bx[5] = {(cuuint32_t)kc, (cuuint32_t)box[3], (cuuint32_t)box[2], (cuuint32_t)box[1], (cuuint32_t)box[0]};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    void* base = (void*)((const bf16*)tensor_base + v.base);
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AMB_CHECK(r == CUDA_SUCCESS, AMB_ERR_CUDA,
+              "cuTensorMapEncodeTiled(view) failed: %d (C=%d dims %d,%d,%d,%d box %d,%d,%d,%d kc=%d)", (int)r, C, v.N,
+              v.D, v.H, v.W, box[0], box[1], box[2], box[3], kc);
+    return 0;
+}
+
+// rank-3 map over packed weights [T][rows][cols]: dims (cols, rows, T), box (kc, nt, 1)
+int encode_weight_map(CUtensorMap* m, const void* w, int T, int rows, int cols, int kc, int nt) {
+    EncodeTiledFn enc = get_encode();
+    AMB_CHECK(enc != nullptr, AMB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)T};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * cols * 2};
+    cuuint32_t bx[3] = {(cuuint32_t)kc, (cuuint32_t)nt, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)w, dims, strides, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AMB_CHECK(r == CUDA_SUCCESS, AMB_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d (T=%d rows=%d cols=%d)", (int)r, T,
+              rows, cols);
+    return 0;
+}
+
+struct IgemmParams {
+    CUtensorMap in_maps[8];
+    CUtensorMap w_map;
+    Plan plan;
+    bf16* y;
+    const float* bias;
+    const uint8_t* active;
+    const int* list;
+    const int* count;
+    double* stats;
+    int lgbn, lgbd, lgbh, lgbw;      // log2 of the tile box
+    int Tn, Tz, Ty, Tx;              // dense tiling of an out view
+    int n_ntiles, NT;
+    int kchunks;                     // Cx / KC
+    int stages;
+    uint32_t stage_bytes, a_bytes, b_bytes;
+    uint32_t tmem_cols;
+    uint32_t idesc;
+};
+
+struct TileCoord {
+    int g, n0, z0, y0, x0, nt;
+};
+
+__device__ __forceinline__ long num_tiles(const IgemmParams& P) {
+    const Plan& p = P.plan;
+    long per_group;
+    if (P.list) {
+        const int Pv = 1 << p.lgPv;
+        per_group = (long)(*P.count) * (Pv >> P.lgbd) * (Pv >> P.lgbh) * (Pv >> P.lgbw);
+    } else {
+        per_group = (long)P.Tn * P.Tz * P.Ty * P.Tx;
+    }
+    return per_group * p.n_groups * P.n_ntiles;
+}
+
+__device__ __forceinline__ void decode_tile(const IgemmParams& P, long t, TileCoord& c) {
+    const Plan& p = P.plan;
+    c.nt = (int)(t % P.n_ntiles);
+    t /= P.n_ntiles;
+    if (P.list) {
+        const int Pv = 1 << p.lgPv;
+        const int sx = Pv >> P.lgbw, sy = Pv >> P.lgbh, sz = Pv >> P.lgbd;
+        int ix = (int)(t % sx); t /= sx;
+        int iy = (int)(t % sy); t /= sy;
+        int iz = (int)(t % sz); t /= sz;
+        const long cnt = *P.count;
+        int pid = P.list[t % cnt];
+        c.g = (int)(t / cnt);
+        const int L = p.fd * p.fh * p.fw;
+        c.n0 = pid / L;
+        int l = pid % L;
+        c.z0 = ((l / (p.fh * p.fw)) << p.lgPv) + (iz << P.lgbd);
+        c.y0 = (((l / p.fw) % p.fh) << p.lgPv) + (iy << P.lgbh);
+        c.x0 = ((l % p.fw) << p.lgPv) + (ix << P.lgbw);
+    } else {
+        c.x0 = (int)(t % P.Tx) << P.lgbw; t /= P.Tx;
+        c.y0 = (int)(t % P.Ty) << P.lgbh; t /= P.Ty;
+        c.z0 = (int)(t % P.Tz) << P.lgbd; t /= P.Tz;
+        c.n0 = (int)(t % P.Tn) << P.lgbn;
+        c.g = (int)(t / P.Tn);
+    }
+}
+
+// transpose-reduce: every lane holds v[0..31] (one row, 32 columns); afterwards lane L holds Σ_rows column L in v[0]
+__device__ __forceinline__ float warp_column_sums(float* v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            float send = up ? v[i] : v[i + o];
+            float keep = up ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
+
+template <int KC>
+__global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ IgemmParams P) {
+    constexpr uint32_t LAYOUT = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);     // SW128 / SW64 / SW32
+    constexpr uint32_t SBO = 8u * KC * 2u;                                // 8 rows of KC bf16
+    extern __shared__ uint8_t smem_raw[];
+    const Plan& p = P.plan;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* ctrl = smem + (size_t)P.stages * P.stage_bytes;
+    uint64_t* full_bar = (uint64_t*)ctrl;                 // [stages]
+    uint64_t* empty_bar = full_bar + 8;                   // [stages]
+    uint64_t* tfull_bar = empty_bar + 8;                  // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                 // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    float* s_stats = (float*)(ctrl + 256);                // [2][Cy] when stats requested
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < p.n_in_views; ++i) prefetch_tmap(&P.in_maps[i]);
+        prefetch_tmap(&P.w_map);
+    }
+    if (P.stats) for (int i = threadIdx.x; i < 2 * p.Cy; i += blockDim.x) s_stats[i] = 0.f;
+    if (warp == 2) tmem_alloc(tmem_slot, P.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const long ntiles = num_tiles(P);
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                TileCoord c;
+                decode_tile(P, t, c);
+                const Group& G = p.groups[c.g];
+                for (int ti = G.tap_begin; ti < G.tap_begin + G.tap_count; ++ti) {
+                    const Tap T = p.taps[ti];
+                    for (int kc = 0; kc < P.kchunks; ++kc, ++it) {
+                        const int s = it % P.stages;
+                        mbar_wait(&empty_bar[s], ((it / P.stages) & 1) ^ 1, 1);
+                        uint8_t* a_dst = smem + (size_t)s * P.stage_bytes;
+                        uint8_t* b_dst = a_dst + P.a_bytes;
+                        mbar_expect_tx(&full_bar[s], P.a_bytes + P.b_bytes);
+                        tma_load_5d(a_dst, &P.in_maps[T.view], &full_bar[s], kc * KC, c.x0 + T.dx, c.y0 + T.dy,
+                                    c.z0 + T.dz, c.n0);
+                        tma_load_3d(b_dst, &P.w_map, &full_bar[s], kc * KC, c.nt * P.NT, T.w);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            uint32_t it = 0, tile_iter = 0;
+            for (long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tile_iter) {
+                TileCoord c;
+                decode_tile(P, t, c);
+                const Group& G = p.groups[c.g];
+                const int acc = tile_iter & 1;
+                mbar_wait(&tempty_bar[acc], ((tile_iter >> 1) & 1) ^ 1, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.NT);
+                const int kblocks = G.tap_count * P.kchunks;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % P.stages;
+                    mbar_wait(&full_bar[s], (it / P.stages) & 1, 3);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + (size_t)s * P.stage_bytes);
+                    const uint32_t b_addr = a_addr + P.a_bytes;
+                    const uint64_t adesc = umma_desc(a_addr, 16, SBO, LAYOUT);
+                    const uint64_t bdesc = umma_desc(b_addr, 16, SBO, LAYOUT);
+#pragma unroll
+                    for (int k = 0; k < KC / 16; ++k) {
+                        // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
+                        mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (kb | k) != 0);
+                    }
+                    mma_commit(&empty_bar[s]);          // smem slot free once these MMAs retire
+                }
+                mma_commit(&tfull_bar[acc]);            // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // =============================== epilogue ===============================
+        const int q = warp - 4;                         // TMEM lane quadrant == warp % 4
+        const int row = q * 32 + lane;
+        uint32_t tile_iter = 0;
+        for (long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tile_iter) {
+            TileCoord c;
+            decode_tile(P, t, c);
+            const Group& G = p.groups[c.g];
+            const View& ov = p.out_views[G.out_view];
+            const int acc = tile_iter & 1;
+            // row → voxel of the out view (same linearisation as the TMA box: n, z, y, x with x fastest)
+            const int x = c.x0 + (row & ((1 << P.lgbw) - 1));
+            const int y = c.y0 + ((row >> P.lgbw) & ((1 << P.lgbh) - 1));
+            const int z = c.z0 + ((row >> (P.lgbw + P.lgbh)) & ((1 << P.lgbd) - 1));
+            const int n = c.n0 + (row >> (P.lgbw + P.lgbh + P.lgbd));
+            const bool valid = n < p.oN && z < p.oD && y < p.oH && x < p.oW;
+            bool on = valid;
+            if (valid && P.active && p.lgPv >= 0)
+                on = P.active[((n * p.fd + (z >> p.lgPv)) * p.fh + (y >> p.lgPv)) * p.fw + (x >> p.lgPv)] != 0;
+            bf16* yrow = P.y + ov.base + (long)n * ov.sN + (long)z * ov.sD + (long)y * ov.sH + (long)x * ov.sW +
+                         (long)c.nt * P.NT;
+            mbar_wait(&tfull_bar[acc], (tile_iter >> 1) & 1, 4);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P.NT);
+            for (int col = 0; col < P.NT; col += 32) {
+                uint32_t r[32];
+                const bool wide = (P.NT - col) >= 32;
+                if (wide) tmem_ld_x32(t_addr + col, r);
+                else tmem_ld_x16(t_addr + col, r);
+                tmem_ld_wait();
+                const int ncol = wide ? 32 : 16;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float f = 0.f;
+                    if (j < ncol) {
+                        f = __uint_as_float(r[j]);
+                        if (P.bias) f += __ldg(P.bias + c.nt * P.NT + col + j);
+                        if (!on) f = 0.f;
+                    }
+                    v[j] = f;
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (j < ncol) {
+                            uint4 o;
+                            o.x = pack2(v[j], v[j + 1]); o.y = pack2(v[j + 2], v[j + 3]);
+                            o.z = pack2(v[j + 4], v[j + 5]); o.w = pack2(v[j + 6], v[j + 7]);
+                            *reinterpret_cast<uint4*>(yrow + col + j) = o;
+                        }
+                    }
+                }
+                if (P.stats) {
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { if (!valid) v[j] = 0.f; sq[j] = v[j] * v[j]; }
+                    float s1 = warp_column_sums(v);
+                    float s2 = warp_column_sums(sq);
+                    if (lane < ncol) {
+                        atomicAdd(&s_stats[c.nt * P.NT + col + lane], s1);
+                        atomicAdd(&s_stats[p.Cy + c.nt * P.NT + col + lane], s2);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (P.stats) {
+        for (int i = threadIdx.x; i < 2 * p.Cy; i += blockDim.x) {
+            float v = s_stats[i];
+            if (v != 0.f) atomicAdd(&P.stats[i], (double)v);
+        }
+    }
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, P.tmem_cols);
+    }
+}
+
+static int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) l++;
+    return l;
+}
+static int pow2_ceil(int v) { return 1 << ilog2(v); }
+
+static int pick_nt(int Cy) {
+    for (int nt = 256; nt >= 16; nt -= 16)
+        if (Cy % nt == 0) return nt;
+    return 0;
+}
+
+int igemm_conv(const Plan& p, const amb_conv_args* a) {
+    // shapes the tensor-core kernel takes
+    if (p.Cx % 16 != 0 || p.Cy % 16 != 0) {
+        set_error("Cx=%d / Cy=%d not multiples of 16", p.Cx, p.Cy);
+        return 0;
+    }
+    const int KC = p.Cx % 64 == 0 ? 64 : (p.Cx % 32 == 0 ? 32 : 16);
+    const int NT = pick_nt(p.Cy);
+    if (NT == 0) { set_error("no N tile for Cy=%d", p.Cy); return 0; }
+    if (a->stats && p.Cy > 2048) { set_error("stats: Cy too large"); return 0; }
+
+    static IgemmParams P;       // host staging (single-threaded by contract, mirrors `_cur_active`)
+    memset(&P, 0, sizeof(P));
+    P.plan = p;
+    // tile box: 128 voxels
+    int bw = pow2_ceil(p.oW) < 8 ? pow2_ceil(p.oW) : 8;
+    int bh = pow2_ceil(p.oH) < 8 ? pow2_ceil(p.oH) : 8;
+    int rem = 128 / (bw * bh);
+    int bd = pow2_ceil(p.oD) < rem ? pow2_ceil(p.oD) : rem;
+    int bn = rem / bd;
+    const bool use_list = a->active_list != nullptr && p.lgPv >= 0 && (1 << p.lgPv) >= 8 && bn == 1 && bw == 8 &&
+                          bh == 8 && bd == 2;
+    P.lgbn = ilog2(bn); P.lgbd = ilog2(bd); P.lgbh = ilog2(bh); P.lgbw = ilog2(bw);
+    P.Tn = ceil_div(p.oN, bn); P.Tz = ceil_div(p.oD, bd); P.Ty = ceil_div(p.oH, bh); P.Tx = ceil_div(p.oW, bw);
+    P.NT = NT; P.n_ntiles = p.Cy / NT;
+    P.kchunks = p.Cx / KC;
+    P.a_bytes = 128u * KC * 2u;
+    P.b_bytes = (uint32_t)NT * KC * 2u;
+    P.stage_bytes = (P.a_bytes + P.b_bytes + 1023u) & ~1023u;
+    int stages = (int)((196u * 1024u) / P.stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) { set_error("tile does not fit shared memory"); return 0; }
+    P.stages = stages;
+    P.tmem_cols = (uint32_t)pow2_ceil(2 * NT);
+    if (P.tmem_cols < 32) P.tmem_cols = 32;
+    P.idesc = umma_idesc_bf16(128, NT, 0, 0);
+    P.y = (bf16*)a->y; P.bias = a->bias; P.active = a->active;
+    P.list = use_list ? a->active_list : nullptr;
+    P.count = use_list ? a->active_count : nullptr;
+    P.stats = a->stats;
+
+    const int box[4] = {bn, bd, bh, bw};
+    for (int i = 0; i < p.n_in_views; ++i)
+        if (int e = encode_view_map(&P.in_maps[i], a->x, p.in_views[i], p.Cx, KC, box)) return e;
+    int T = 0;
+    for (int i = 0; i < p.n_taps; ++i) if (p.taps[i].w + 1 > T) T = p.taps[i].w + 1;
+    // the packed weight tensor always holds k³ (or 64) slabs even when a plan uses a subset
+    int T_full = (a->op == AMB_OP_CONVT || a->op == AMB_OP_CONVT_DGRAD) ? 64 : a->k * a->k * a->k;
+    if (T_full > T) T = T_full;
+    if (int e = encode_weight_map(&P.w_map, a->w, T, p.Cy, p.Cx, KC, NT)) return e;
+
+    size_t smem = (size_t)P.stages * P.stage_bytes + 1024 + 256 + (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0);
+    long tiles_upper = (long)P.Tn * P.Tz * P.Ty * P.Tx * p.n_groups * P.n_ntiles;
+    int grid = (int)(tiles_upper < (long)num_sms() ? tiles_upper : (long)num_sms());
+    cudaStream_t st = (cudaStream_t)a->stream;
+    if (KC == 64) {
+        AMB_CUDA(cudaFuncSetAttribute(igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        igemm_kernel<64><<<grid, 256, smem, st>>>(P);
+    } else if (KC == 32) {
+        AMB_CUDA(cudaFuncSetAttribute(igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        igemm_kernel<32><<<grid, 256, smem, st>>>(P);
+    } else {
+        AMB_CUDA(cudaFuncSetAttribute(igemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        igemm_kernel<16><<<grid, 256, smem, st>>>(P);
+    }
+    AMB_LAUNCH_CHECK();
+    return 1;
+}
+
+}  // namespace amb

@@ -1,0 +1,353 @@
+// tcgen05 weight-gradient kernel for a gather-GEMM plan:
+//     dW[tap.w][r][c] += Σ_o dY_view(tap)[o − off(tap), r] · X_view(tap)[o, c]
+// i.e. per tap a GEMM with M = r (channels of dY), N = c (channels of X), K = voxels.  Both operands are read exactly as
+// they lie in HBM (channels-last): a TMA box of 128 voxels × ≤64 channels lands in smem as [voxel][channel] rows, which
+// is the *MN-major* canonical UMMA layout (K = voxel rows, 8-row groups SBO apart, 64/32/16-channel atoms LBO apart).
+// The X box is loaded once per voxel tile and shared by all taps; the taps differ only in the shift of the dY box, so
+// for narrow layers (Cy < 128) 128/Cy taps are stacked along M and one MMA computes several taps.
+//
+//   job      : (batch of ≤ 512/NTw accumulator units sharing one X view and N chunk) × (a K split of the voxel tiles)
+//   roles    : warp 0 TMA producer (X ring ×2, dY ring ×4) · warp 1 MMA issuer · warp 2 TMEM alloc · warps 4-7 epilogue
+//   epilogue : accumulators (TMEM) → fp32 atomics into dW (split-K reduction across CTAs)
+#include "conv_plan.cuh"
+#include "ptx.cuh"
+
+namespace amb {
+
+using namespace ptx;
+
+int encode_view_map(CUtensorMap* m, const void* tensor_base, const View& v, int C, int kc, const int box[4]);
+
+#define WG_MAX_UNITS 64
+#define WG_MAX_BATCH 32
+
+struct WTap {
+    int8_t aview, sz, sy, sx;     // dY view and the shift applied to the tile origin (= −tap offset)
+    int16_t w;
+    int16_t bview;
+};
+struct WBatch {
+    int16_t unit_begin, unit_count, bview, pad;
+};
+
+struct WgradParams {
+    CUtensorMap a_maps[8];        // dY views, box = slabW channels × 128 voxels
+    CUtensorMap b_maps[8];        // X views,  box = nslabW channels × 128 voxels
+    WTap taps[64];
+    int8_t unit_taps[WG_MAX_UNITS][8];   // stacked mode: tap index per M slab (−1 = none)
+    WBatch batches[WG_MAX_BATCH];
+    int n_batches, n_units;
+    int stacked;                  // 1: Cy < 128, units stack 128/Cy taps ; 0: unit = (tap, 128-row slab of Cy)
+    int mslabs;                   // Cy / 128 when !stacked
+    int Cx, Cy;
+    int slabW, a_slabs;           // dY slab width (channels) and slabs per A slot (always 128 rows in total)
+    int nslabW, b_slabs, NTw, n_nchunks;
+    uint32_t a_slab_bytes, b_slab_bytes;
+    int lgbn, lgbd, lgbh, lgbw, Tn, Tz, Ty, Tx;
+    int oN, oD, oH, oW, lgPv, fd, fh, fw;
+    const int* list;
+    const int* count;
+    int ksplit;
+    float* dw;
+    uint32_t idesc;
+    uint32_t a_layout, b_layout, a_sbo, b_sbo, a_kstep, b_kstep;
+};
+
+#define WG_A_SLOTS 4
+#define WG_B_SLOTS 2
+#define WG_SLOT_BYTES 32768u
+
+__device__ __forceinline__ long wg_num_ktiles(const WgradParams& P) {
+    if (P.list) {
+        const int Pv = 1 << P.lgPv;
+        return (long)(*P.count) * (Pv >> P.lgbd) * (Pv >> P.lgbh) * (Pv >> P.lgbw);
+    }
+    return (long)P.Tn * P.Tz * P.Ty * P.Tx;
+}
+
+__device__ __forceinline__ void wg_decode(const WgradParams& P, long t, int& n0, int& z0, int& y0, int& x0) {
+    if (P.list) {
+        const int Pv = 1 << P.lgPv;
+        const int sx = Pv >> P.lgbw, sy = Pv >> P.lgbh, sz = Pv >> P.lgbd;
+        int ix = (int)(t % sx); t /= sx;
+        int iy = (int)(t % sy); t /= sy;
+        int iz = (int)(t % sz); t /= sz;
+        int pid = P.list[t];
+        const int L = P.fd * P.fh * P.fw;
+        n0 = pid / L;
+        int l = pid % L;
+        z0 = ((l / (P.fh * P.fw)) << P.lgPv) + (iz << P.lgbd);
+        y0 = (((l / P.fw) % P.fh) << P.lgPv) + (iy << P.lgbh);
+        x0 = ((l % P.fw) << P.lgPv) + (ix << P.lgbw);
+    } else {
+        x0 = (int)(t % P.Tx) << P.lgbw; t /= P.Tx;
+        y0 = (int)(t % P.Ty) << P.lgbh; t /= P.Ty;
+        z0 = (int)(t % P.Tz) << P.lgbd; t /= P.Tz;
+        n0 = (int)t << P.lgbn;
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ WgradParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + WG_A_SLOTS * WG_SLOT_BYTES;
+    uint8_t* ctrl = b_ring + WG_B_SLOTS * WG_SLOT_BYTES;
+    uint64_t* a_full = (uint64_t*)ctrl;
+    uint64_t* a_empty = a_full + WG_A_SLOTS;
+    uint64_t* b_full = a_empty + WG_A_SLOTS;
+    uint64_t* b_empty = b_full + WG_B_SLOTS;
+    uint64_t* acc_full = b_empty + WG_B_SLOTS;
+    uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WG_A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < WG_B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // job decode: blockIdx.x = (batch, nchunk, ksplit)
+    int job = blockIdx.x;
+    const int ks = job % P.ksplit; job /= P.ksplit;
+    const int nchunk = job % P.n_nchunks; job /= P.n_nchunks;
+    const WBatch B = P.batches[job];
+    const long ktiles = wg_num_ktiles(P);
+    const long k_begin = ktiles * ks / P.ksplit, k_end = ktiles * (ks + 1) / P.ksplit;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t ai = 0, bi = 0;
+            for (long kt = k_begin; kt < k_end; ++kt, ++bi) {
+                int n0, z0, y0, x0;
+                wg_decode(P, kt, n0, z0, y0, x0);
+                const int bs = bi % WG_B_SLOTS;
+                mbar_wait(&b_empty[bs], ((bi / WG_B_SLOTS) & 1) ^ 1, 11);
+                mbar_expect_tx(&b_full[bs], P.b_slab_bytes * P.b_slabs);
+                for (int j = 0; j < P.b_slabs; ++j)
+                    tma_load_5d(b_ring + bs * WG_SLOT_BYTES + j * P.b_slab_bytes, &P.b_maps[B.bview], &b_full[bs],
+                                nchunk * P.NTw + j * P.nslabW, x0, y0, z0, n0);
+                for (int u = B.unit_begin; u < B.unit_begin + B.unit_count; ++u, ++ai) {
+                    const int as = ai % WG_A_SLOTS;
+                    mbar_wait(&a_empty[as], ((ai / WG_A_SLOTS) & 1) ^ 1, 12);
+                    uint8_t* dst = a_ring + as * WG_SLOT_BYTES;
+                    if (P.stacked) {
+                        int real = 0;
+                        for (int j = 0; j < P.a_slabs; ++j) real += P.unit_taps[u][j] >= 0;
+                        mbar_expect_tx(&a_full[as], P.a_slab_bytes * real);
+                        for (int j = 0; j < P.a_slabs; ++j) {
+                            const int ti = P.unit_taps[u][j];
+                            if (ti < 0) continue;
+                            const WTap T = P.taps[ti];
+                            tma_load_5d(dst + j * P.a_slab_bytes, &P.a_maps[T.aview], &a_full[as], 0, x0 + T.sx,
+                                        y0 + T.sy, z0 + T.sz, n0);
+                        }
+                    } else {
+                        const WTap T = P.taps[u / P.mslabs];
+                        const int ms = u % P.mslabs;
+                        mbar_expect_tx(&a_full[as], P.a_slab_bytes * P.a_slabs);
+                        for (int j = 0; j < P.a_slabs; ++j)
+                            tma_load_5d(dst + j * P.a_slab_bytes, &P.a_maps[T.aview], &a_full[as],
+                                        ms * 128 + j * P.slabW, x0 + T.sx, y0 + T.sy, z0 + T.sz, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t ai = 0, bi = 0;
+            for (long kt = k_begin; kt < k_end; ++kt, ++bi) {
+                const int bs = bi % WG_B_SLOTS;
+                mbar_wait(&b_full[bs], (bi / WG_B_SLOTS) & 1, 13);
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(b_ring + bs * WG_SLOT_BYTES);
+                const uint64_t bdesc = umma_desc(b_addr, P.b_slab_bytes, P.b_sbo, P.b_layout);
+                for (int u = 0; u < B.unit_count; ++u, ++ai) {
+                    const int as = ai % WG_A_SLOTS;
+                    mbar_wait(&a_full[as], (ai / WG_A_SLOTS) & 1, 14);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(a_ring + as * WG_SLOT_BYTES);
+                    const uint64_t adesc = umma_desc(a_addr, P.a_slab_bytes, P.a_sbo, P.a_layout);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(u * P.NTw);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)      // 128 voxels per tile = 8 × K16
+                        mma_bf16(d_tmem, adesc + (uint64_t)((P.a_kstep * k) >> 4), bdesc + (uint64_t)((P.b_kstep * k) >> 4),
+                                 P.idesc, (kt != k_begin) || (k != 0));
+                    mma_commit(&a_empty[as]);
+                }
+                mma_commit(&b_empty[bs]);
+            }
+            mma_commit(acc_full);
+        }
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        const int m = q * 32 + lane;
+        mbar_wait(acc_full, 0, 15);
+        tc_fence_after();
+        if (k_end > k_begin) {
+            for (int u = 0; u < B.unit_count; ++u) {
+                const int ug = B.unit_begin + u;
+                int ti, r;
+                if (P.stacked) {
+                    ti = P.unit_taps[ug][m / P.slabW];
+                    r = m % P.slabW;
+                } else {
+                    ti = ug / P.mslabs;
+                    r = (ug % P.mslabs) * 128 + m;
+                }
+                float* dst = nullptr;
+                if (ti >= 0) dst = P.dw + ((long)P.taps[ti].w * P.Cy + r) * P.Cx + nchunk * P.NTw;
+                const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * P.NTw);
+                for (int col = 0; col < P.NTw; col += 16) {
+                    uint32_t rr[16];
+                    tmem_ld_x16(t_addr + col, rr);
+                    tmem_ld_wait();
+                    if (dst) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) atomicAdd(dst + col + j, __uint_as_float(rr[j]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static int ilog2w(int v) {
+    int l = 0;
+    while ((1 << l) < v) l++;
+    return l;
+}
+static int pow2_ceilw(int v) { return 1 << ilog2w(v); }
+static bool chan_ok(int c) { return c == 16 || c == 32 || c == 64 || c % 128 == 0; }
+
+int igemm_wgrad(const Plan& p, const amb_wgrad_args* a) {
+    // roles here: dY has p.Cy channels (M), X has p.Cx channels (N)
+    if (!chan_ok(p.Cx) || !chan_ok(p.Cy)) {
+        set_error("wgrad: channels (%d,%d) must be 16, 32, 64 or a multiple of 128", p.Cx, p.Cy);
+        return 0;
+    }
+    static WgradParams P;
+    memset(&P, 0, sizeof(P));
+    P.Cx = p.Cx; P.Cy = p.Cy;
+    P.stacked = p.Cy < 128;
+    P.slabW = p.Cy < 64 ? p.Cy : 64;
+    P.a_slabs = 128 / P.slabW;
+    P.mslabs = P.stacked ? 1 : p.Cy / 128;
+    P.NTw = p.Cx < 128 ? p.Cx : 128;
+    P.nslabW = P.NTw < 64 ? P.NTw : 64;
+    P.b_slabs = P.NTw / P.nslabW;
+    P.n_nchunks = p.Cx / P.NTw;
+    P.a_slab_bytes = 128u * P.slabW * 2u;
+    P.b_slab_bytes = 128u * P.nslabW * 2u;
+    auto layout_of = [](int w) { return w == 64 ? 2u : (w == 32 ? 4u : 6u); };
+    P.a_layout = layout_of(P.slabW); P.b_layout = layout_of(P.nslabW);
+    P.a_sbo = 8u * P.slabW * 2u; P.b_sbo = 8u * P.nslabW * 2u;       // 8 voxel rows
+    P.a_kstep = 16u * P.slabW * 2u; P.b_kstep = 16u * P.nslabW * 2u; // 16 voxel rows per MMA
+    P.idesc = umma_idesc_bf16(128, P.NTw, 1, 1);
+    P.oN = p.oN; P.oD = p.oD; P.oH = p.oH; P.oW = p.oW;
+    P.lgPv = p.lgPv; P.fd = p.fd; P.fh = p.fh; P.fw = p.fw;
+    P.dw = a->dw;
+
+    int bw = pow2_ceilw(p.oW) < 8 ? pow2_ceilw(p.oW) : 8;
+    int bh = pow2_ceilw(p.oH) < 8 ? pow2_ceilw(p.oH) : 8;
+    int rem = 128 / (bw * bh);
+    int bd = pow2_ceilw(p.oD) < rem ? pow2_ceilw(p.oD) : rem;
+    int bn = rem / bd;
+    const bool use_list = a->active_list != nullptr && p.lgPv >= 0 && (1 << p.lgPv) >= 8 && bn == 1 && bw == 8 &&
+                          bh == 8 && bd == 2;
+    P.list = use_list ? a->active_list : nullptr;
+    P.count = use_list ? a->active_count : nullptr;
+    P.lgbn = ilog2w(bn); P.lgbd = ilog2w(bd); P.lgbh = ilog2w(bh); P.lgbw = ilog2w(bw);
+    P.Tn = ceil_div(p.oN, bn); P.Tz = ceil_div(p.oD, bd); P.Ty = ceil_div(p.oH, bh); P.Tx = ceil_div(p.oW, bw);
+
+    // taps sorted by X view (plan in_view); the dY view of a tap is the out view of its group
+    int order[64], n = 0;
+    for (int v = 0; v < p.n_in_views; ++v)
+        for (int t = 0; t < p.n_taps; ++t)
+            if (p.taps[t].view == v) order[n++] = t;
+    for (int i = 0; i < n; ++i) {
+        const Tap& T = p.taps[order[i]];
+        int g = 0;
+        for (int j = 0; j < p.n_groups; ++j)
+            if (order[i] >= p.groups[j].tap_begin && order[i] < p.groups[j].tap_begin + p.groups[j].tap_count) g = j;
+        WTap& w = P.taps[i];
+        w.aview = (int8_t)p.groups[g].out_view;
+        w.sz = (int8_t)-T.dz; w.sy = (int8_t)-T.dy; w.sx = (int8_t)-T.dx;
+        w.w = T.w;
+        w.bview = T.view;
+    }
+    // units and batches
+    const int per_batch = 512 / P.NTw;
+    memset(P.unit_taps, -1, sizeof(P.unit_taps));
+    int nu = 0, nb = 0;
+    if (P.stacked) {
+        int i = 0;
+        while (i < n) {
+            const int bv = P.taps[i].bview;
+            int first_unit = nu;
+            while (i < n && P.taps[i].bview == bv) {
+                if (nu >= WG_MAX_UNITS) { set_error("wgrad: too many units"); return 0; }
+                for (int j = 0; j < P.a_slabs && i < n && P.taps[i].bview == bv; ++j) P.unit_taps[nu][j] = (int8_t)i++;
+                nu++;
+            }
+            for (int u = first_unit; u < nu; u += per_batch) {
+                if (nb >= WG_MAX_BATCH) { set_error("wgrad: too many batches"); return 0; }
+                P.batches[nb].unit_begin = (int16_t)u;
+                P.batches[nb].unit_count = (int16_t)((nu - u) < per_batch ? (nu - u) : per_batch);
+                P.batches[nb].bview = (int16_t)bv;
+                nb++;
+            }
+        }
+    } else {
+        // unit index = tap * mslabs + mslab ; batches never straddle an X view
+        int i = 0;
+        while (i < n) {
+            const int bv = P.taps[i].bview;
+            int j = i;
+            while (j < n && P.taps[j].bview == bv) ++j;
+            for (int u = i * P.mslabs; u < j * P.mslabs; u += per_batch) {
+                if (nb >= WG_MAX_BATCH) { set_error("wgrad: too many batches (Cy=%d)", p.Cy); return 0; }
+                int cnt = j * P.mslabs - u;
+                P.batches[nb].unit_begin = (int16_t)u;
+                P.batches[nb].unit_count = (int16_t)(cnt < per_batch ? cnt : per_batch);
+                P.batches[nb].bview = (int16_t)bv;
+                nb++;
+            }
+            i = j;
+        }
+        nu = n * P.mslabs;
+    }
+    P.n_units = nu; P.n_batches = nb;
+
+    const int box[4] = {bn, bd, bh, bw};
+    for (int i = 0; i < p.n_out_views; ++i)
+        if (int e = encode_view_map(&P.a_maps[i], a->dy, p.out_views[i], p.Cy, P.slabW, box)) return e;
+    for (int i = 0; i < p.n_in_views; ++i)
+        if (int e = encode_view_map(&P.b_maps[i], a->x, p.in_views[i], p.Cx, P.nslabW, box)) return e;
+
+    long ktiles_upper = (long)P.Tn * P.Tz * P.Ty * P.Tx;
+    int base_jobs = nb * P.n_nchunks;
+    int ksplit = (2 * num_sms() + base_jobs - 1) / base_jobs;
+    if (ksplit > ktiles_upper) ksplit = (int)ktiles_upper;
+    if (ksplit < 1) ksplit = 1;
+    P.ksplit = ksplit;
+    size_t smem = (size_t)(WG_A_SLOTS + WG_B_SLOTS) * WG_SLOT_BYTES + 1024 + 256;
+    AMB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad_kernel<<<base_jobs * ksplit, 256, smem, (cudaStream_t)a->stream>>>(P);
+    AMB_LAUNCH_CHECK();
+    return 1;
+}
+
+}  // namespace amb

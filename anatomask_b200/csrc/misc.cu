@@ -1,0 +1,614 @@
+// Patch loss, hard-mask generation, EMA / AdamW over the flat parameter arena, weight packing, the Cin=1 stem and
+// the Cout=1 reconstruction head.  All HBM-bound: 128-bit accesses, warp-shuffle / shared-memory reductions.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace amb {
+
+static thread_local char g_err[512] = "";
+int g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// patch loss.  One CTA (256 threads) per 16³ patch; thread t owns the 16-float row (z = t/16, y = t%16).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v, float* sh) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+patch_loss_fwd_kernel(const float* __restrict__ inp, const float* __restrict__ rec, const uint8_t* __restrict__ active,
+                      int N, int D, int H, int W, int normalize, float* __restrict__ per_patch,
+                      float* __restrict__ loss, float* __restrict__ pstats, unsigned int* ticket) {
+    __shared__ float sh[8];
+    __shared__ bool is_last;
+    const int fd = D / 16, fh = H / 16, fw = W / 16, L = fd * fh * fw;
+    const int pid = blockIdx.x, n = pid / L, l = pid % L;
+    const int pz = l / (fh * fw), py = (l / fw) % fh, px = l % fw;
+    const bool masked = active[pid] == 0;
+    float l2 = 0.f, mean = 0.f, rstd = 1.f;
+    if (masked) {   // uniform per block
+        const int z = threadIdx.x >> 4, y = threadIdx.x & 15;
+        const long off = (((long)n * D + pz * 16 + z) * H + py * 16 + y) * W + px * 16;
+        float t[16], r[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 a = *reinterpret_cast<const float4*>(inp + off + j * 4);
+            float4 b = *reinterpret_cast<const float4*>(rec + off + j * 4);
+            t[j * 4] = a.x; t[j * 4 + 1] = a.y; t[j * 4 + 2] = a.z; t[j * 4 + 3] = a.w;
+            r[j * 4] = b.x; r[j * 4 + 1] = b.y; r[j * 4 + 2] = b.z; r[j * 4 + 3] = b.w;
+        }
+        if (normalize) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s += t[j];
+            mean = block_sum_256(s, sh) * (1.f / 4096.f);
+            float q = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) q += (t[j] - mean) * (t[j] - mean);
+            float var = block_sum_256(q, sh) * (1.f / 4095.f);          // unbiased (torch.var default)
+            rstd = 1.f / sqrtf(var + 1e-6f);
+        }
+        float e = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float d = r[j] - (t[j] - mean) * rstd;
+            e += d * d;
+        }
+        l2 = block_sum_256(e, sh) * (1.f / 4096.f);
+    }
+    if (threadIdx.x == 0) {
+        per_patch[pid] = l2;
+        if (pstats) { pstats[2 * pid] = mean; pstats[2 * pid + 1] = rstd; }
+        __threadfence();
+        unsigned int done = atomicAdd(ticket, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {      // deterministic final reduction by the last CTA
+        __threadfence();
+        const int total = N * L;
+        float s = 0.f, c = 0.f;
+        for (int i = threadIdx.x; i < total; i += 256) {
+            s += __ldcg(per_patch + i);
+            c += active[i] == 0 ? 1.f : 0.f;
+        }
+        s = block_sum_256(s, sh);
+        c = block_sum_256(c, sh);
+        if (threadIdx.x == 0) {
+            float denom = c + 1e-8f;
+            if (loss) loss[0] = s / denom;
+            if (pstats) pstats[2 * total] = denom;
+            *ticket = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+patch_loss_bwd_kernel(const float* __restrict__ inp, const float* __restrict__ rec, const uint8_t* __restrict__ active,
+                      const float* __restrict__ pstats, const float* __restrict__ dloss, int N, int D, int H, int W,
+                      float* __restrict__ drec) {
+    const int fd = D / 16, fh = H / 16, fw = W / 16, L = fd * fh * fw;
+    const int pid = blockIdx.x, n = pid / L, l = pid % L;
+    const int pz = l / (fh * fw), py = (l / fw) % fh, px = l % fw;
+    const int z = threadIdx.x >> 4, y = threadIdx.x & 15;
+    const long off = (((long)n * D + pz * 16 + z) * H + py * 16 + y) * W + px * 16;
+    if (active[pid] != 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(drec + off + j * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const float mean = pstats[2 * pid], rstd = pstats[2 * pid + 1];
+    const float k = dloss[0] * 2.f / (4096.f * pstats[2 * N * L]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float4 a = *reinterpret_cast<const float4*>(inp + off + j * 4);
+        float4 b = *reinterpret_cast<const float4*>(rec + off + j * 4);
+        float4 o;
+        o.x = k * (b.x - (a.x - mean) * rstd);
+        o.y = k * (b.y - (a.y - mean) * rstd);
+        o.z = k * (b.z - (a.z - mean) * rstd);
+        o.w = k * (b.w - (a.w - mean) * rstd);
+        *reinterpret_cast<float4*>(drec + off + j * 4) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// hard mask: one CTA per sample, in-smem bitonic sort of (key, index) pairs, L ≤ 1024
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pair_less(float ka, int ia, float kb, int ib) {
+    return ka < kb || (ka == kb && ia < ib);
+}
+
+__device__ void bitonic_sort(float* key, int* idx, int n) {   // n power of two, ascending
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int p = i ^ j;
+                if (p > i) {
+                    bool up = (i & k) == 0;
+                    bool lt = pair_less(key[p], idx[p], key[i], idx[i]);
+                    if (lt == up) {
+                        float tk = key[i]; key[i] = key[p]; key[p] = tk;
+                        int ti = idx[i]; idx[i] = idx[p]; idx[p] = ti;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(512)
+hard_mask_kernel(const float* __restrict__ loss_pred, int L, int Lp2, int len_loss, int len_keep,
+                 unsigned long long seed, unsigned long long offset, int* __restrict__ hard,
+                 uint8_t* __restrict__ mask_out) {
+    extern __shared__ unsigned char smraw[];
+    float* key = reinterpret_cast<float*>(smraw);
+    int* idx = reinterpret_cast<int*>(key + Lp2);
+    uint8_t* is_hard = reinterpret_cast<uint8_t*>(idx + Lp2);
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < Lp2; i += blockDim.x) {
+        key[i] = i < L ? loss_pred[(long)b * L + i] : __int_as_float(0x7f800000);
+        idx[i] = i;
+        if (i < L) is_hard[i] = 0;
+    }
+    bitonic_sort(key, idx, Lp2);
+    // hard set = the len_loss largest losses = sorted positions [L-len_loss, L)
+    for (int i = threadIdx.x; i < len_loss; i += blockDim.x) {
+        int id = idx[L - len_loss + i];
+        if (hard) hard[(long)b * len_loss + i] = id;
+        is_hard[id] = 1;
+    }
+    __syncthreads();
+    if (mask_out == nullptr) return;
+    // random fill: the len_keep smallest counter-based keys among the non-hard patches become visible
+    for (int i = threadIdx.x; i < Lp2; i += blockDim.x) {
+        float k = __int_as_float(0x7f800000);
+        if (i < L && !is_hard[i]) {
+            unsigned long long r = splitmix64(seed ^ splitmix64(offset + (unsigned long long)b * L + i));
+            k = (float)(r >> 40) * (1.0f / 16777216.0f);
+        }
+        key[i] = k;
+        idx[i] = i;
+    }
+    bitonic_sort(key, idx, Lp2);
+    for (int i = threadIdx.x; i < L; i += blockDim.x) mask_out[(long)b * L + i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < len_keep; i += blockDim.x) mask_out[(long)b * L + idx[i]] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// flat-arena EMA / AdamW / Σg²
+// ------------------------------------------------------------------------------------------------------------
+__global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ model, long n, float d, float omd) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long n4 = n >> 2;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 e = reinterpret_cast<float4*>(ema)[i];
+        float4 m = reinterpret_cast<const float4*>(model)[i];
+        // two separately rounded products then a rounded add — no FMA contraction (torch: ema*d + (1-d)*model)
+        e.x = __fadd_rn(__fmul_rn(e.x, d), __fmul_rn(omd, m.x));
+        e.y = __fadd_rn(__fmul_rn(e.y, d), __fmul_rn(omd, m.y));
+        e.z = __fadd_rn(__fmul_rn(e.z, d), __fmul_rn(omd, m.z));
+        e.w = __fadd_rn(__fmul_rn(e.w, d), __fmul_rn(omd, m.w));
+        reinterpret_cast<float4*>(ema)[i] = e;
+    }
+    for (long i = (n4 << 2) + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        ema[i] = __fadd_rn(__fmul_rn(ema[i], d), __fmul_rn(omd, model[i]));
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ g, long n, double* __restrict__ out) {
+    __shared__ double sh[32];
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long n4 = n >> 2;
+    float acc = 0.f;
+    double dacc = 0.0;
+    int cnt = 0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v = reinterpret_cast<const float4*>(g)[i];
+        acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        if (++cnt == 64) { dacc += acc; acc = 0.f; cnt = 0; }
+    }
+    for (long i = (n4 << 2) + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc += g[i] * g[i];
+    dacc += acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = dacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+        atomicAdd(out, t);
+    }
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float wd,
+                             float bc1, float bc2_sqrt, const double* __restrict__ gnorm_sq, float max_norm) {
+    float coef = 1.f;
+    if (gnorm_sq) {   // torch.nn.utils.clip_grad_norm_: coef = clamp(max_norm / (norm + 1e-6), max=1)
+        float norm = (float)sqrt(*gnorm_sq);
+        coef = fminf(max_norm / (norm + 1e-6f), 1.f);
+    }
+    const float step_size = lr / bc1;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float gi = g[i] * coef;
+        float pi = p[i] * (1.f - lr * wd);
+        float mi = m[i] + (gi - m[i]) * (1.f - b1);
+        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - step_size * (mi / denom);
+        m[i] = mi;
+        v[i] = vi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int T, int A, int B,
+                                   long st, long sa, long sb) {
+    const long total = (long)T * A * B;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int b = (int)(i % B);
+        long r = i / B;
+        int a = (int)(r % A);
+        int t = (int)(r / A);
+        dst[i] = __float2bfloat16(src[t * st + a * sa + b * sb]);
+    }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int T, int A, int B,
+                                    long st, long sa, long sb) {
+    const long total = (long)T * A * B;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int b = (int)(i % B);
+        long r = i / B;
+        int a = (int)(r % A);
+        int t = (int)(r / A);
+        dst[t * st + a * sa + b * sb] = src[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// stem: masked fp32 input (Cin = 1) → conv1 k3 (+b1) and conv3 k1 (+b3) at active voxels, bf16 channels-last out
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float masked_input(const Geo& g, const float* __restrict__ inp, int n, int z, int y, int x) {
+    if ((unsigned)z >= (unsigned)g.D || (unsigned)y >= (unsigned)g.H || (unsigned)x >= (unsigned)g.W) return 0.f;
+    if (!g.active[((n * g.fd + (z >> g.lgP)) * g.fh + (y >> g.lgP)) * g.fw + (x >> g.lgP)]) return 0.f;
+    return inp[(((long)n * g.D + z) * g.H + y) * g.W + x];
+}
+
+__global__ void __launch_bounds__(256)
+stem_fwd_kernel(Geo g, const float* __restrict__ inp, const float* __restrict__ w1, const float* __restrict__ b1,
+                const float* __restrict__ w3, const float* __restrict__ b3, bf16* __restrict__ out1,
+                bf16* __restrict__ out3) {
+    extern __shared__ float sw[];      // [27][C] w1 transposed, then b1[C], w3[C], b3[C]
+    const int C = g.C, CG = C / 8;
+    for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) sw[i] = w1[(i % C) * 27 + i / C];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        sw[27 * C + i] = b1[i];
+        sw[28 * C + i] = w3[i];
+        sw[29 * C + i] = b3[i];
+    }
+    __syncthreads();
+    const long runs = geo_num_runs(g);
+    const long total = (runs << g.lgP) * CG;
+    for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(item % CG);
+        const long t = item / CG;
+        const int v = (int)(t & (g.P - 1));
+        RunPos r = decode_run(g, t >> g.lgP);
+        const long voxel = r.voxel + v;
+        const int x = (int)(voxel % g.W);
+        const int y = (int)((voxel / g.W) % g.H);
+        const int z = (int)((voxel / ((long)g.W * g.H)) % g.D);
+        float acc[8], o3[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = sw[27 * C + cg * 8 + j];
+        float center = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 27; ++tap) {
+            const int dz = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
+            const float xv = masked_input(g, inp, r.n, z + dz, y + dy, x + dx);
+            if (tap == 13) center = xv;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, sw[tap * C + cg * 8 + j], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o3[j] = fmaf(center, sw[28 * C + cg * 8 + j], sw[29 * C + cg * 8 + j]);
+        *reinterpret_cast<bf16x8*>(out1 + voxel * C + cg * 8) = pack8(acc);
+        *reinterpret_cast<bf16x8*>(out3 + voxel * C + cg * 8) = pack8(o3);
+    }
+}
+
+// thread = (voxel lane, channel group, "slot"): slots 0..26 = conv1 taps, 27 = db1, 28 = dw3, 29 = db3
+__global__ void __launch_bounds__(1024)
+stem_wgrad_kernel(Geo g, const float* __restrict__ inp, const bf16* __restrict__ dy1, const bf16* __restrict__ dy3,
+                  float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw3, float* __restrict__ db3,
+                  int lanes) {
+    extern __shared__ float sacc[];    // [32][C]
+    const int C = g.C, CG = C / 8;
+    for (int i = threadIdx.x; i < 32 * C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    const int slot = threadIdx.x & 31;
+    const int cg = (threadIdx.x >> 5) % CG;
+    const int lane = (threadIdx.x >> 5) / CG;
+    const long nvox = geo_num_runs(g) << g.lgP;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (slot < 30) {
+        const int dz = slot < 27 ? slot / 9 - 1 : 0, dy = slot < 27 ? (slot / 3) % 3 - 1 : 0,
+                  dx = slot < 27 ? slot % 3 - 1 : 0;
+        for (long t = (long)blockIdx.x * lanes + lane; t < nvox; t += (long)gridDim.x * lanes) {
+            const int v = (int)(t & (g.P - 1));
+            RunPos r = decode_run(g, t >> g.lgP);
+            const long voxel = r.voxel + v;
+            const int x = (int)(voxel % g.W);
+            const int y = (int)((voxel / g.W) % g.H);
+            const int z = (int)((voxel / ((long)g.W * g.H)) % g.D);
+            float d[8];
+            unpack8(*reinterpret_cast<const bf16x8*>((slot >= 28 ? dy3 : dy1) + voxel * C + cg * 8), d);
+            float xv = 1.f;
+            if (slot < 27 || slot == 28) xv = masked_input(g, inp, r.n, z + dz, y + dy, x + dx);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(d[j], xv, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&sacc[slot * C + cg * 8 + j], acc[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 30 * C; i += blockDim.x) {
+        const int s = i / C, c = i % C;
+        const float v = sacc[i];
+        if (s < 27) atomicAdd(&dw1[c * 27 + s], v);
+        else if (s == 27) atomicAdd(&db1[c], v);
+        else if (s == 28) atomicAdd(&dw3[c], v);
+        else atomicAdd(&db3[c], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// reconstruction head (C → 1)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void proj_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                float* __restrict__ rec, long voxels, int C) {
+    extern __shared__ float sw[];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const float bias = b[0];
+    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < voxels; v += (long)gridDim.x * blockDim.x) {
+        float acc = bias;
+        for (int c = 0; c < C; c += 8) {
+            float f[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(x + v * C + c), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(f[j], sw[c + j], acc);
+        }
+        rec[v] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(512)
+proj_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ drec,
+                bf16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, long voxels, int C) {
+    extern __shared__ float sacc[];    // [C] + 1
+    const int CG = C / 8;
+    for (int i = threadIdx.x; i <= C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    const int cg = threadIdx.x % CG;
+    float wv[8], acc[8], accb = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { wv[j] = w[cg * 8 + j]; acc[j] = 0.f; }
+    const long total = voxels * CG;
+    for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += (long)gridDim.x * blockDim.x) {
+        const long v = item / CG;
+        const float d = drec[v];
+        float f[8], o[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(x + v * C + cg * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { o[j] = d * wv[j]; acc[j] = fmaf(d, f[j], acc[j]); }
+        *reinterpret_cast<bf16x8*>(dx + v * C + cg * 8) = pack8(o);
+        if (cg == 0) accb += d;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sacc[cg * 8 + j], acc[j]);
+    if (cg == 0) atomicAdd(&sacc[C], accb);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dw[i], sacc[i]);
+    if (threadIdx.x == 0) atomicAdd(db, sacc[C]);
+}
+
+static int grid_cap(long items, int block, int per_sm) {
+    long b = (items + block - 1) / block, cap = (long)num_sms() * per_sm;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+static int stem_geo(Geo& g, const uint8_t* active, const int* list, const int* count, int N, int D, int H, int W,
+                    int fd, int fh, int fw, int C) {
+    AMB_CHECK(C % 8 == 0 && C <= 256, AMB_ERR_ARG, "stem: C=%d must be a multiple of 8 and <= 256", C);
+    AMB_CHECK(active != nullptr, AMB_ERR_ARG, "stem: active mask required");
+    AMB_CHECK(D % fd == 0 && H / fh == D / fd && W / fw == D / fd && H % fh == 0 && W % fw == 0, AMB_ERR_ARG,
+              "stem: bad mask grid");
+    g.N = N; g.D = D; g.H = H; g.W = W; g.C = C;
+    g.P = D / fd; g.lgP = 0;
+    while ((1 << g.lgP) < g.P) g.lgP++;
+    AMB_CHECK((1 << g.lgP) == g.P, AMB_ERR_ARG, "stem: patch edge must be a power of two");
+    g.fd = fd; g.fh = fh; g.fw = fw;
+    g.list = list; g.count = count; g.active = active;
+    return 0;
+}
+
+}  // namespace amb
+
+using namespace amb;
+
+extern "C" const char* amb_last_error(void) { return g_err; }
+extern "C" int amb_version(void) { return AMB_VERSION; }
+extern "C" int amb_sm_arch(void) { return 100; }
+extern "C" long amb_launch_count(void) { return g_launch_count; }
+extern "C" void amb_reset_launch_count(void) { g_launch_count = 0; }
+
+extern "C" int amb_patch_loss_fwd(const float* inp, const float* rec, const uint8_t* active, int N, int D, int H,
+                                  int W, int normalize, float* per_patch, float* loss, float* patch_stats,
+                                  unsigned int* ticket, void* stream) {
+    AMB_CHECK(D % 16 == 0 && H % 16 == 0 && W % 16 == 0, AMB_ERR_ARG, "patch loss: dims must be multiples of 16");
+    AMB_CHECK(inp && rec && active && per_patch && ticket, AMB_ERR_ARG, "patch loss: null argument");
+    int L = (D / 16) * (H / 16) * (W / 16);
+    patch_loss_fwd_kernel<<<N * L, 256, 0, (cudaStream_t)stream>>>(inp, rec, active, N, D, H, W, normalize, per_patch,
+                                                                   loss, patch_stats, ticket);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_patch_loss_bwd(const float* inp, const float* rec, const uint8_t* active, const float* patch_stats,
+                                  const float* dloss, int N, int D, int H, int W, float* drec, void* stream) {
+    AMB_CHECK(D % 16 == 0 && H % 16 == 0 && W % 16 == 0, AMB_ERR_ARG, "patch loss: dims must be multiples of 16");
+    int L = (D / 16) * (H / 16) * (W / 16);
+    patch_loss_bwd_kernel<<<N * L, 256, 0, (cudaStream_t)stream>>>(inp, rec, active, patch_stats, dloss, N, D, H, W,
+                                                                   drec);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_hard_mask(const float* loss_pred, int B, int L, int len_loss, int len_keep,
+                             unsigned long long seed, unsigned long long offset, int* hard, uint8_t* mask_out,
+                             void* stream) {
+    AMB_CHECK(L >= 1 && L <= 4096, AMB_ERR_ARG, "hard mask: L=%d out of range (1..4096)", L);
+    AMB_CHECK(len_loss >= 0 && len_loss <= L && len_keep >= 0 && len_keep + len_loss <= L, AMB_ERR_ARG,
+              "hard mask: len_loss=%d len_keep=%d L=%d", len_loss, len_keep, L);
+    int Lp2 = 1;
+    while (Lp2 < L) Lp2 <<= 1;
+    size_t smem = (size_t)Lp2 * 8 + L;
+    hard_mask_kernel<<<B, 512, smem, (cudaStream_t)stream>>>(loss_pred, L, Lp2, len_loss, len_keep, seed, offset, hard,
+                                                             mask_out);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_ema_update(float* ema, const float* model, long n, double decay, void* stream) {
+    AMB_CHECK(((uintptr_t)ema % 16 == 0) && ((uintptr_t)model % 16 == 0), AMB_ERR_ARG, "ema: 16B alignment required");
+    ema_kernel<<<grid_cap(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(ema, model, n, (float)decay,
+                                                                              (float)(1.0 - decay));
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_sumsq(const float* g, long n, double* out, void* stream) {
+    AMB_CHECK((uintptr_t)g % 16 == 0, AMB_ERR_ARG, "sumsq: 16B alignment required");
+    sumsq_kernel<<<grid_cap(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(g, n, out);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_adamw_step(float* p, const float* g, float* m, float* v, long n, double lr, double beta1,
+                              double beta2, double eps, double weight_decay, int step, const double* gnorm_sq,
+                              double max_norm, void* stream) {
+    AMB_CHECK(step >= 1, AMB_ERR_ARG, "adamw: step must be >= 1");
+    double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
+    adamw_kernel<<<grid_cap(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)lr, (float)beta1,
+                                                                        (float)beta2, (float)eps, (float)weight_decay,
+                                                                        (float)bc1, (float)sqrt(bc2), gnorm_sq,
+                                                                        (float)max_norm);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_pack_weight(const float* src, void* dst, int T, int A, int B, long st, long sa, long sb,
+                               void* stream) {
+    pack_weight_kernel<<<grid_cap((long)T * A * B, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, T, A, B,
+                                                                                           st, sa, sb);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_unpack_wgrad(const float* src, float* dst, int T, int A, int B, long st, long sa, long sb,
+                                void* stream) {
+    unpack_wgrad_kernel<<<grid_cap((long)T * A * B, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, dst, T, A, B, st, sa,
+                                                                                            sb);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_stem_fwd(const float* inp, const uint8_t* active, const int* active_list, const int* active_count,
+                            int N, int D, int H, int W, int fd, int fh, int fw, int C, const float* w1,
+                            const float* b1, const float* w3, const float* b3, void* out1, void* out3, void* stream) {
+    Geo g;
+    if (int e = stem_geo(g, active, active_list, active_count, N, D, H, W, fd, fh, fw, C)) return e;
+    int block = (256 / (C / 8)) * (C / 8);
+    stem_fwd_kernel<<<grid_cap((long)N * D * H * W * (C / 8), block, 8), block, 30 * C * sizeof(float),
+                      (cudaStream_t)stream>>>(g, inp, w1, b1, w3, b3, (bf16*)out1, (bf16*)out3);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_stem_wgrad(const float* inp, const uint8_t* active, const int* active_list,
+                              const int* active_count, int N, int D, int H, int W, int fd, int fh, int fw, int C,
+                              const void* dy1, const void* dy3, float* dw1, float* db1, float* dw3, float* db3,
+                              void* stream) {
+    Geo g;
+    if (int e = stem_geo(g, active, active_list, active_count, N, D, H, W, fd, fh, fw, C)) return e;
+    int CG = C / 8;
+    int lanes = 1024 / (32 * CG);
+    AMB_CHECK(lanes >= 1, AMB_ERR_ARG, "stem wgrad: C=%d too large", C);
+    int block = lanes * 32 * CG;
+    stem_wgrad_kernel<<<num_sms() * 2, block, 32 * C * sizeof(float), (cudaStream_t)stream>>>(
+        g, inp, (const bf16*)dy1, (const bf16*)dy3, dw1, db1, dw3, db3, lanes);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_proj_fwd(const void* x, const float* w, const float* b, float* rec, long voxels, int C,
+                            void* stream) {
+    AMB_CHECK(C % 8 == 0, AMB_ERR_ARG, "proj: C must be a multiple of 8");
+    proj_fwd_kernel<<<grid_cap(voxels, 256, 8), 256, C * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, w, b,
+                                                                                               rec, voxels, C);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_proj_bwd(const void* x, const float* w, const float* drec, void* dx, float* dw, float* db,
+                            long voxels, int C, void* stream) {
+    AMB_CHECK(C % 8 == 0 && C / 8 <= 512, AMB_ERR_ARG, "proj: C must be a multiple of 8");
+    int CG = C / 8, block = (256 / CG) * CG;
+    if (block == 0) block = CG;
+    proj_bwd_kernel<<<grid_cap(voxels * CG, block, 4), block, (C + 1) * sizeof(float), (cudaStream_t)stream>>>(
+        (const bf16*)x, w, drec, (bf16*)dx, dw, db, voxels, C);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,452 @@
+// HBM-bound kernels: pooled masked norm / BatchNorm (stats, finalize, apply, backward), densify fill, skip add,
+// layout conversion and the active-patch work-list.  All activations bf16 channels-last, 128-bit accesses,
+// one item = 8 channels of one voxel.
+#include "common.cuh"
+
+namespace amb {
+
+static int make_geo(const amb_geo* a, Geo& g) {
+    AMB_CHECK(a != nullptr, AMB_ERR_ARG, "geo is null");
+    AMB_CHECK(a->C % 8 == 0 && a->C >= 8, AMB_ERR_ARG, "C=%d must be a multiple of 8", a->C);
+    AMB_CHECK(a->fd > 0 && a->D % a->fd == 0 && a->H % a->fh == 0 && a->W % a->fw == 0, AMB_ERR_ARG,
+              "dims (%d,%d,%d) not divisible by mask grid (%d,%d,%d)", a->D, a->H, a->W, a->fd, a->fh, a->fw);
+    int P = a->D / a->fd;
+    AMB_CHECK(a->H / a->fh == P && a->W / a->fw == P && (P & (P - 1)) == 0, AMB_ERR_ARG,
+              "patch edge must be a power of two and equal on all axes (got %d,%d,%d)", P, a->H / a->fh, a->W / a->fw);
+    g.N = a->N; g.D = a->D; g.H = a->H; g.W = a->W; g.C = a->C;
+    g.P = P; g.lgP = 0;
+    while ((1 << g.lgP) < P) g.lgP++;
+    g.fd = a->fd; g.fh = a->fh; g.fw = a->fw;
+    g.list = a->active_list; g.count = a->active_count; g.active = a->active;
+    AMB_CHECK((g.list == nullptr) == (g.count == nullptr), AMB_ERR_ARG, "active_list and active_count go together");
+    return 0;
+}
+
+static int pick_block(int CG) {
+    // block size: a multiple of the channel-group count so a thread keeps its channel group across the grid stride
+    AMB_CHECK(CG <= 512, AMB_ERR_ARG, "C=%d too large for the elementwise kernels (max 4096)", CG * 8);
+    int b = (256 / CG) * CG;
+    if (b == 0) b = CG;
+    return b;
+}
+
+// item → (voxel, channel-group); returns false when out of range
+struct Item {
+    long voxel;
+    int cg;
+    int patch;
+};
+
+__device__ __forceinline__ bool get_item(const Geo& g, long item, long total, int CG, Item& it) {
+    if (item >= total) return false;
+    it.cg = (int)(item % CG);
+    long t = item / CG;
+    if (g.list == nullptr) {       // dense: flat
+        it.voxel = t;
+        it.patch = -1;
+        return true;
+    }
+    int v = (int)(t & (g.P - 1));
+    RunPos r = decode_run(g, t >> g.lgP);
+    it.voxel = r.voxel + v;
+    it.patch = r.patch;
+    return true;
+}
+
+__device__ __forceinline__ long total_items(const Geo& g, int CG) {
+    if (g.list == nullptr) return (long)g.N * g.D * g.H * g.W * CG;
+    return (geo_num_runs(g) << g.lgP) * CG;
+}
+
+__device__ __forceinline__ float act_fwd(float u, int act) {
+    if (act == AMB_ACT_LRELU) return u > 0.f ? u : 0.01f * u;
+    if (act == AMB_ACT_RELU6) return fminf(fmaxf(u, 0.f), 6.f);
+    return u;
+}
+__device__ __forceinline__ float act_grad(float u, int act) {
+    if (act == AMB_ACT_LRELU) return u > 0.f ? 1.f : 0.01f;
+    if (act == AMB_ACT_RELU6) return (u > 0.f && u < 6.f) ? 1.f : 0.f;
+    return 1.f;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Σx, Σx² (mode 0)   |   Σg, Σg·x̂ (+ Σ_inactive dout → dtoken) (mode 1)
+// ------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(512) reduce_kernel(Geo g, const bf16* __restrict__ x, const bf16* __restrict__ dout,
+                                                     const bf16* __restrict__ res, const float* __restrict__ scale,
+                                                     const float* __restrict__ shift, const float* __restrict__ saved,
+                                                     int act, int fill, double* __restrict__ sums,
+                                                     double* __restrict__ dtoken) {
+    extern __shared__ double sacc[];          // [C][2] (+ [C] for dtoken)
+    const int CG = g.C / 8;
+    for (int i = threadIdx.x; i < g.C * 3; i += blockDim.x) sacc[i] = 0.0;
+    __syncthreads();
+    float a0[8], a1[8], a2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = a2[j] = 0.f;
+    Geo gd = g;
+    if (MODE == 1 && fill) gd.list = nullptr;            // densify backward visits every voxel
+    const long total = total_items(gd, CG);
+    const long stride = (long)gridDim.x * blockDim.x;
+    const int cg = threadIdx.x % CG;
+    float sc[8], sh[8], mu[8], rs[8];
+    if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j];
+            mu[j] = saved[cg * 8 + j]; rs[j] = saved[g.C + cg * 8 + j];
+        }
+    }
+    for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride) {
+        Item it;
+        get_item(gd, item, total, CG, it);
+        const long off = it.voxel * g.C + it.cg * 8;
+        if (MODE == 0) {
+            float f[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(x + off), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a0[j] += f[j]; a1[j] += f[j] * f[j]; }
+        } else {
+            float d[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(dout + off), d);
+            if (fill && !voxel_active(g, it.voxel)) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a2[j] += d[j];
+                continue;
+            }
+            float f[8], r[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(x + off), f);
+            if (res) unpack8(*reinterpret_cast<const bf16x8*>(res + off), r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float u = sc[j] * f[j] + sh[j] + (res ? r[j] : 0.f);
+                float gj = d[j] * act_grad(u, act);
+                a0[j] += gj;
+                a1[j] += gj * (f[j] - mu[j]) * rs[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sacc[(cg * 8 + j) * 2 + 0], (double)a0[j]);
+        atomicAdd(&sacc[(cg * 8 + j) * 2 + 1], (double)a1[j]);
+        if (MODE == 1 && fill) atomicAdd(&sacc[g.C * 2 + cg * 8 + j], (double)a2[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < g.C; i += blockDim.x) {
+        atomicAdd(&sums[i], sacc[i * 2]);
+        atomicAdd(&sums[g.C + i], sacc[i * 2 + 1]);
+        if (MODE == 1 && fill && dtoken) atomicAdd(&dtoken[i], sacc[g.C * 2 + i]);
+    }
+}
+
+__global__ void finalize_kernel(Geo g, const double* __restrict__ sums, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, float* __restrict__ scale,
+                                float* __restrict__ shift, float* __restrict__ saved, float* running_mean,
+                                float* running_var, long* nbt, float momentum) {
+    const double n = g.list ? (double)((long)(*g.count) << (3 * g.lgP)) : (double)g.N * g.D * g.H * g.W;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.C; c += gridDim.x * blockDim.x) {
+        double mean = sums[c] / n;
+        double var = sums[g.C + c] / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        float s = gamma[c] * rstd;
+        scale[c] = s;
+        shift[c] = beta[c] - (float)mean * s;
+        saved[c] = (float)mean;
+        saved[g.C + c] = rstd;
+        if (running_mean) {
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * n / (n - 1.0));
+        }
+    }
+    if (nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
+}
+
+__global__ void eval_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                            float* scale, float* shift, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) {
+        float s = gamma[c] * rsqrtf(rv[c] + eps);
+        scale[c] = s;
+        shift[c] = beta[c] - rm[c] * s;
+    }
+}
+
+__global__ void __launch_bounds__(512) apply_kernel(Geo g, const bf16* __restrict__ x, const float* __restrict__ scale,
+                                                    const float* __restrict__ shift, const bf16* __restrict__ res,
+                                                    const float* __restrict__ token, int act, bf16* __restrict__ out) {
+    const int CG = g.C / 8;
+    Geo gd = g;
+    if (token) gd.list = nullptr;
+    const long total = total_items(gd, CG);
+    const long stride = (long)gridDim.x * blockDim.x;
+    const int cg = threadIdx.x % CG;
+    float sc[8], sh[8], tk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j];
+        tk[j] = token ? token[cg * 8 + j] : 0.f;
+    }
+    for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride) {
+        Item it;
+        get_item(gd, item, total, CG, it);
+        const long off = it.voxel * g.C + it.cg * 8;
+        float o[8];
+        if (token && !voxel_active(g, it.voxel)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = tk[j];
+        } else {
+            float f[8], r[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(x + off), f);
+            if (res) unpack8(*reinterpret_cast<const bf16x8*>(res + off), r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = act_fwd(sc[j] * f[j] + sh[j] + (res ? r[j] : 0.f), act);
+        }
+        *reinterpret_cast<bf16x8*>(out + off) = pack8(o);
+    }
+}
+
+__global__ void __launch_bounds__(512)
+bwd_apply_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ x, const bf16* __restrict__ res,
+                 const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ saved,
+                 const double* __restrict__ sums, int act, int fill, bf16* __restrict__ dx, bf16* __restrict__ dres,
+                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int CG = g.C / 8;
+    const long total = total_items(g, CG);
+    const long stride = (long)gridDim.x * blockDim.x;
+    const int cg = threadIdx.x % CG;
+    const double n = g.list ? (double)((long)(*g.count) << (3 * g.lgP)) : (double)g.N * g.D * g.H * g.W;
+    float sc[8], sh[8], mu[8], rs[8], m1[8], m2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int c = cg * 8 + j;
+        sc[j] = scale[c]; sh[j] = shift[c]; mu[j] = saved[c]; rs[j] = saved[g.C + c];
+        m1[j] = (float)(sums[c] / n);
+        m2[j] = (float)(sums[g.C + c] / n);
+    }
+    if (blockIdx.x == 0 && dgamma) {
+        for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+            dbeta[c] = (float)sums[c];
+            dgamma[c] = (float)sums[g.C + c];
+        }
+    }
+    for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride) {
+        Item it;
+        get_item(g, item, total, CG, it);
+        const long off = it.voxel * g.C + it.cg * 8;
+        float d[8], f[8], r[8], o[8], gg[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(dout + off), d);
+        unpack8(*reinterpret_cast<const bf16x8*>(x + off), f);
+        if (res) unpack8(*reinterpret_cast<const bf16x8*>(res + off), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float u = sc[j] * f[j] + sh[j] + (res ? r[j] : 0.f);
+            gg[j] = d[j] * act_grad(u, act);
+            float xh = (f[j] - mu[j]) * rs[j];
+            o[j] = sc[j] * (gg[j] - m1[j] - xh * m2[j]);
+        }
+        *reinterpret_cast<bf16x8*>(dx + off) = pack8(o);
+        if (dres) *reinterpret_cast<bf16x8*>(dres + off) = pack8(gg);
+    }
+}
+
+__global__ void add_kernel(const bf16x8* __restrict__ a, const bf16x8* __restrict__ b, bf16x8* __restrict__ out,
+                           long n8) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        float fa[8], fb[8];
+        unpack8(a[i], fa);
+        unpack8(b[i], fb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fa[j] += fb[j];
+        out[i] = pack8(fa);
+    }
+}
+
+// NCDHW fp32 → NDHWC bf16 through a padded smem tile (coalesced on both sides)
+__global__ void to_ndhwc_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int C, long S) {
+    __shared__ float tile[32][33];
+    const long n = blockIdx.z;
+    const long s0 = (long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i;
+        long s = s0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && s < S) ? src[(n * C + c) * S + s] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        long s = s0 + i;
+        int c = c0 + threadIdx.x;
+        if (c < C && s < S) dst[(n * S + s) * C + c] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+}
+
+__global__ void to_ncdhw_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int C, long S) {
+    __shared__ float tile[32][33];
+    const long n = blockIdx.z;
+    const long s0 = (long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        long s = s0 + i;
+        int c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && s < S) ? bf2f(src[(n * S + s) * C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i;
+        long s = s0 + threadIdx.x;
+        if (c < C && s < S) dst[(n * C + c) * S + s] = tile[threadIdx.x][i];
+    }
+}
+
+// deterministic compaction of the (N·L) visibility bytes into an ascending list of active patch ids
+__global__ void active_list_kernel(const uint8_t* __restrict__ active, int n, int* __restrict__ list,
+                                   int* __restrict__ count) {
+    __shared__ int warp_tot[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int start = 0; start < n; start += blockDim.x) {
+        int i = start + threadIdx.x;
+        int a = (i < n) && active[i] != 0;
+        unsigned bal = __ballot_sync(0xffffffffu, a);
+        int pre = __popc(bal & ((1u << lane) - 1));
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+        if (a) list[base + woff + pre] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < nw; ++w) t += warp_tot[w];
+            base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
+static int grid_for(long work_items, int block) {
+    long b = (work_items + block - 1) / block;
+    long cap = (long)num_sms() * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+static long host_items_upper(const Geo& g) { return (long)g.N * g.D * g.H * g.W * (g.C / 8); }
+
+}  // namespace amb
+
+using namespace amb;
+
+extern "C" int amb_build_active_list(const uint8_t* active, int n_patches, int* list, int* count, void* stream) {
+    AMB_CHECK(active && list && count && n_patches > 0, AMB_ERR_ARG, "amb_build_active_list: null argument");
+    active_list_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(active, n_patches, list, count);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int N, int C, int D, int H, int W,
+                                           void* stream) {
+    long S = (long)D * H * W;
+    dim3 grid(ceil_div(S, 32), ceil_div(C, 32), N), block(32, 8);
+    to_ndhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, C, S);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int N, int C, int D, int H, int W,
+                                           void* stream) {
+    long S = (long)D * H * W;
+    dim3 grid(ceil_div(S, 32), ceil_div(C, 32), N), block(32, 8);
+    to_ncdhw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, C, S);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_norm_stats(const amb_geo* a, const void* x, double* sums, void* stream) {
+    Geo g;
+    if (int e = make_geo(a, g)) return e;
+    int CG = g.C / 8, block = pick_block(CG);
+    if (block < 0) return block;
+    reduce_kernel<0><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(double), (cudaStream_t)stream>>>(
+        g, (const bf16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, sums, nullptr);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_norm_finalize(const amb_geo* a, const double* sums, const float* gamma, const float* beta,
+                                 float eps, float* scale, float* shift, float* saved, float* running_mean,
+                                 float* running_var, long* nbt, float momentum, void* stream) {
+    Geo g;
+    if (int e = make_geo(a, g)) return e;
+    finalize_kernel<<<ceil_div(g.C, 128), 128, 0, (cudaStream_t)stream>>>(g, sums, gamma, beta, eps, scale, shift,
+                                                                          saved, running_mean, running_var, nbt,
+                                                                          momentum);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_norm_eval(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                             float* scale, float* shift, int C, void* stream) {
+    eval_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, rm, rv, eps, scale, shift, C);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_norm_apply(const amb_geo* a, const void* x, const float* scale, const float* shift,
+                              const void* residual, const float* token, int act, void* out, void* stream) {
+    Geo g;
+    if (int e = make_geo(a, g)) return e;
+    AMB_CHECK(!token || g.active, AMB_ERR_ARG, "densify fill needs the active mask");
+    int CG = g.C / 8, block = pick_block(CG);
+    if (block < 0) return block;
+    apply_kernel<<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(
+        g, (const bf16*)x, scale, shift, (const bf16*)residual, token, act, (bf16*)out);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_norm_bwd_reduce(const amb_geo* a, const void* dout, const void* x, const void* residual,
+                                   const float* scale, const float* shift, const float* saved, int act, int fill,
+                                   double* sums, double* dtoken, void* stream) {
+    Geo g;
+    if (int e = make_geo(a, g)) return e;
+    AMB_CHECK(!fill || g.active, AMB_ERR_ARG, "densify backward needs the active mask");
+    int CG = g.C / 8, block = pick_block(CG);
+    if (block < 0) return block;
+    reduce_kernel<1><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(double), (cudaStream_t)stream>>>(
+        g, (const bf16*)x, (const bf16*)dout, (const bf16*)residual, scale, shift, saved, act, fill, sums, dtoken);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_norm_bwd_apply(const amb_geo* a, const void* dout, const void* x, const void* residual,
+                                  const float* scale, const float* shift, const float* saved, const double* sums,
+                                  int act, int fill, void* dx, void* dres, float* dgamma, float* dbeta,
+                                  void* stream) {
+    Geo g;
+    if (int e = make_geo(a, g)) return e;
+    (void)fill;   // dx is only defined on visited (active) voxels; the caller zero-fills dx when the list is sparse
+    int CG = g.C / 8, block = pick_block(CG);
+    if (block < 0) return block;
+    bwd_apply_kernel<<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(
+        g, (const bf16*)dout, (const bf16*)x, (const bf16*)residual, scale, shift, saved, sums, act, fill, (bf16*)dx,
+        (bf16*)dres, dgamma, dbeta);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_add(const void* a, const void* b, void* out, long n, void* stream) {
+    AMB_CHECK(n % 8 == 0, AMB_ERR_ARG, "amb_add: n must be a multiple of 8");
+    add_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16x8*)a, (const bf16x8*)b,
+                                                                       (bf16x8*)out, n / 8);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,419 @@
+"""Autograd operators over the C ABI.  Internal activation format: bf16, shape (N, D, H, W, C), contiguous.
+
+Each Function enqueues hand-written sm_100a kernels on torch's current stream through ctypes; PyTorch only owns the
+memory (caching allocator), the streams and the autograd tape.  Nothing here synchronises the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+bf16 = torch.bfloat16
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def require_cuda(t: torch.Tensor):
+    if not t.is_cuda:
+        raise RuntimeError('anatomask_b200 runs on a B200 only: got a CPU tensor (there is no CPU fallback)')
+
+
+class MaskCtx:
+    """Per-forward visibility state: replaces the reference's `_cur_active` + `_get_active_ex_or_ii` (P/encoder3D.py:5-10).
+
+    active: (N, fd, fh, fw) uint8 on device; the active-patch work-list is built once on the device."""
+
+    def __init__(self, active_b1fff: torch.Tensor):
+        require_cuda(active_b1fff)
+        a = active_b1fff
+        if a.dim() == 5:
+            a = a[:, 0]
+        self.active = a.to(torch.uint8).contiguous()
+        self.N, self.fd, self.fh, self.fw = self.active.shape
+        n = self.active.numel()
+        self.list = torch.empty(n, dtype=torch.int32, device=a.device)
+        self.count = torch.empty(1, dtype=torch.int32, device=a.device)
+        L.call('amb_build_active_list', _p(self.active), n, _p(self.list), _p(self.count), _stream())
+
+    def geo(self, x: torch.Tensor, sparse: bool) -> L.Geo:
+        N, D, H, W, Cc = x.shape
+        return L.Geo(N, D, H, W, Cc, self.fd, self.fh, self.fw, self.active.data_ptr(),
+                     self.list.data_ptr() if sparse else 0, self.count.data_ptr() if sparse else 0)
+
+
+def dense_geo(x: torch.Tensor) -> L.Geo:
+    N, D, H, W, Cc = x.shape
+    # any mask grid that divides the tensor works for dense iteration; use one patch per voxel row block
+    return L.Geo(N, D, H, W, Cc, D, H, W, 0, 0, 0)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# layout conversion at the module boundary
+# ----------------------------------------------------------------------------------------------------------------
+def to_internal(x: torch.Tensor) -> torch.Tensor:
+    """(N,C,D,H,W) logical tensor → (N,D,H,W,C) bf16 contiguous.  Zero-copy for channels-last bf16 inputs."""
+    require_cuda(x)
+    xi = x.permute(0, 2, 3, 4, 1)
+    if x.dtype == bf16 and xi.is_contiguous():
+        return xi
+    return _ToInternal.apply(x)
+
+
+def to_external(xi: torch.Tensor) -> torch.Tensor:
+    """(N,D,H,W,C) → logical (N,C,D,H,W) view (channels_last_3d strides, bf16)."""
+    return xi.permute(0, 4, 1, 2, 3)
+
+
+class _ToInternal(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.float().contiguous()
+        N, Cc, D, H, W = x.shape
+        out = torch.empty((N, D, H, W, Cc), dtype=bf16, device=x.device)
+        L.call('amb_ncdhw_f32_to_ndhwc_bf16', _p(x), _p(out), N, Cc, D, H, W, _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        N, D, H, W, Cc = g.shape
+        out = torch.empty((N, Cc, D, H, W), dtype=torch.float32, device=g.device)
+        L.call('amb_ndhwc_bf16_to_ncdhw_f32', _p(g), _p(out), N, Cc, D, H, W, _stream())
+        return out
+
+
+def to_ncdhw_f32(xi: torch.Tensor) -> torch.Tensor:
+    xi = xi.contiguous()
+    N, D, H, W, Cc = xi.shape
+    out = torch.empty((N, Cc, D, H, W), dtype=torch.float32, device=xi.device)
+    L.call('amb_ndhwc_bf16_to_ncdhw_f32', _p(xi), _p(out), N, Cc, D, H, W, _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# convolutions
+# ----------------------------------------------------------------------------------------------------------------
+def _pack(w: torch.Tensor, T: int, A: int, B: int, st: int, sa: int, sb: int) -> torch.Tensor:
+    out = torch.empty((T, A, B), dtype=bf16, device=w.device)
+    L.call('amb_pack_weight', _p(w), _p(out), T, A, B, st, sa, sb, _stream())
+    return out
+
+
+def _conv_call(op, impl, dims, Cin, Cout, k, stride, x, y, w, bias=None, m: Optional[MaskCtx] = None, sparse=False,
+               stats=None):
+    N, D, H, W = dims
+    a = L.ConvArgs(op, impl, N, D, H, W, Cin, Cout, k, stride, x.data_ptr(), y.data_ptr(), w.data_ptr(),
+                   0 if bias is None else bias.data_ptr(), 0 if m is None else m.active.data_ptr(),
+                   1 if m is None else m.fd, 1 if m is None else m.fh, 1 if m is None else m.fw,
+                   m.list.data_ptr() if (m is not None and sparse) else 0,
+                   m.count.data_ptr() if (m is not None and sparse) else 0,
+                   0 if stats is None else stats.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    L.call('amb_conv', C.byref(a))
+
+
+def column_sums(x: torch.Tensor, m: Optional[MaskCtx]) -> torch.Tensor:
+    """Σ over voxels per channel (fp32) — bias gradients."""
+    Cc = x.shape[-1]
+    sums = torch.zeros(2 * Cc, dtype=torch.float64, device=x.device)
+    g = m.geo(x, True) if m is not None else dense_geo(x)
+    L.call('amb_norm_stats', C.byref(g), _p(x), _p(sums), _stream())
+    return sums[:Cc].float()
+
+
+class ConvFn(torch.autograd.Function):
+    """nn.Conv3d (k∈{1,3}, stride∈{1,2}, pad k//2) and nn.ConvTranspose3d (k4 s2 p1) on channels-last bf16.
+
+    With a MaskCtx the output is zero outside visible patches (SparseConv3d, P/encoder3D.py:12-15) and — where a
+    2×8×8 tile fits a patch — masked tiles are never computed."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, k, stride, m, transposed, impl):
+        require_cuda(x)
+        x = x.contiguous()
+        N, D, H, W, Cin = x.shape
+        k3 = k * k * k
+        if transposed:
+            Cout = weight.shape[1]
+            wp = _pack(weight, 64, Cout, Cin, 1, 64, Cout * 64)
+            y = torch.empty((N, 2 * D, 2 * H, 2 * W, Cout), dtype=bf16, device=x.device)
+            _conv_call(L.OP_CONVT, impl, (N, D, H, W), Cin, Cout, 4, 2, x, y, wp, bias)
+        else:
+            Cout = weight.shape[0]
+            wp = _pack(weight, k3, Cout, Cin, 1, Cin * k3, k3)
+            shape = (N, D // stride, H // stride, W // stride, Cout)
+            y = torch.zeros(shape, dtype=bf16, device=x.device) if m is not None else \
+                torch.empty(shape, dtype=bf16, device=x.device)
+            _conv_call(L.OP_CONV, impl, (N, D, H, W), Cin, Cout, k, stride, x, y, wp, bias, m, sparse=m is not None)
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (k, stride, m, transposed, impl, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        k, stride, m, transposed, impl, has_bias = ctx.cfg
+        dy = dy.contiguous()
+        N, D, H, W, Cin = x.shape
+        k3 = k * k * k
+        dx = dw = db = None
+        if transposed:
+            Cout = weight.shape[1]
+            if ctx.needs_input_grad[0]:
+                wp = _pack(weight, 64, Cin, Cout, 1, Cout * 64, 64)
+                dx = torch.empty_like(x)
+                _conv_call(L.OP_CONVT_DGRAD, impl, (N, D, H, W), Cin, Cout, 4, 2, dy, dx, wp)
+            if ctx.needs_input_grad[1]:
+                dwp = torch.zeros((64, Cout, Cin), dtype=torch.float32, device=x.device)
+                a = L.WgradArgs(L.OP_CONVT, impl, N, D, H, W, Cin, Cout, 4, 2, x.data_ptr(), dy.data_ptr(),
+                                dwp.data_ptr(), 1, 1, 1, 0, 0, torch.cuda.current_stream().cuda_stream)
+                L.call('amb_conv_wgrad', C.byref(a))
+                dw = torch.empty_like(weight)
+                L.call('amb_unpack_wgrad', _p(dwp), _p(dw), 64, Cout, Cin, 1, 64, Cout * 64, _stream())
+        else:
+            Cout = weight.shape[0]
+            if ctx.needs_input_grad[0]:
+                wp = _pack(weight, k3, Cin, Cout, 1, k3, Cin * k3)
+                need_zero = m is not None or (k == 1 and stride == 2)
+                dx = torch.zeros_like(x) if need_zero else torch.empty_like(x)
+                _conv_call(L.OP_CONV_DGRAD, impl, (N, D, H, W), Cin, Cout, k, stride, dy, dx, wp, None, m,
+                           sparse=m is not None)
+            if ctx.needs_input_grad[1]:
+                dwp = torch.zeros((k3, Cout, Cin), dtype=torch.float32, device=x.device)
+                a = L.WgradArgs(L.OP_CONV, impl, N, D, H, W, Cin, Cout, k, stride, x.data_ptr(), dy.data_ptr(),
+                                dwp.data_ptr(), 1 if m is None else m.fd, 1 if m is None else m.fh,
+                                1 if m is None else m.fw, 0 if m is None else m.list.data_ptr(),
+                                0 if m is None else m.count.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                L.call('amb_conv_wgrad', C.byref(a))
+                dw = torch.empty_like(weight)
+                L.call('amb_unpack_wgrad', _p(dwp), _p(dw), k3, Cout, Cin, 1, Cin * k3, k3, _stream())
+        if has_bias and ctx.needs_input_grad[2]:
+            db = column_sums(dy, m if not transposed else None)
+        return dx, dw, db, None, None, None, None, None
+
+
+def conv3d(x, weight, bias=None, k=3, stride=1, m: Optional[MaskCtx] = None, impl=L.IMPL_AUTO):
+    return ConvFn.apply(x, weight, bias, k, stride, m, False, impl)
+
+
+def conv_transpose3d(x, weight, bias=None, impl=L.IMPL_AUTO):
+    return ConvFn.apply(x, weight, bias, 4, 2, None, True, impl)
+
+
+class StemFn(torch.autograd.Function):
+    """Cin = 1 stage-0 pair: conv1 (k3) and the 1×1 shortcut conv3 on the masked fp32 input, one pass
+    (P/STUNet_head.py:96-101 with P/spark3D.py:104-107 folded in)."""
+
+    @staticmethod
+    def forward(ctx, inp, w1, b1, w3, b3, m: MaskCtx):
+        require_cuda(inp)
+        inp = inp.float().contiguous()
+        N, _, D, H, W = inp.shape
+        Cc = w1.shape[0]
+        out1 = torch.zeros((N, D, H, W, Cc), dtype=bf16, device=inp.device)
+        out3 = torch.zeros((N, D, H, W, Cc), dtype=bf16, device=inp.device)
+        L.call('amb_stem_fwd', _p(inp), _p(m.active), _p(m.list), _p(m.count), N, D, H, W, m.fd, m.fh, m.fw, Cc,
+               _p(w1), _p(b1), _p(w3), _p(b3), _p(out1), _p(out3), _stream())
+        ctx.save_for_backward(inp)
+        ctx.m, ctx.C = m, Cc
+        return out1, out3
+
+    @staticmethod
+    def backward(ctx, d1, d3):
+        (inp,) = ctx.saved_tensors
+        m, Cc = ctx.m, ctx.C
+        N, _, D, H, W = inp.shape
+        d1, d3 = d1.contiguous(), d3.contiguous()
+        g = torch.zeros(Cc * 30, dtype=torch.float32, device=inp.device)
+        dw1, db1, dw3, db3 = g[:Cc * 27], g[Cc * 27:Cc * 28], g[Cc * 28:Cc * 29], g[Cc * 29:]
+        L.call('amb_stem_wgrad', _p(inp), _p(m.active), _p(m.list), _p(m.count), N, D, H, W, m.fd, m.fh, m.fw, Cc,
+               _p(d1), _p(d3), _p(dw1), _p(db1), _p(dw3), _p(db3), _stream())
+        return None, dw1.view(Cc, 1, 3, 3, 3), db1, dw3.view(Cc, 1, 1, 1, 1), db3, None
+
+
+class ProjFn(torch.autograd.Function):
+    """Conv3d(C→1, k1, bias): (N,D,H,W,C) bf16 → rec fp32 (N,1,D,H,W)  (P/decoder3D.py:51,61)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = x.contiguous()
+        N, D, H, W, Cc = x.shape
+        rec = torch.empty((N, 1, D, H, W), dtype=torch.float32, device=x.device)
+        L.call('amb_proj_fwd', _p(x), _p(w), _p(b), _p(rec), N * D * H * W, Cc, _stream())
+        ctx.save_for_backward(x, w)
+        return rec
+
+    @staticmethod
+    def backward(ctx, drec):
+        x, w = ctx.saved_tensors
+        drec = drec.contiguous()
+        N, D, H, W, Cc = x.shape
+        dx = torch.empty_like(x)
+        g = torch.zeros(Cc + 1, dtype=torch.float32, device=x.device)
+        L.call('amb_proj_bwd', _p(x), _p(w), _p(drec), _p(dx), _p(g[:Cc]), _p(g[Cc:]), N * D * H * W, Cc, _stream())
+        return dx, g[:Cc].view_as(w), g[Cc:]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# pooled masked norm / BatchNorm / densify fill
+# ----------------------------------------------------------------------------------------------------------------
+class NormFn(torch.autograd.Function):
+    """y = act(γ·(x−μ)/√(σ²+eps) + β [+ residual]) with μ, σ² (biased) pooled over the visited voxels of the local batch.
+
+    m given, token None  : SparseInstanceNorm / SparseBatchNorm3d (P/encoder3D.py:17-25,149-158) — visible voxels only
+    m given, token given : densify — normalise visible voxels, fill masked ones with the mask token (P/spark3D.py:117-122)
+    m None               : nn.BatchNorm3d in training mode (decoder)
+    running = (rm, rv, nbt) updates the running statistics in place (momentum 0.1, unbiased variance)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, token, eps, act, m, running, momentum):
+        x = x.contiguous()
+        Cc = x.shape[-1]
+        dev = x.device
+        sparse = m is not None
+        g = m.geo(x, True) if sparse else dense_geo(x)
+        sums = torch.zeros(2 * Cc, dtype=torch.float64, device=dev)
+        L.call('amb_norm_stats', C.byref(g), _p(x), _p(sums), _stream())
+        ss = torch.empty(4 * Cc, dtype=torch.float32, device=dev)
+        scale, shift, saved = ss[:Cc], ss[Cc:2 * Cc], ss[2 * Cc:]
+        rm, rv, nbt = running if running is not None else (None, None, None)
+        L.call('amb_norm_finalize', C.byref(g), _p(sums), _p(gamma), _p(beta), eps, _p(scale), _p(shift), _p(saved),
+               _p(rm), _p(rv), _p(nbt), momentum, _stream())
+        fill = token is not None
+        out = torch.zeros_like(x) if (sparse and not fill) else torch.empty_like(x)
+        tok = token.reshape(-1).contiguous() if fill else None
+        if residual is not None:
+            residual = residual.contiguous()
+        L.call('amb_norm_apply', C.byref(g), _p(x), _p(scale), _p(shift), _p(residual), _p(tok), act, _p(out),
+               _stream())
+        ctx.save_for_backward(x, residual, ss)
+        ctx.cfg = (act, m, fill, token.shape if fill else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, residual, ss = ctx.saved_tensors
+        act, m, fill, tshape = ctx.cfg
+        dout = dout.contiguous()
+        Cc = x.shape[-1]
+        dev = x.device
+        sparse = m is not None
+        g = m.geo(x, True) if sparse else dense_geo(x)
+        scale, shift, saved = ss[:Cc], ss[Cc:2 * Cc], ss[2 * Cc:]
+        sums = torch.zeros(3 * Cc, dtype=torch.float64, device=dev)
+        L.call('amb_norm_bwd_reduce', C.byref(g), _p(dout), _p(x), _p(residual), _p(scale), _p(shift), _p(saved), act,
+               int(fill), _p(sums), _p(sums[2 * Cc:]) if fill else C.c_void_p(0), _stream())
+        dx = torch.zeros_like(x) if sparse else torch.empty_like(x)
+        dres = None
+        if residual is not None:
+            dres = torch.zeros_like(x) if sparse else torch.empty_like(x)
+        gb = torch.empty(2 * Cc, dtype=torch.float32, device=dev)
+        L.call('amb_norm_bwd_apply', C.byref(g), _p(dout), _p(x), _p(residual), _p(scale), _p(shift), _p(saved),
+               _p(sums), act, int(fill), _p(dx), _p(dres), _p(gb[:Cc]), _p(gb[Cc:]), _stream())
+        dtoken = sums[2 * Cc:].float().view(tshape) if fill else None
+        return dx, gb[:Cc], gb[Cc:], dres, dtoken, None, None, None, None, None
+
+
+def masked_norm(x, gamma, beta, eps, m: MaskCtx, act=L.ACT_NONE, residual=None):
+    return NormFn.apply(x, gamma, beta, residual, None, eps, act, m, None, 0.0)
+
+
+def densify_norm_fill(x, gamma, beta, token, eps, m: MaskCtx):
+    return NormFn.apply(x, gamma, beta, None, token, eps, L.ACT_NONE, m, None, 0.0)
+
+
+def batch_norm_train(x, gamma, beta, eps, act, running, momentum):
+    return NormFn.apply(x, gamma, beta, None, None, eps, act, None, running, momentum)
+
+
+def batch_norm_eval(x, gamma, beta, rm, rv, eps, act):
+    """Inference-mode BatchNorm (teacher forward, P/pretrain_AntoMask.py:422): running statistics, no grad."""
+    x = x.contiguous()
+    Cc = x.shape[-1]
+    ss = torch.empty(2 * Cc, dtype=torch.float32, device=x.device)
+    L.call('amb_norm_eval', _p(gamma), _p(beta), _p(rm), _p(rv), eps, _p(ss[:Cc]), _p(ss[Cc:]), Cc, _stream())
+    out = torch.empty_like(x)
+    g = dense_geo(x)
+    L.call('amb_norm_apply', C.byref(g), _p(x), _p(ss[:Cc]), _p(ss[Cc:]), C.c_void_p(0), C.c_void_p(0), act, _p(out),
+           _stream())
+    return out
+
+
+class AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        out = torch.empty_like(a)
+        L.call('amb_add', _p(a), _p(b), _p(out), a.numel(), _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# loss / hard mask / arena optimiser pieces
+# ----------------------------------------------------------------------------------------------------------------
+class PatchLossFn(torch.autograd.Function):
+    """patchify + per-patch normalised masked MSE (P/spark3D.py:130-138).  Returns (loss, per_patch (N,L))."""
+
+    @staticmethod
+    def forward(ctx, inp, rec, active_u8, normalize):
+        inp, rec = inp.float().contiguous(), rec.float().contiguous()
+        N, _, D, H, W = inp.shape
+        Lp = (D // 16) * (H // 16) * (W // 16)
+        dev = inp.device
+        per_patch = torch.empty((N, Lp), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        pstats = torch.empty(2 * N * Lp + 1, dtype=torch.float32, device=dev)
+        ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.call('amb_patch_loss_fwd', _p(inp), _p(rec), _p(active_u8), N, D, H, W, int(normalize), _p(per_patch),
+               _p(loss), _p(pstats), _p(ticket), _stream())
+        ctx.save_for_backward(inp, rec, active_u8, pstats)
+        ctx.mark_non_differentiable(per_patch)
+        return loss, per_patch
+
+    @staticmethod
+    def backward(ctx, dloss, _dpp):
+        inp, rec, active_u8, pstats = ctx.saved_tensors
+        N, _, D, H, W = inp.shape
+        drec = torch.empty_like(rec)
+        dl = dloss.float().contiguous()
+        L.call('amb_patch_loss_bwd', _p(inp), _p(rec), _p(active_u8), _p(pstats), _p(dl), N, D, H, W, _p(drec),
+               _stream())
+        return None, drec, None, None
+
+
+def hard_mask(loss_pred: torch.Tensor, len_loss: int, len_keep: int, seed: int = 0, offset: int = 0,
+              want_mask: bool = True):
+    """Returns (hard indices (B,len_loss) int32 in ascending-loss order, mask (B,L) uint8 or None)."""
+    loss_pred = loss_pred.float().contiguous()
+    B, Lp = loss_pred.shape
+    hard = torch.empty((B, max(len_loss, 1)), dtype=torch.int32, device=loss_pred.device)
+    mask = torch.empty((B, Lp), dtype=torch.uint8, device=loss_pred.device) if want_mask else None
+    L.call('amb_hard_mask', _p(loss_pred), B, Lp, len_loss, len_keep, seed, offset, _p(hard), _p(mask), _stream())
+    return hard[:, :len_loss], mask
+
+
+def ema_update_(ema_flat: torch.Tensor, model_flat: torch.Tensor, decay: float):
+    L.call('amb_ema_update', _p(ema_flat), _p(model_flat), ema_flat.numel(), float(decay), _stream())
+
+
+def adamw_step_(p, g, m, v, lr, betas, eps, wd, step, max_norm: Optional[float]):
+    gn = None
+    if max_norm is not None:
+        gn = torch.zeros(1, dtype=torch.float64, device=p.device)
+        L.call('amb_sumsq', _p(g), g.numel(), _p(gn), _stream())
+    L.call('amb_adamw_step', _p(p), _p(g), _p(m), _p(v), p.numel(), lr, betas[0], betas[1], eps, wd, step, _p(gn),
+           0.0 if max_norm is None else float(max_norm), _stream())
+    return gn

@@ -1,0 +1,195 @@
+/*
+ * libanatomask_b200 — C ABI of the B200-native (sm_100a) kernels behind AnatoMask's SparK-style masked 3-D ConvNet
+ * pre-training step.  This is the drop-in boundary: plain pointers, sizes and a CUDA stream; no torch types.
+ *
+ * The reference (ricklisz/AnatoMask) has no native layer of its own — every entry point below replaces a
+ * PyTorch library call site of the reference's Python modules (P = nnunetv2/training/nnUNetTrainer/variants/
+ * pretrain).  The reference-side binding is a ctypes stub; the shipped host mirror is
+ * anatomask_b200/{encoder3D,STUNet_head,decoder3D,spark3D,AnatoMask}.py.
+ *
+ * Conventions
+ *   - activations: bf16, channels-last (N, D, H, W, C), C % 8 == 0 (tensor-core paths: C % 16 == 0)
+ *   - packed conv weights: bf16 [tap][rows][cols] with `cols` (the contraction channel) contiguous
+ *   - `active`: uint8 (N, fd, fh, fw), 1 = visible patch; the patch edge at a given resolution is D / fd
+ *   - `active_list` / `active_count`: device work-list of active patch ids (n*L + l) built by
+ *     amb_build_active_list — no host synchronisation anywhere on the step path
+ *   - every function returns 0 on success or a negative AMB_ERR_* code; amb_last_error() gives the message.
+ *     Unsupported shapes fail loudly — there is no CPU fallback and no other-arch dispatch.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises the host.
+ */
+#ifndef ANATOMASK_B200_H
+#define ANATOMASK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMB_VERSION 100
+
+#define AMB_OK 0
+#define AMB_ERR_ARG (-1)       /* bad argument / unsupported shape */
+#define AMB_ERR_CUDA (-2)      /* CUDA runtime / driver error      */
+#define AMB_ERR_UNSUPPORTED (-3)
+
+/* activation codes for the fused normalise-apply kernels */
+#define AMB_ACT_NONE 0
+#define AMB_ACT_LRELU 1        /* LeakyReLU(0.01)  — P/STUNet_head.py:84,89 */
+#define AMB_ACT_RELU6 2        /* ReLU6            — P/decoder3D.py:21      */
+
+/* convolution operators (all stride/padding variants the path uses) */
+#define AMB_OP_CONV 0          /* nn.Conv3d k∈{1,3}, stride∈{1,2}, pad k/2      — P/encoder3D.py:13, P/decoder3D.py:21-22, P/spark3D.py:82 */
+#define AMB_OP_CONV_DGRAD 1    /* its input gradient                                                               */
+#define AMB_OP_CONVT 2         /* nn.ConvTranspose3d k4 s2 p1                   — P/decoder3D.py:19                */
+#define AMB_OP_CONVT_DGRAD 3   /* its input gradient                                                               */
+
+#define AMB_IMPL_AUTO 0        /* tcgen05 implicit GEMM when the shape allows it, CUDA-core gather kernel otherwise */
+#define AMB_IMPL_DIRECT 1      /* force the CUDA-core gather kernel (differential testing)                          */
+#define AMB_IMPL_TCGEN05 2     /* force the tcgen05 kernel, error when the shape is unsupported                     */
+
+const char* amb_last_error(void);
+int amb_version(void);
+int amb_sm_arch(void);                 /* 100: the only architecture this library is built for */
+long amb_launch_count(void);           /* kernels launched by this library since the last reset */
+void amb_reset_launch_count(void);
+
+/* ---- work-list: replaces `_get_active_ex_or_ii(...).nonzero()` (host sync) — P/encoder3D.py:7-10 ------------- */
+int amb_build_active_list(const uint8_t* active, int n_patches, int* list, int* count, void* stream);
+
+/* ---- layout / dtype conversion at the module boundary (reference tensors are NCDHW fp32) ---------------------- */
+int amb_ncdhw_f32_to_ndhwc_bf16(const float* src, void* dst, int N, int C, int D, int H, int W, void* stream);
+int amb_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int N, int C, int D, int H, int W, void* stream);
+
+/* ---- weight packing: dst[t][a][b] (bf16) = src[t*st + a*sa + b*sb] (fp32); and the inverse for weight grads ---- */
+int amb_pack_weight(const float* src, void* dst, int T, int A, int B, long st, long sa, long sb, void* stream);
+int amb_unpack_wgrad(const float* src, float* dst, int T, int A, int B, long st, long sa, long sb, void* stream);
+
+/* ---- convolutions ---------------------------------------------------------------------------------------------
+ * (N, D, H, W) are the dims of the FINE-resolution tensor of the operator: the input of CONV (output is /stride),
+ * the OUTPUT of CONV_DGRAD, the input of CONVT (output is ×2) and the output of CONVT_DGRAD is (N,D,H,W) too.
+ *   CONV        x (N,D,H,W,Cin)          → y (N,D/s,H/s,W/s,Cout)      w [k³][Cout][Cin]
+ *   CONV_DGRAD  x=dy (N,D/s,..,Cout)     → y=dx (N,D,H,W,Cin)          w [k³][Cin][Cout]
+ *   CONVT       x (N,D,H,W,Cin)          → y (N,2D,2H,2W,Cout)         w [64][Cout][Cin]
+ *   CONVT_DGRAD x=dy (N,2D,2H,2W,Cout)   → y=dx (N,D,H,W,Cin)          w [64][Cin][Cout]
+ * Optional epilogue: + bias[rows]; zero the outputs of inactive patches (`active`, mask grid fd×fh×fw at the
+ * OUTPUT resolution); with `active_list` only the output tiles inside active patches are computed at all
+ * (the output buffer must have been zeroed once — inactive voxels are never written).
+ * `stats` (optional, double[2*rows], accumulated) receives Σy and Σy² per output channel over the written
+ * (active) outputs — the producer-side half of SparseInstanceNorm / BatchNorm (P/encoder3D.py:149-158).       */
+typedef struct amb_conv_args {
+    int op, impl;
+    int N, D, H, W;
+    int Cin, Cout;              /* channels of x and y as named in the table above (contraction = channels of x) */
+    int k, stride;
+    const void* x;
+    void* y;
+    const void* w;
+    const float* bias;
+    const uint8_t* active;
+    int fd, fh, fw;
+    const int* active_list;
+    const int* active_count;
+    double* stats;
+    void* stream;
+} amb_conv_args;
+int amb_conv(const amb_conv_args* a);
+
+/* weight gradient of CONV / CONVT: dw [taps][Cout][Cin] fp32 (accumulated into, caller zeroes), from the
+ * operator's input x and output gradient dy, dims as in the table above.  With `active_list` only active
+ * patches of dy (OUTPUT resolution) are visited (dy is zero elsewhere).                                      */
+typedef struct amb_wgrad_args {
+    int op, impl;               /* op: AMB_OP_CONV or AMB_OP_CONVT */
+    int N, D, H, W;
+    int Cin, Cout;
+    int k, stride;
+    const void* x;
+    const void* dy;
+    float* dw;
+    int fd, fh, fw;
+    const int* active_list;
+    const int* active_count;
+    void* stream;
+} amb_wgrad_args;
+int amb_conv_wgrad(const amb_wgrad_args* a);
+
+/* ---- encoder stem (Cin = 1): masked input → conv1 (k3) and conv3 (k1) in one pass — P/STUNet_head.py:96-101 ---- */
+int amb_stem_fwd(const float* inp, const uint8_t* active, const int* active_list, const int* active_count,
+                 int N, int D, int H, int W, int fd, int fh, int fw, int C,
+                 const float* w1, const float* b1, const float* w3, const float* b3,
+                 void* out1, void* out3, void* stream);
+/* weight/bias grads of the stem: dw1[C][27], db1[C], dw3[C], db3[C] (fp32, accumulated into) */
+int amb_stem_wgrad(const float* inp, const uint8_t* active, const int* active_list, const int* active_count,
+                   int N, int D, int H, int W, int fd, int fh, int fw, int C,
+                   const void* dy1, const void* dy3, float* dw1, float* db1, float* dw3, float* db3, void* stream);
+
+/* ---- reconstruction head: Conv3d(C → 1, k1, bias) — P/decoder3D.py:51,61 -------------------------------------- */
+int amb_proj_fwd(const void* x, const float* w, const float* b, float* rec, long voxels, int C, void* stream);
+int amb_proj_bwd(const void* x, const float* w, const float* drec, void* dx, float* dw, float* db,
+                 long voxels, int C, void* stream);
+
+/* ---- pooled masked norm / BatchNorm (one formula: P/encoder3D.py:17-25,149-158; nn.BatchNorm3d) ---------------
+ * Tensor (N, D, H, W, C) with mask grid (fd,fh,fw); `active_list == NULL` → dense (all voxels).
+ *   stats     : sums[2C] (double, accumulated) += Σx, Σx² over the visited voxels
+ *   finalize  : mean/biased var from sums and n = visited voxels (count·P³ read on device, or N·D·H·W),
+ *               scale = γ/√(var+eps), shift = β − mean·scale, saved[2C] = (mean, rstd);
+ *               optional running stats update (momentum, unbiased var) and num_batches_tracked += 1
+ *   eval      : scale/shift from running stats (teacher forward)
+ *   apply     : out = act(scale·x + shift [+ residual]) on visited voxels; with `token` != NULL the tensor is
+ *               densified instead: inactive voxels get token[c] (P/spark3D.py:119-122), no activation
+ *   bwd_reduce: sums[2C] += Σg, Σg·x̂ with g = dout·act'(scale·x+shift[+res]); dtoken[C] += Σ_inactive dout
+ *   bwd_apply : dx = scale·(g − Σg/n − x̂·Σ(g·x̂)/n); dres = g (optional); dgamma = Σg·x̂, dbeta = Σg (finalized)
+ */
+typedef struct amb_geo {
+    int N, D, H, W, C;
+    int fd, fh, fw;
+    const uint8_t* active;
+    const int* active_list;
+    const int* active_count;
+} amb_geo;
+int amb_norm_stats(const amb_geo* g, const void* x, double* sums, void* stream);
+int amb_norm_finalize(const amb_geo* g, const double* sums, const float* gamma, const float* beta, float eps,
+                      float* scale, float* shift, float* saved, float* running_mean, float* running_var,
+                      long* num_batches_tracked, float momentum, void* stream);
+int amb_norm_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                  float eps, float* scale, float* shift, int C, void* stream);
+int amb_norm_apply(const amb_geo* g, const void* x, const float* scale, const float* shift, const void* residual,
+                   const float* token, int act, void* out, void* stream);
+int amb_norm_bwd_reduce(const amb_geo* g, const void* dout, const void* x, const void* residual,
+                        const float* scale, const float* shift, const float* saved, int act, int fill,
+                        double* sums, double* dtoken, void* stream);
+int amb_norm_bwd_apply(const amb_geo* g, const void* dout, const void* x, const void* residual,
+                       const float* scale, const float* shift, const float* saved, const double* sums, int act,
+                       int fill, void* dx, void* dres, float* dgamma, float* dbeta, void* stream);
+/* plain elementwise add (decoder skip: x + to_dec[i], P/decoder3D.py:58): out = a + b, n bf16 elements */
+int amb_add(const void* a, const void* b, void* out, long n, void* stream);
+
+/* ---- patchify + per-patch (optionally mean/var-normalised) masked MSE — P/spark3D.py:130-138,
+ *      P/AnatoMask.py:190-202, teacher score P/pretrain_AntoMask.py:423-425 ------------------------------------
+ * inp, rec: fp32 (N,1,D,H,W); patch p=16.  per_patch[N*L] = mean_n (rec − tgt)² · nonactive;
+ * loss[0] = Σ per_patch / (Σ nonactive + 1e-8) (written by the last block; no host sync).
+ * bwd: drec = dloss · 2 (rec − tgt) / (p³ · (Σnonactive + 1e-8)) on masked patches, 0 on active ones.        */
+int amb_patch_loss_fwd(const float* inp, const float* rec, const uint8_t* active, int N, int D, int H, int W,
+                       int normalize, float* per_patch, float* loss, float* patch_stats, unsigned int* ticket,
+                       void* stream);
+int amb_patch_loss_bwd(const float* inp, const float* rec, const uint8_t* active, const float* patch_stats,
+                       const float* dloss, int N, int D, int H, int W, float* drec, void* stream);
+
+/* ---- AnatoMask hard-mask generation — P/AnatoMask.py:81-135 ----------------------------------------------------
+ * loss_pred (B, L) fp32.  hard[b, :len_loss] = indices of the len_loss largest losses (ascending loss order,
+ * i.e. exactly argsort(loss)[L-len_loss:]) — bit-exact in the selected set.
+ * mask_out (B, L) uint8: len_keep visible patches drawn uniformly from the non-hard ones with a counter-based
+ * device RNG (seed, offset) — "throughput mode"; parity mode replays numpy's shuffle on the host from `hard`.  */
+int amb_hard_mask(const float* loss_pred, int B, int L, int len_loss, int len_keep, unsigned long long seed,
+                  unsigned long long offset, int* hard, uint8_t* mask_out, void* stream);
+
+/* ---- flat-arena optimiser pieces: EMA teacher (timm ModelEma.update), grad-norm clip + AdamW ------------------- */
+int amb_ema_update(float* ema, const float* model, long n, double decay, void* stream);   /* ema = ema*d + (1-d)*model, fp32 products rounded separately like torch */
+int amb_sumsq(const float* g, long n, double* out, void* stream);                 /* out[0] += Σ g² */
+int amb_adamw_step(float* p, const float* g, float* m, float* v, long n, double lr, double beta1, double beta2,
+                   double eps, double weight_decay, int step, const double* gnorm_sq, double max_norm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANATOMASK_B200_H */

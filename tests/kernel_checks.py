@@ -1,0 +1,353 @@
+"""Per-kernel parity checks (CUDA path through the C ABI vs fp32 torch / the oracle on identical bf16-rounded inputs).
+
+Used by tests/test_kernels_gpu.py (pytest -m gpu) and by tests/gpu_bringup.py, which runs every check in its own
+process so that one trapped kernel cannot poison the rest.   CLI:  python -m tests.kernel_checks <check> [json-kwargs]
+"""
+from __future__ import annotations
+
+import json
+import sys
+
+import torch
+import torch.nn.functional as F
+
+bf16 = torch.bfloat16
+
+
+def _dev():
+    assert torch.cuda.is_available(), 'GPU checks need a B200'
+    return torch.device('cuda:0')
+
+
+def _rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _maxerr(a, b) -> float:
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _rand_mask(N, f, keep=0.4, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    Lp = f ** 3
+    k = max(1, round(Lp * keep))
+    idx = torch.rand(N, Lp, generator=g).argsort(1)[:, :k]
+    m = torch.zeros(N, Lp, dtype=torch.bool).scatter_(1, idx, True)
+    return m.view(N, 1, f, f, f)
+
+
+def _up(mask, size):
+    r = size // mask.shape[-1]
+    return mask.repeat_interleave(r, 2).repeat_interleave(r, 3).repeat_interleave(r, 4)
+
+
+def check_conv(Cin=64, Cout=64, k=3, stride=1, S=16, N=2, impl=2, masked=False, f=2, bias=True, seed=0, tol=1.5e-2):
+    """conv fwd + dgrad + wgrad (+bias grad) vs fp32 torch on the same bf16-rounded operands."""
+    from anatomask_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, Cin, S, S, S, generator=g).to(bf16)
+    w = (torch.randn(Cout, Cin, k, k, k, generator=g) / (Cin * k ** 3) ** 0.5)
+    b = torch.randn(Cout, generator=g) * 0.1 if bias else None
+    mask = _rand_mask(N, f, seed=seed + 1) if masked else None
+    if masked:
+        x = x * _up(mask, S).to(bf16)
+    wq = w.to(bf16).float()
+    xr = x.float().to(dev).requires_grad_(True)
+    wr = wq.to(dev).requires_grad_(True)
+    br = b.to(dev).requires_grad_(True) if bias else None
+    yr = F.conv3d(xr, wr, br, stride=stride, padding=k // 2)
+    if masked:
+        yr = yr * _up(mask, S // stride).to(dev)
+    gy = torch.randn(yr.shape, generator=g).to(bf16)
+    if masked:
+        gy = gy * _up(mask, S // stride).to(bf16)
+    yr.backward(gy.float().to(dev))
+
+    xi = x.to(dev).permute(0, 2, 3, 4, 1).contiguous().requires_grad_(True)
+    wp = wq.to(dev).requires_grad_(True)
+    bp = b.to(dev).requires_grad_(True) if bias else None
+    m = ops.MaskCtx(mask.to(dev)) if masked else None
+    y = ops.conv3d(xi, wp, bp, k, stride, m, impl)
+    y.backward(gy.to(dev).permute(0, 2, 3, 4, 1).contiguous())
+    torch.cuda.synchronize()
+    res = {'fwd': _rel(y.permute(0, 4, 1, 2, 3), yr.detach()), 'wgrad': _rel(wp.grad, wr.grad)}
+    dx, dxr = xi.grad.permute(0, 4, 1, 2, 3).float(), xr.grad
+    if masked:      # only the visible voxels of dx are consumed downstream
+        mm = _up(mask, S).to(dev)
+        dx, dxr = dx * mm, dxr * mm
+    res['dgrad'] = _rel(dx, dxr)
+    if bias:
+        res['bgrad'] = _rel(bp.grad, br.grad)
+    bad = {k_: v for k_, v in res.items() if not (v < tol)}
+    assert not bad, f'conv Cin={Cin} Cout={Cout} k={k} s={stride} S={S} impl={impl} masked={masked}: {res}'
+    return res
+
+
+def check_convT(Cin=64, Cout=64, S=8, N=2, impl=2, seed=0, tol=1.5e-2):
+    from anatomask_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, Cin, S, S, S, generator=g).to(bf16)
+    w = (torch.randn(Cin, Cout, 4, 4, 4, generator=g) / (Cin * 8) ** 0.5).to(bf16).float()
+    b = torch.randn(Cout, generator=g) * 0.1
+    xr = x.float().to(dev).requires_grad_(True)
+    wr = w.to(dev).requires_grad_(True)
+    br = b.to(dev).requires_grad_(True)
+    yr = F.conv_transpose3d(xr, wr, br, stride=2, padding=1)
+    gy = torch.randn(yr.shape, generator=g).to(bf16)
+    yr.backward(gy.float().to(dev))
+    xi = x.to(dev).permute(0, 2, 3, 4, 1).contiguous().requires_grad_(True)
+    wp = w.to(dev).requires_grad_(True)
+    bp = b.to(dev).requires_grad_(True)
+    y = ops.conv_transpose3d(xi, wp, bp, impl)
+    y.backward(gy.to(dev).permute(0, 2, 3, 4, 1).contiguous())
+    torch.cuda.synchronize()
+    res = {'fwd': _rel(y.permute(0, 4, 1, 2, 3), yr.detach()), 'dgrad': _rel(xi.grad.permute(0, 4, 1, 2, 3), xr.grad),
+           'wgrad': _rel(wp.grad, wr.grad), 'bgrad': _rel(bp.grad, br.grad)}
+    bad = {k_: v for k_, v in res.items() if not (v < tol)}
+    assert not bad, f'convT Cin={Cin} Cout={Cout} S={S} impl={impl}: {res}'
+    return res
+
+
+def check_conv_stats(Cin=32, Cout=64, S=16, N=2, seed=0):
+    """fused Σy / Σy² epilogue of the tcgen05 kernel vs sums over its own bf16 output's fp32 source."""
+    import ctypes as C
+    from anatomask_b200 import ops, _lib as L
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, S, S, S, Cin, generator=g).to(bf16).to(dev)
+    w = (torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (Cin * 27) ** 0.5).to(dev)
+    wp = ops._pack(w, 27, Cout, Cin, 1, Cin * 27, 27)
+    y = torch.empty(N, S, S, S, Cout, dtype=bf16, device=dev)
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
+    ops._conv_call(L.OP_CONV, L.IMPL_TCGEN05, (N, S, S, S), Cin, Cout, 3, 1, x, y, wp, stats=stats)
+    yr = F.conv3d(x.permute(0, 4, 1, 2, 3).float(), w.to(bf16).float(), padding=1)
+    s1, s2 = yr.sum((0, 2, 3, 4)).double(), (yr * yr).sum((0, 2, 3, 4)).double()
+    torch.cuda.synchronize()
+    res = {'sum': float((stats[:Cout] - s1).abs().max() / s1.abs().max()), 'sumsq': _rel(stats[Cout:], s2)}
+    assert res['sum'] < 2e-3 and res['sumsq'] < 2e-3, res
+    return res
+
+
+def check_norm(Cc=64, S=16, N=2, f=2, mode='sparse', act=1, residual=True, seed=0, tol=1.2e-2):
+    """pooled masked norm (+act, +residual) / dense BatchNorm (+running stats) / densify fill: fwd + bwd vs the oracle formula."""
+    from anatomask_b200 import ops
+    from oracle import reference_port as rp
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    mask = _rand_mask(N, f, seed=seed + 1)
+    mu = _up(mask, S).float()
+    x = (torch.randn(N, Cc, S, S, S, generator=g) * 1.5 + 0.3).to(bf16)
+    r = torch.randn(N, Cc, S, S, S, generator=g).to(bf16) if residual else None
+    if mode != 'dense':
+        x = x * mu.to(bf16)
+        if residual:
+            r = r * mu.to(bf16)
+    gamma = (1 + 0.2 * torch.randn(Cc, generator=g))
+    beta = 0.2 * torch.randn(Cc, generator=g)
+    token = 0.5 * torch.randn(1, Cc, 1, 1, 1, generator=g) if mode == 'fill' else None
+    gy = torch.randn(N, Cc, S, S, S, generator=g).to(bf16)
+    if mode == 'sparse':
+        gy = gy * mu.to(bf16)
+    eps = 1e-5
+    # reference (fp32, CPU)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rr = r.float().requires_grad_(True) if residual else None
+    tr = token.clone().requires_grad_(True) if token is not None else None
+    rm0, rv0 = torch.zeros(Cc), torch.ones(Cc)
+    if mode == 'dense':
+        P = {'w.weight': gr, 'w.bias': br, 'w.running_mean': rm0, 'w.running_var': rv0,
+             'w.num_batches_tracked': torch.zeros((), dtype=torch.long)}
+        nb = {}
+        yr = rp.batch_norm(P, 'w.', xr, True, nb)
+    else:
+        yr = rp.pooled_masked_norm(xr, gr, br, eps, mask)
+    if mode == 'fill':
+        yr = torch.where(_up(mask, S).expand_as(yr), yr, tr.expand_as(yr))
+    if residual:
+        yr = yr + rr
+    yr = F.leaky_relu(yr, 0.01) if act == 1 else (F.relu6(yr) if act == 2 else yr)
+    yr.backward(gy.float())
+    # CUDA
+    m = ops.MaskCtx(mask.to(dev)) if mode != 'dense' else None
+    xi = x.to(dev).permute(0, 2, 3, 4, 1).contiguous().requires_grad_(True)
+    ri = r.to(dev).permute(0, 2, 3, 4, 1).contiguous().requires_grad_(True) if residual else None
+    gp, bp = gamma.to(dev).requires_grad_(True), beta.to(dev).requires_grad_(True)
+    tp = token.to(dev).requires_grad_(True) if token is not None else None
+    running = None
+    if mode == 'dense':
+        running = (rm0.to(dev), rv0.to(dev), torch.zeros((), dtype=torch.long, device=dev))
+    y = ops.NormFn.apply(xi, gp, bp, ri, tp, eps, act, m, running, 0.1)
+    y.backward(gy.to(dev).permute(0, 2, 3, 4, 1).contiguous())
+    torch.cuda.synchronize()
+    res = {'fwd': _rel(y.permute(0, 4, 1, 2, 3).cpu(), yr.detach()),
+           'dx': _rel(xi.grad.permute(0, 4, 1, 2, 3).cpu(), xr.grad),
+           'dgamma': _rel(gp.grad.cpu(), gr.grad), 'dbeta': _rel(bp.grad.cpu(), br.grad)}
+    if residual:
+        res['dres'] = _rel(ri.grad.permute(0, 4, 1, 2, 3).cpu(), rr.grad)
+    if token is not None:
+        res['dtoken'] = _rel(tp.grad.cpu(), tr.grad)
+    if mode == 'dense':
+        res['rmean'] = _maxerr(running[0].cpu(), nb['w.running_mean'])
+        res['rvar'] = _maxerr(running[1].cpu(), nb['w.running_var'])
+        assert int(running[2]) == 1
+    bad = {k_: v for k_, v in res.items() if not (v < tol)}
+    assert not bad, f'norm C={Cc} S={S} mode={mode} act={act} residual={residual}: {res}'
+    return res
+
+
+def check_stem(Cc=32, S=32, N=2, f=2, seed=0, tol=1.2e-2):
+    from anatomask_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    mask = _rand_mask(N, f, seed=seed + 1)
+    inp = torch.randn(N, 1, S, S, S, generator=g)
+    w1 = torch.randn(Cc, 1, 3, 3, 3, generator=g) / 27 ** 0.5
+    b1, w3, b3 = 0.1 * torch.randn(Cc, generator=g), torch.randn(Cc, 1, 1, 1, 1, generator=g), 0.1 * torch.randn(Cc, generator=g)
+    mu = _up(mask, S).float()
+    ps = [t.clone().requires_grad_(True) for t in (w1, b1, w3, b3)]
+    xm = inp * mu
+    y1 = F.conv3d(xm, ps[0], ps[1], padding=1) * mu
+    y3 = F.conv3d(xm, ps[2], ps[3]) * mu
+    g1 = (torch.randn(y1.shape, generator=g) * mu).to(bf16)
+    g3 = (torch.randn(y3.shape, generator=g) * mu).to(bf16)
+    (y1 * g1.float() + y3 * g3.float()).sum().backward()
+    m = ops.MaskCtx(mask.to(dev))
+    pc = [t.to(dev).requires_grad_(True) for t in (w1, b1, w3, b3)]
+    o1, o3 = ops.StemFn.apply(inp.to(dev), *pc, m)
+    torch.autograd.backward([o1, o3], [g1.to(dev).permute(0, 2, 3, 4, 1).contiguous(),
+                                       g3.to(dev).permute(0, 2, 3, 4, 1).contiguous()])
+    torch.cuda.synchronize()
+    res = {'y1': _rel(o1.permute(0, 4, 1, 2, 3).cpu(), y1.detach()), 'y3': _rel(o3.permute(0, 4, 1, 2, 3).cpu(), y3.detach())}
+    for nme, a, b in zip(('dw1', 'db1', 'dw3', 'db3'), pc, ps):
+        res[nme] = _rel(a.grad.cpu(), b.grad)
+    bad = {k_: v for k_, v in res.items() if not (v < tol)}
+    assert not bad, f'stem: {res}'
+    return res
+
+
+def check_proj(Cc=32, S=16, N=2, seed=0, tol=1e-2):
+    from anatomask_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, Cc, S, S, S, generator=g).to(bf16)
+    w, b = torch.randn(1, Cc, 1, 1, 1, generator=g) / Cc ** 0.5, torch.randn(1, generator=g)
+    xr, wr, br = x.float().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv3d(xr, wr, br)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    xi = x.to(dev).permute(0, 2, 3, 4, 1).contiguous().requires_grad_(True)
+    wp, bp = w.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+    y = ops.ProjFn.apply(xi, wp, bp)
+    y.backward(gy.to(dev))
+    torch.cuda.synchronize()
+    res = {'fwd': _rel(y.cpu(), yr.detach()), 'dx': _rel(xi.grad.permute(0, 4, 1, 2, 3).cpu(), xr.grad),
+           'dw': _rel(wp.grad.cpu(), wr.grad), 'db': _rel(bp.grad.cpu(), br.grad)}
+    bad = {k_: v for k_, v in res.items() if not (v < tol)}
+    assert not bad, f'proj: {res}'
+    return res
+
+
+def check_loss(S=32, N=2, seed=0):
+    from anatomask_b200 import ops
+    from oracle import reference_port as rp
+    dev = _dev()
+    cfg = rp.Cfg(base=8, input_size=(S, S, S))
+    g = torch.Generator().manual_seed(seed)
+    inp = torch.randn(N, 1, S, S, S, generator=g) * 2 + 0.5
+    rec = torch.randn(N, 1, S, S, S, generator=g)
+    mask = rp.random_mask(cfg, N, g)
+    rr = rec.clone().requires_grad_(True)
+    loss_r, pp_r = rp.patch_loss(cfg, inp, rr, mask)
+    (loss_r * 1.7).backward()
+    raw_r = rp.teacher_patch_loss(cfg, inp, rec, mask)
+    rc = rec.to(dev).requires_grad_(True)
+    au8 = mask[:, 0].to(torch.uint8).contiguous().to(dev)
+    loss, pp = ops.PatchLossFn.apply(inp.to(dev), rc, au8, True)
+    (loss * 1.7).backward()
+    _, raw = ops.PatchLossFn.apply(inp.to(dev), rec.to(dev), au8, False)
+    torch.cuda.synchronize()
+    res = {'loss': abs(float(loss) - float(loss_r)) / abs(float(loss_r)), 'per_patch': _rel(pp.cpu(), pp_r.detach()),
+           'drec': _rel(rc.grad.cpu(), rr.grad), 'raw': _rel(raw.cpu(), raw_r)}
+    assert res['loss'] < 1e-5 and res['per_patch'] < 1e-5 and res['drec'] < 1e-5 and res['raw'] < 1e-5, res
+    return res
+
+
+def check_hard_mask(B=4, Lp=512, len_keep=205, seed=0):
+    """hard set bit-exact vs argsort; random fill = exactly len_keep visible, none of them hard, varies with offset."""
+    from anatomask_b200 import ops
+    from oracle import reference_port as rp
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    cfg = rp.CONFIGS['B128'] if Lp == 512 else rp.Cfg(base=8, input_size=(32, 32, 32))
+    for epoch, total in ((0, 999), (100, 999), (500, 999), (998, 999)):
+        loss = torch.rand(B, Lp, generator=g) * 3
+        m1 = torch.rand(B, Lp, generator=g) < 0.4
+        loss = loss * (~m1)                       # visible patches carry exactly-zero teacher loss
+        len_loss, _ = rp.hard_mask_lengths(cfg, epoch, total)
+        hard, mask = ops.hard_mask(loss.to(dev), len_loss, len_keep, seed=7, offset=epoch)
+        hard2, mask2 = ops.hard_mask(loss.to(dev), len_loss, len_keep, seed=7, offset=epoch + 1)
+        torch.cuda.synchronize()
+        order = torch.argsort(loss, dim=1)
+        assert torch.equal(hard.cpu().long(), order[:, Lp - len_loss:]), f'hard set differs at epoch {epoch}'
+        mk = mask.cpu().bool()
+        assert (mk.sum(1) == len_keep).all()
+        if len_loss:
+            assert not mk.gather(1, hard.cpu().long()).any(), 'a hard patch was left visible'
+        assert not torch.equal(mask.cpu(), mask2.cpu()), 'RNG offset ignored'
+    return {'ok': 1}
+
+
+def check_ema_adamw(n=1000003, seed=0):
+    from anatomask_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    n_al = (n + 3) // 4 * 4
+    e, mdl = torch.randn(n_al, generator=g), torch.randn(n_al, generator=g)
+    d = 0.999 + 3 / 250 * (0.9999 - 0.999)
+    ref = e * d + (1. - d) * mdl
+    ec = e.to(dev)
+    ops.ema_update_(ec, mdl.to(dev), d)
+    torch.cuda.synchronize()
+    assert torch.equal(ec.cpu(), ref), f'EMA not bit-exact: {float((ec.cpu() - ref).abs().max())}'
+    # AdamW with global-norm clipping, 3 steps vs torch.optim.AdamW + clip_grad_norm_
+    p0 = torch.randn(n_al, generator=g)
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-2)
+    pc = p0.to(dev)
+    m, v = torch.zeros_like(pc), torch.zeros_like(pc)
+    for step in range(1, 4):
+        gr = torch.randn(n_al, generator=g) * (5.0 if step == 2 else 0.001)
+        pr.grad = gr.clone()
+        torch.nn.utils.clip_grad_norm_([pr], 12.0)
+        opt.step()
+        ops.adamw_step_(pc, gr.to(dev), m, v, 1e-3, (0.9, 0.999), 1e-8, 1e-2, step, 12.0)
+    torch.cuda.synchronize()
+    err = float((pc.cpu() - pr.detach()).abs().max())
+    assert err < 2e-6, f'AdamW differs: {err}'
+    return {'ema': 0.0, 'adamw': err}
+
+
+def check_layout(Cc=24, S=12, N=2):
+    from anatomask_b200 import ops
+    dev = _dev()
+    x = torch.randn(N, Cc, S, S + 2, S + 4)
+    xi = ops.to_internal(x.to(dev))
+    back = ops.to_ncdhw_f32(xi)
+    torch.cuda.synchronize()
+    assert torch.equal(xi.permute(0, 4, 1, 2, 3).float().cpu(), x.to(bf16).float())
+    assert torch.equal(back.cpu(), x.to(bf16).float())
+    return {'ok': 1}
+
+
+CHECKS = {n[6:]: f for n, f in list(globals().items()) if n.startswith('check_')}
+
+if __name__ == '__main__':
+    name = sys.argv[1]
+    kwargs = json.loads(sys.argv[2]) if len(sys.argv) > 2 else {}
+    out = CHECKS[name](**kwargs)
+    print('RESULT', name, json.dumps(kwargs), json.dumps(out))
