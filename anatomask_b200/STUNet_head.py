@@ -1,0 +1,101 @@
+"""Encoder-only STUNet (the `cnn` handed to SparseEncoder) — P/STUNet_head.py:8-103.
+
+Same constructor, attribute and parameter names.  After `SparseEncoder` has swapped its layers, a BasicResBlock runs a
+fused schedule on channels-last bf16: the Cin=1 stem computes conv1 and the 1×1 shortcut in one pass, norm+LeakyReLU and
+norm+residual+LeakyReLU are single kernels.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import encoder3D, ops
+from ._lib import ACT_LRELU
+
+
+class Decoder(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.deep_supervision = True
+
+
+class BasicResBlock(nn.Module):
+    def __init__(self, input_channels, output_channels, kernel_size=3, padding=1, stride=1, use_1x1conv=False):
+        super().__init__()
+        self.conv1 = nn.Conv3d(input_channels, output_channels, kernel_size, stride=stride, padding=padding)
+        self.norm1 = nn.InstanceNorm3d(output_channels, affine=True)
+        self.act1 = nn.LeakyReLU(inplace=True)
+        self.conv2 = nn.Conv3d(output_channels, output_channels, kernel_size, padding=padding)
+        self.norm2 = nn.InstanceNorm3d(output_channels, affine=True)
+        self.act2 = nn.LeakyReLU(inplace=True)
+        self.conv3 = nn.Conv3d(input_channels, output_channels, kernel_size=1, stride=stride) if use_1x1conv else None
+
+    def _fusable(self):
+        return (isinstance(self.conv1, encoder3D.SparseConv3d) and isinstance(self.norm1, encoder3D.SparseInstanceNorm)
+                and isinstance(self.norm2, encoder3D.SparseInstanceNorm))
+
+    def forward(self, x):
+        if not self._fusable():                 # un-converted (dense) or exotic head: plain module-by-module path
+            y = self.act1(self.norm1(self.conv1(x)))
+            y = self.norm2(self.conv2(y))
+            if self.conv3:
+                x = self.conv3(x)
+            y = y + x
+            return self.act2(y)
+        m = encoder3D._mask_ctx()
+        c1, c2, c3 = self.conv1, self.conv2, self.conv3
+        stride = c1.stride[0]
+        if c1.in_channels == 1:                 # stem: masked fp32 input → conv1 and shortcut in one kernel
+            if c3 is None or stride != 1:
+                raise NotImplementedError('in_channels=1 block needs stride 1 and a 1x1 shortcut')
+            y, sc = ops.StemFn.apply(x, c1.weight, c1.bias, c3.weight, c3.bias, m)
+        else:
+            xi = ops.to_internal(x)
+            y = ops.conv3d(xi, c1.weight, c1.bias, c1.kernel_size[0], stride, m)
+            sc = ops.conv3d(xi, c3.weight, c3.bias, 1, stride, m) if c3 is not None else xi
+        y = ops.masked_norm(y, self.norm1.weight, self.norm1.bias, self.norm1.eps, m, ACT_LRELU)
+        y = ops.conv3d(y, c2.weight, c2.bias, c2.kernel_size[0], 1, m)
+        y = ops.masked_norm(y, self.norm2.weight, self.norm2.bias, self.norm2.eps, m, ACT_LRELU, residual=sc)
+        return ops.to_external(y)
+
+
+class STUNet(nn.Module):
+    def __init__(self, input_channels, num_classes, depth=[1, 1, 1, 1, 1, 1], dims=[32, 64, 128, 256, 512, 512],
+                 pool_op_kernel_sizes=None, conv_kernel_sizes=None, enable_deep_supervision=True):
+        super().__init__()
+        self.conv_op = nn.Conv3d
+        self.input_channels = input_channels
+        self.num_classes = num_classes
+        self.final_nonlin = lambda x: x
+        self.decoder = Decoder()
+        self.decoder.deep_supervision = enable_deep_supervision
+        self.upscale_logits = False
+        self.dims = dims
+        self.pool_op_kernel_sizes = pool_op_kernel_sizes
+        self.conv_kernel_sizes = conv_kernel_sizes
+        self.conv_pad_sizes = [[i // 2 for i in krnl] for krnl in self.conv_kernel_sizes]
+        num_pool = len(pool_op_kernel_sizes)
+        assert num_pool == len(dims) - 1
+        self.conv_blocks_context = nn.ModuleList()
+        k, p = self.conv_kernel_sizes, self.conv_pad_sizes
+        self.conv_blocks_context.append(nn.Sequential(
+            BasicResBlock(input_channels, dims[0], k[0], p[0], use_1x1conv=True),
+            *[BasicResBlock(dims[0], dims[0], k[0], p[0]) for _ in range(depth[0] - 1)]))
+        for d in range(1, num_pool):
+            self.conv_blocks_context.append(nn.Sequential(
+                BasicResBlock(dims[d - 1], dims[d], k[d], p[d], stride=self.pool_op_kernel_sizes[d - 1],
+                              use_1x1conv=True),
+                *[BasicResBlock(dims[d], dims[d], k[d], p[d]) for _ in range(depth[d] - 1)]))
+
+    def get_downsample_ratio(self) -> int:
+        return 16
+
+    def get_feature_map_channels(self):
+        return self.dims[:5]
+
+    def forward(self, x, hierarchical=False):
+        skips = []
+        for d in range(len(self.conv_blocks_context)):
+            x = self.conv_blocks_context[d](x)
+            skips.append(x)
+        return skips if hierarchical else x

@@ -53,18 +53,19 @@ _SIGNATURES = {
     'amb_proj_fwd': (i32, [vp, vp, vp, vp, i64, i32, vp]),
     'amb_proj_bwd': (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp]),
     'amb_norm_stats': (i32, [C.POINTER(Geo), vp, vp, vp]),
-    'amb_norm_finalize': (i32, [C.POINTER(Geo), vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp]),
+    'amb_norm_finalize': (i32, [C.POINTER(Geo), vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp, vp]),
+    'amb_count_voxels': (i32, [C.POINTER(Geo), vp, vp]),
     'amb_norm_eval': (i32, [vp, vp, vp, vp, f32, vp, vp, i32, vp]),
     'amb_norm_apply': (i32, [C.POINTER(Geo), vp, vp, vp, vp, vp, i32, vp, vp]),
     'amb_norm_bwd_reduce': (i32, [C.POINTER(Geo), vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]),
-    'amb_norm_bwd_apply': (i32, [C.POINTER(Geo), vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),
+    'amb_norm_bwd_apply': (i32, [C.POINTER(Geo), vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
     'amb_add': (i32, [vp, vp, vp, i64, vp]),
     'amb_patch_loss_fwd': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
     'amb_patch_loss_bwd': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
-    'amb_hard_mask': (i32, [vp, i32, i32, i32, i32, u64, u64, vp, vp, vp]),
+    'amb_hard_mask': (i32, [vp, i32, i32, i32, i32, u64, u64, vp, vp, vp, vp]),
     'amb_ema_update': (i32, [vp, vp, i64, f64, vp]),
     'amb_sumsq': (i32, [vp, i64, vp, vp]),
-    'amb_adamw_step': (i32, [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i32, vp, f64, vp]),
+    'amb_adamw_step': (i32, [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i32, vp, f64, f64, vp]),
 }
 
 EXPORTED = tuple(_SIGNATURES.keys())

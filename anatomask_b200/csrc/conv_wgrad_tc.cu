@@ -19,7 +19,6 @@ using namespace ptx;
 int encode_view_map(CUtensorMap* m, const void* tensor_base, const View& v, int C, int kc, const int box[4]);
 
 #define WG_MAX_UNITS 64
-#define WG_MAX_BATCH 32
 
 struct WTap {
     int8_t aview, sz, sy, sx;     // dY view and the shift applied to the tile origin (= −tap offset)
@@ -27,7 +26,7 @@ struct WTap {
     int16_t bview;
 };
 struct WBatch {
-    int16_t unit_begin, unit_count, bview, pad;
+    int unit_begin, unit_count, bview;
 };
 
 struct WgradParams {
@@ -35,8 +34,10 @@ struct WgradParams {
     CUtensorMap b_maps[8];        // X views,  box = nslabW channels × 128 voxels
     WTap taps[64];
     int8_t unit_taps[WG_MAX_UNITS][8];   // stacked mode: tap index per M slab (−1 = none)
-    WBatch batches[WG_MAX_BATCH];
-    int n_batches, n_units;
+    int view_unit_begin[9];       // units of X view v are [view_unit_begin[v], view_unit_begin[v+1])
+    int view_batch_begin[9];      // batches never straddle an X view
+    int per_batch;                // accumulator units per CTA = 512 / NTw
+    int n_batches, n_units, n_views;
     int stacked;                  // 1: Cy < 128, units stack 128/Cy taps ; 0: unit = (tap, 128-row slab of Cy)
     int mslabs;                   // Cy / 128 when !stacked
     int Cx, Cy;
@@ -117,7 +118,15 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     int job = blockIdx.x;
     const int ks = job % P.ksplit; job /= P.ksplit;
     const int nchunk = job % P.n_nchunks; job /= P.n_nchunks;
-    const WBatch B = P.batches[job];
+    WBatch B;
+    {
+        int v = 0;
+        while (v + 1 < P.n_views && job >= P.view_batch_begin[v + 1]) ++v;
+        B.bview = v;
+        B.unit_begin = P.view_unit_begin[v] + (job - P.view_batch_begin[v]) * P.per_batch;
+        const int left = P.view_unit_begin[v + 1] - B.unit_begin;
+        B.unit_count = left < P.per_batch ? left : P.per_batch;
+    }
     const long ktiles = wg_num_ktiles(P);
     const long k_begin = ktiles * ks / P.ksplit, k_end = ktiles * (ks + 1) / P.ksplit;
 
@@ -288,47 +297,29 @@ int igemm_wgrad(const Plan& p, const amb_wgrad_args* a) {
         w.w = T.w;
         w.bview = T.view;
     }
-    // units and batches
+    // units (per X view, contiguous) and batches (chunks of per_batch units inside a view)
     const int per_batch = 512 / P.NTw;
+    P.per_batch = per_batch;
+    P.n_views = p.n_in_views;
     memset(P.unit_taps, -1, sizeof(P.unit_taps));
-    int nu = 0, nb = 0;
-    if (P.stacked) {
-        int i = 0;
-        while (i < n) {
-            const int bv = P.taps[i].bview;
-            int first_unit = nu;
-            while (i < n && P.taps[i].bview == bv) {
+    int nu = 0, nb = 0, i = 0;
+    for (int v = 0; v < p.n_in_views; ++v) {
+        P.view_unit_begin[v] = nu;
+        P.view_batch_begin[v] = nb;
+        if (P.stacked) {
+            while (i < n && P.taps[i].bview == v) {
                 if (nu >= WG_MAX_UNITS) { set_error("wgrad: too many units"); return 0; }
-                for (int j = 0; j < P.a_slabs && i < n && P.taps[i].bview == bv; ++j) P.unit_taps[nu][j] = (int8_t)i++;
+                for (int j = 0; j < P.a_slabs && i < n && P.taps[i].bview == v; ++j) P.unit_taps[nu][j] = (int8_t)i++;
                 nu++;
             }
-            for (int u = first_unit; u < nu; u += per_batch) {
-                if (nb >= WG_MAX_BATCH) { set_error("wgrad: too many batches"); return 0; }
-                P.batches[nb].unit_begin = (int16_t)u;
-                P.batches[nb].unit_count = (int16_t)((nu - u) < per_batch ? (nu - u) : per_batch);
-                P.batches[nb].bview = (int16_t)bv;
-                nb++;
-            }
+        } else {
+            // unit index = tap * mslabs + mslab (taps are sorted by view, so a view's units are contiguous)
+            while (i < n && P.taps[i].bview == v) { ++i; nu += P.mslabs; }
         }
-    } else {
-        // unit index = tap * mslabs + mslab ; batches never straddle an X view
-        int i = 0;
-        while (i < n) {
-            const int bv = P.taps[i].bview;
-            int j = i;
-            while (j < n && P.taps[j].bview == bv) ++j;
-            for (int u = i * P.mslabs; u < j * P.mslabs; u += per_batch) {
-                if (nb >= WG_MAX_BATCH) { set_error("wgrad: too many batches (Cy=%d)", p.Cy); return 0; }
-                int cnt = j * P.mslabs - u;
-                P.batches[nb].unit_begin = (int16_t)u;
-                P.batches[nb].unit_count = (int16_t)(cnt < per_batch ? cnt : per_batch);
-                P.batches[nb].bview = (int16_t)bv;
-                nb++;
-            }
-            i = j;
-        }
-        nu = n * P.mslabs;
+        nb += (nu - P.view_unit_begin[v] + per_batch - 1) / per_batch;
     }
+    P.view_unit_begin[p.n_in_views] = nu;
+    P.view_batch_begin[p.n_in_views] = nb;
     P.n_units = nu; P.n_batches = nb;
 
     const int box[4] = {bn, bd, bh, bw};

@@ -174,7 +174,7 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 __global__ void __launch_bounds__(512)
 hard_mask_kernel(const float* __restrict__ loss_pred, int L, int Lp2, int len_loss, int len_keep,
                  unsigned long long seed, unsigned long long offset, int* __restrict__ hard,
-                 uint8_t* __restrict__ mask_out) {
+                 int* __restrict__ order, uint8_t* __restrict__ mask_out) {
     extern __shared__ unsigned char smraw[];
     float* key = reinterpret_cast<float*>(smraw);
     int* idx = reinterpret_cast<int*>(key + Lp2);
@@ -186,6 +186,8 @@ hard_mask_kernel(const float* __restrict__ loss_pred, int L, int Lp2, int len_lo
         if (i < L) is_hard[i] = 0;
     }
     bitonic_sort(key, idx, Lp2);
+    if (order)
+        for (int i = threadIdx.x; i < L; i += blockDim.x) order[(long)b * L + i] = idx[i];
     // hard set = the len_loss largest losses = sorted positions [L-len_loss, L)
     for (int i = threadIdx.x; i < len_loss; i += blockDim.x) {
         int id = idx[L - len_loss + i];
@@ -257,11 +259,12 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long n, double* __rest
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float wd,
-                             float bc1, float bc2_sqrt, const double* __restrict__ gnorm_sq, float max_norm) {
-    float coef = 1.f;
+                             float bc1, float bc2_sqrt, const double* __restrict__ gnorm_sq, float max_norm,
+                             float gscale) {
+    float coef = gscale;   // gscale = 1/world when g holds the all-reduced SUM of the ranks' gradients
     if (gnorm_sq) {   // torch.nn.utils.clip_grad_norm_: coef = clamp(max_norm / (norm + 1e-6), max=1)
-        float norm = (float)sqrt(*gnorm_sq);
-        coef = fminf(max_norm / (norm + 1e-6f), 1.f);
+        float norm = (float)sqrt(*gnorm_sq) * gscale;
+        coef = fminf(max_norm / (norm + 1e-6f), 1.f) * gscale;
     }
     const float step_size = lr / bc1;
     const long stride = (long)gridDim.x * blockDim.x;
@@ -507,8 +510,8 @@ extern "C" int amb_patch_loss_bwd(const float* inp, const float* rec, const uint
 }
 
 extern "C" int amb_hard_mask(const float* loss_pred, int B, int L, int len_loss, int len_keep,
-                             unsigned long long seed, unsigned long long offset, int* hard, uint8_t* mask_out,
-                             void* stream) {
+                             unsigned long long seed, unsigned long long offset, int* hard, int* order,
+                             uint8_t* mask_out, void* stream) {
     AMB_CHECK(L >= 1 && L <= 4096, AMB_ERR_ARG, "hard mask: L=%d out of range (1..4096)", L);
     AMB_CHECK(len_loss >= 0 && len_loss <= L && len_keep >= 0 && len_keep + len_loss <= L, AMB_ERR_ARG,
               "hard mask: len_loss=%d len_keep=%d L=%d", len_loss, len_keep, L);
@@ -516,7 +519,7 @@ extern "C" int amb_hard_mask(const float* loss_pred, int B, int L, int len_loss,
     while (Lp2 < L) Lp2 <<= 1;
     size_t smem = (size_t)Lp2 * 8 + L;
     hard_mask_kernel<<<B, 512, smem, (cudaStream_t)stream>>>(loss_pred, L, Lp2, len_loss, len_keep, seed, offset, hard,
-                                                             mask_out);
+                                                             order, mask_out);
     AMB_LAUNCH_CHECK();
     return 0;
 }
@@ -538,13 +541,13 @@ extern "C" int amb_sumsq(const float* g, long n, double* out, void* stream) {
 
 extern "C" int amb_adamw_step(float* p, const float* g, float* m, float* v, long n, double lr, double beta1,
                               double beta2, double eps, double weight_decay, int step, const double* gnorm_sq,
-                              double max_norm, void* stream) {
+                              double max_norm, double gscale, void* stream) {
     AMB_CHECK(step >= 1, AMB_ERR_ARG, "adamw: step must be >= 1");
     double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
     adamw_kernel<<<grid_cap(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)lr, (float)beta1,
                                                                         (float)beta2, (float)eps, (float)weight_decay,
                                                                         (float)bc1, (float)sqrt(bc2), gnorm_sq,
-                                                                        (float)max_norm);
+                                                                        (float)max_norm, (float)gscale);
     AMB_LAUNCH_CHECK();
     return 0;
 }

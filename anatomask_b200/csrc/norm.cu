@@ -144,8 +144,9 @@ __global__ void __launch_bounds__(512) reduce_kernel(Geo g, const bf16* __restri
 __global__ void finalize_kernel(Geo g, const double* __restrict__ sums, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, float* __restrict__ scale,
                                 float* __restrict__ shift, float* __restrict__ saved, float* running_mean,
-                                float* running_var, long* nbt, float momentum) {
-    const double n = g.list ? (double)((long)(*g.count) << (3 * g.lgP)) : (double)g.N * g.D * g.H * g.W;
+                                float* running_var, long* nbt, float momentum, const double* n_total) {
+    const double n = n_total ? *n_total
+                             : (g.list ? (double)((long)(*g.count) << (3 * g.lgP)) : (double)g.N * g.D * g.H * g.W);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.C; c += gridDim.x * blockDim.x) {
         double mean = sums[c] / n;
         double var = sums[g.C + c] / n - mean * mean;
@@ -212,12 +213,13 @@ __global__ void __launch_bounds__(512)
 bwd_apply_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ x, const bf16* __restrict__ res,
                  const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ saved,
                  const double* __restrict__ sums, int act, int fill, bf16* __restrict__ dx, bf16* __restrict__ dres,
-                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                 float* __restrict__ dgamma, float* __restrict__ dbeta, const double* n_total) {
     const int CG = g.C / 8;
     const long total = total_items(g, CG);
     const long stride = (long)gridDim.x * blockDim.x;
     const int cg = threadIdx.x % CG;
-    const double n = g.list ? (double)((long)(*g.count) << (3 * g.lgP)) : (double)g.N * g.D * g.H * g.W;
+    const double n = n_total ? *n_total
+                             : (g.list ? (double)((long)(*g.count) << (3 * g.lgP)) : (double)g.N * g.D * g.H * g.W);
     float sc[8], sh[8], mu[8], rs[8], m1[8], m2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -383,12 +385,12 @@ extern "C" int amb_norm_stats(const amb_geo* a, const void* x, double* sums, voi
 
 extern "C" int amb_norm_finalize(const amb_geo* a, const double* sums, const float* gamma, const float* beta,
                                  float eps, float* scale, float* shift, float* saved, float* running_mean,
-                                 float* running_var, long* nbt, float momentum, void* stream) {
+                                 float* running_var, long* nbt, float momentum, const double* n_total, void* stream) {
     Geo g;
     if (int e = make_geo(a, g)) return e;
     finalize_kernel<<<ceil_div(g.C, 128), 128, 0, (cudaStream_t)stream>>>(g, sums, gamma, beta, eps, scale, shift,
                                                                           saved, running_mean, running_var, nbt,
-                                                                          momentum);
+                                                                          momentum, n_total);
     AMB_LAUNCH_CHECK();
     return 0;
 }
@@ -430,7 +432,7 @@ extern "C" int amb_norm_bwd_reduce(const amb_geo* a, const void* dout, const voi
 extern "C" int amb_norm_bwd_apply(const amb_geo* a, const void* dout, const void* x, const void* residual,
                                   const float* scale, const float* shift, const float* saved, const double* sums,
                                   int act, int fill, void* dx, void* dres, float* dgamma, float* dbeta,
-                                  void* stream) {
+                                  const double* n_total, void* stream) {
     Geo g;
     if (int e = make_geo(a, g)) return e;
     (void)fill;   // dx is only defined on visited (active) voxels; the caller zero-fills dx when the list is sparse
@@ -438,7 +440,19 @@ extern "C" int amb_norm_bwd_apply(const amb_geo* a, const void* dout, const void
     if (block < 0) return block;
     bwd_apply_kernel<<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(
         g, (const bf16*)dout, (const bf16*)x, (const bf16*)residual, scale, shift, saved, sums, act, fill, (bf16*)dx,
-        (bf16*)dres, dgamma, dbeta);
+        (bf16*)dres, dgamma, dbeta, n_total);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void count_voxels_kernel(Geo g, double* out) {
+    *out = g.list ? (double)((long)(*g.count) << (3 * g.lgP)) : (double)g.N * g.D * g.H * g.W;
+}
+
+extern "C" int amb_count_voxels(const amb_geo* a, double* out, void* stream) {
+    Geo g;
+    if (int e = make_geo(a, g)) return e;
+    count_voxels_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(g, out);
     AMB_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,207 @@
+"""Sparse layer API of the reference (P/encoder3D.py) backed by sm_100a kernels.
+
+Same names, constructor signatures, parameter/buffer names and error behaviour as the reference classes; the arithmetic
+goes through anatomask_b200.ops (C ABI → CUDA).  Tensors crossing a module boundary are logical (N, C, D, H, W);
+channels-last bf16 tensors pass through zero-copy, anything else is converted once by a layout kernel.
+
+`_cur_active` is kept as the settable module global the reference uses (P/encoder3D.py:5, set at P/spark3D.py:103):
+assign the (B,1,f,f,f) bool mask and every sparse layer picks it up.  The device work-list derived from it is cached
+per mask tensor, so it is built once per forward instead of `nonzero()`-ing 30 times (P/encoder3D.py:7-10).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import ACT_NONE
+
+_cur_active: torch.Tensor = None            # B1fff bool, True = visible
+_ctx_cache = (None, None)
+
+
+def _mask_ctx() -> ops.MaskCtx:
+    global _ctx_cache
+    if _cur_active is None:
+        raise RuntimeError('encoder3D._cur_active is not set (SparK.forward sets it; P/spark3D.py:103)')
+    if isinstance(_cur_active, ops.MaskCtx):
+        return _cur_active
+    if _ctx_cache[0] is not _cur_active:
+        _ctx_cache = (_cur_active, ops.MaskCtx(_cur_active))
+    return _ctx_cache[1]
+
+
+def _single(v):
+    return v[0] if isinstance(v, (tuple, list)) else v
+
+
+def _uniform(v, what):
+    if isinstance(v, (tuple, list)):
+        if len(set(v)) != 1:
+            raise NotImplementedError(f'anisotropic {what}={v} is not supported by the sm_100a kernels')
+        return v[0]
+    return v
+
+
+class SparseConv3d(nn.Conv3d):
+    """(conv3d(x, W) + b) · mask at the output resolution — P/encoder3D.py:12-15,27-28."""
+
+    def forward(self, x: torch.Tensor):
+        k, s, p = _uniform(self.kernel_size, 'kernel_size'), _uniform(self.stride, 'stride'), _uniform(self.padding, 'padding')
+        if k not in (1, 3) or s not in (1, 2) or p != k // 2 or _uniform(self.dilation, 'dilation') != 1 \
+                or self.groups != 1 or self.padding_mode != 'zeros':
+            raise NotImplementedError(f'SparseConv3d(k={k}, s={s}, p={p}, groups={self.groups}) has no sm_100a kernel yet')
+        m = _mask_ctx()
+        if self.in_channels == 1:
+            if k == 3 and s == 1:
+                w3 = torch.zeros(self.out_channels, 1, 1, 1, 1, device=x.device)
+                b = self.bias if self.bias is not None else torch.zeros(self.out_channels, device=x.device)
+                y, _ = ops.StemFn.apply(x, self.weight, b, w3, torch.zeros_like(b), m)
+                return ops.to_external(y)
+            if k == 1 and s == 1:
+                w1 = torch.zeros(self.out_channels, 1, 3, 3, 3, device=x.device)
+                b = self.bias if self.bias is not None else torch.zeros(self.out_channels, device=x.device)
+                _, y = ops.StemFn.apply(x, w1, torch.zeros_like(b), self.weight, b, m)
+                return ops.to_external(y)
+            raise NotImplementedError('SparseConv3d with in_channels=1 supports stride 1 only')
+        y = ops.conv3d(ops.to_internal(x), self.weight, self.bias, k, s, m)
+        return ops.to_external(y)
+
+
+class SparseMaxPooling(nn.MaxPool3d):
+    def forward(self, x):
+        raise NotImplementedError('SparseMaxPooling: not on the STUNet path (SURVEY.md §8f row 4)')
+
+
+class SparseAvgPooling(nn.AvgPool3d):
+    def forward(self, x):
+        raise NotImplementedError('SparseAvgPooling: not on the STUNet path (SURVEY.md §8f row 4)')
+
+
+def _sp_bn_forward(self, x: torch.Tensor, group=None):
+    """P/encoder3D.py:17-25: BatchNorm1d over the visible voxels (pooled over the local batch, or all ranks when Sync)."""
+    m = _mask_ctx()
+    xi = ops.to_internal(x)
+    if self.training or not self.track_running_stats:
+        running, mom = None, 0.0
+        if self.track_running_stats and self.training:
+            running = (self.running_mean, self.running_var, self.num_batches_tracked)
+            mom = 0.1 if self.momentum is None else self.momentum
+        y = ops.masked_norm(xi, self.weight, self.bias, self.eps, m, ACT_NONE, None, running, mom, group)
+    else:
+        y = ops.norm_eval(xi, self.weight, self.bias, self.running_mean, self.running_var, self.eps, ACT_NONE, m)
+    return ops.to_external(y)
+
+
+class SparseBatchNorm3d(nn.BatchNorm1d):
+    forward = _sp_bn_forward
+
+
+class SparseSyncBatchNorm3d(nn.SyncBatchNorm):
+    def forward(self, x):
+        import torch.distributed as dist
+        group = None
+        if self.training and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            group = self.process_group if self.process_group is not None else dist.group.WORLD
+        return _sp_bn_forward(self, x, group)
+
+
+class SparseInstanceNorm(nn.InstanceNorm1d):
+    """NOT an instance norm in the reference: the visible voxels of the whole local batch are fed to InstanceNorm1d as
+    one unbatched (C, N_active) sample → per-channel statistics pooled over the batch, biased variance, no running
+    stats, same in train and eval (P/encoder3D.py:149-158)."""
+
+    def __init__(self, num_features, eps=1e-6, sparse=True):
+        super().__init__(num_features, eps, affine=True)
+        self.sparse = sparse
+
+    def forward(self, x):
+        if x.ndim == 5:
+            if self.sparse:
+                y = ops.masked_norm(ops.to_internal(x), self.weight, self.bias, self.eps, _mask_ctx())
+                return ops.to_external(y)
+            return super().forward(x)
+        if self.sparse:
+            raise NotImplementedError
+        return super().forward(x)
+
+    def __repr__(self):
+        return super().__repr__()[:-1] + f', sp={self.sparse})'
+
+
+class SparseGroupNorm(nn.GroupNorm):
+    def __init__(self, num_groups, num_channels, eps=1e-6, sparse=True):
+        super().__init__(num_groups, num_channels, eps)
+        self.sparse = sparse
+
+    def forward(self, x):
+        raise NotImplementedError('SparseGroupNorm (MedNeXt head) is outside the STUNet hot path (SURVEY.md §8f row 4)')
+
+
+class SparseConvNeXtLayerNorm(nn.LayerNorm):
+    def __init__(self, normalized_shape, eps=1e-6, data_format='channels_last', sparse=True):
+        super().__init__(normalized_shape, eps, elementwise_affine=True)
+        self.data_format, self.sparse = data_format, sparse
+
+    def forward(self, x):
+        raise NotImplementedError('SparseConvNeXtLayerNorm is outside the STUNet hot path (SURVEY.md §8f row 4)')
+
+
+class SparseEncoder(nn.Module):
+    """Wraps any CNN following the `get_downsample_ratio / get_feature_map_channels / forward(x, hierarchical)` protocol
+    and swaps its dense layers for the sparse ones — P/encoder3D.py:293-367."""
+
+    def __init__(self, cnn, input_size, sbn=False, verbose=False):
+        super().__init__()
+        self.sp_cnn = SparseEncoder.dense_model_to_sparse(m=cnn, verbose=verbose, sbn=sbn)
+        self.input_size, self.downsample_ratio, self.enc_feat_map_chs = \
+            input_size, cnn.get_downsample_ratio(), cnn.get_feature_map_channels()
+
+    @staticmethod
+    def dense_model_to_sparse(m: nn.Module, verbose=False, sbn=False):
+        oup = m
+        if isinstance(m, nn.Conv3d) and not isinstance(m, SparseConv3d):
+            if not getattr(m, 'skip_sparse_conversion', False):
+                bias = m.bias is not None
+                oup = SparseConv3d(m.in_channels, m.out_channels, kernel_size=m.kernel_size, stride=m.stride,
+                                   padding=m.padding, dilation=m.dilation, groups=m.groups, bias=bias,
+                                   padding_mode=m.padding_mode)
+                oup.weight.data.copy_(m.weight.data)
+                if bias:
+                    oup.bias.data.copy_(m.bias.data)
+        elif isinstance(m, nn.MaxPool3d):
+            oup = SparseMaxPooling(m.kernel_size, stride=m.stride, padding=m.padding, dilation=m.dilation,
+                                   return_indices=m.return_indices, ceil_mode=m.ceil_mode)
+        elif isinstance(m, nn.AvgPool3d):
+            oup = SparseAvgPooling(m.kernel_size, m.stride, m.padding, ceil_mode=m.ceil_mode,
+                                   count_include_pad=m.count_include_pad, divisor_override=m.divisor_override)
+        elif isinstance(m, nn.GroupNorm) and not isinstance(m, SparseGroupNorm):
+            oup = SparseGroupNorm(m.num_groups, m.num_channels, eps=m.eps)
+        elif isinstance(m, nn.InstanceNorm3d):
+            oup = SparseInstanceNorm(m.num_features, m.eps)
+            oup.weight.data.copy_(m.weight.data)
+            oup.bias.data.copy_(m.bias.data)
+        elif isinstance(m, (nn.BatchNorm3d, nn.SyncBatchNorm)) and not isinstance(m, SparseSyncBatchNorm3d):
+            oup = (SparseSyncBatchNorm3d if sbn else SparseBatchNorm3d)(
+                m.weight.shape[0], eps=m.eps, momentum=m.momentum, affine=m.affine,
+                track_running_stats=m.track_running_stats)
+            oup.weight.data.copy_(m.weight.data)
+            oup.bias.data.copy_(m.bias.data)
+            oup.running_mean.data.copy_(m.running_mean.data)
+            oup.running_var.data.copy_(m.running_var.data)
+            oup.num_batches_tracked.data.copy_(m.num_batches_tracked.data)
+            if hasattr(m, 'qconfig'):
+                oup.qconfig = m.qconfig
+        elif isinstance(m, nn.LayerNorm) and not isinstance(m, SparseConvNeXtLayerNorm):
+            oup = SparseConvNeXtLayerNorm(m.weight.shape[0], eps=m.eps)
+            oup.weight.data.copy_(m.weight.data)
+            oup.bias.data.copy_(m.bias.data)
+        elif isinstance(m, (nn.Conv1d,)):
+            raise NotImplementedError
+        for name, child in m.named_children():
+            oup.add_module(name, SparseEncoder.dense_model_to_sparse(child, verbose=verbose, sbn=sbn))
+        del m
+        return oup
+
+    def forward(self, x):
+        return self.sp_cnn(x, hierarchical=True)

@@ -272,22 +272,30 @@ class NormFn(torch.autograd.Function):
     m given, token None  : SparseInstanceNorm / SparseBatchNorm3d (P/encoder3D.py:17-25,149-158) — visible voxels only
     m given, token given : densify — normalise visible voxels, fill masked ones with the mask token (P/spark3D.py:117-122)
     m None               : nn.BatchNorm3d in training mode (decoder)
-    running = (rm, rv, nbt) updates the running statistics in place (momentum 0.1, unbiased variance)."""
+    running = (rm, rv, nbt) updates the running statistics in place (momentum 0.1, unbiased variance).
+    group (torch.distributed process group) pools the statistics over all ranks: one all-reduce of (Σx, Σx², n) forward
+    and one of (Σg, Σg·x̂) backward — SparseSyncBatchNorm3d / nn.SyncBatchNorm (P/encoder3D.py:43, P/decoder3D.py:42)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, token, eps, act, m, running, momentum):
+    def forward(ctx, x, gamma, beta, residual, token, eps, act, m, running, momentum, group=None):
         x = x.contiguous()
         Cc = x.shape[-1]
         dev = x.device
         sparse = m is not None
         g = m.geo(x, True) if sparse else dense_geo(x)
-        sums = torch.zeros(2 * Cc, dtype=torch.float64, device=dev)
+        sums = torch.zeros(2 * Cc + 1, dtype=torch.float64, device=dev)
         L.call('amb_norm_stats', C.byref(g), _p(x), _p(sums), _stream())
+        ntot = None
+        if group is not None:
+            import torch.distributed as dist
+            L.call('amb_count_voxels', C.byref(g), _p(sums[2 * Cc:]), _stream())
+            dist.all_reduce(sums, group=group)
+            ntot = sums[2 * Cc:]
         ss = torch.empty(4 * Cc, dtype=torch.float32, device=dev)
         scale, shift, saved = ss[:Cc], ss[Cc:2 * Cc], ss[2 * Cc:]
         rm, rv, nbt = running if running is not None else (None, None, None)
         L.call('amb_norm_finalize', C.byref(g), _p(sums), _p(gamma), _p(beta), eps, _p(scale), _p(shift), _p(saved),
-               _p(rm), _p(rv), _p(nbt), momentum, _stream())
+               _p(rm), _p(rv), _p(nbt), momentum, _p(ntot), _stream())
         fill = token is not None
         out = torch.zeros_like(x) if (sparse and not fill) else torch.empty_like(x)
         tok = token.reshape(-1).contiguous() if fill else None
@@ -295,14 +303,14 @@ class NormFn(torch.autograd.Function):
             residual = residual.contiguous()
         L.call('amb_norm_apply', C.byref(g), _p(x), _p(scale), _p(shift), _p(residual), _p(tok), act, _p(out),
                _stream())
-        ctx.save_for_backward(x, residual, ss)
-        ctx.cfg = (act, m, fill, token.shape if fill else None)
+        ctx.save_for_backward(x, residual, ss, ntot)
+        ctx.cfg = (act, m, fill, token.shape if fill else None, group)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, residual, ss = ctx.saved_tensors
-        act, m, fill, tshape = ctx.cfg
+        x, residual, ss, ntot = ctx.saved_tensors
+        act, m, fill, tshape, group = ctx.cfg
         dout = dout.contiguous()
         Cc = x.shape[-1]
         dev = x.device
@@ -312,40 +320,57 @@ class NormFn(torch.autograd.Function):
         sums = torch.zeros(3 * Cc, dtype=torch.float64, device=dev)
         L.call('amb_norm_bwd_reduce', C.byref(g), _p(dout), _p(x), _p(residual), _p(scale), _p(shift), _p(saved), act,
                int(fill), _p(sums), _p(sums[2 * Cc:]) if fill else C.c_void_p(0), _stream())
+        gb = torch.empty(2 * Cc, dtype=torch.float32, device=dev)
+        local_gb = None
+        if group is not None:       # parameter grads stay rank-local (DDP averages them); dx needs the pooled sums
+            import torch.distributed as dist
+            local_gb = sums[:2 * Cc].float()
+            dist.all_reduce(sums[:2 * Cc], group=group)
         dx = torch.zeros_like(x) if sparse else torch.empty_like(x)
         dres = None
         if residual is not None:
             dres = torch.zeros_like(x) if sparse else torch.empty_like(x)
-        gb = torch.empty(2 * Cc, dtype=torch.float32, device=dev)
         L.call('amb_norm_bwd_apply', C.byref(g), _p(dout), _p(x), _p(residual), _p(scale), _p(shift), _p(saved),
-               _p(sums), act, int(fill), _p(dx), _p(dres), _p(gb[:Cc]), _p(gb[Cc:]), _stream())
+               _p(sums), act, int(fill), _p(dx), _p(dres), _p(gb[:Cc]), _p(gb[Cc:]), _p(ntot), _stream())
+        if local_gb is not None:
+            dbeta, dgamma = local_gb[:Cc], local_gb[Cc:]
+        else:
+            dgamma, dbeta = gb[:Cc], gb[Cc:]
         dtoken = sums[2 * Cc:].float().view(tshape) if fill else None
-        return dx, gb[:Cc], gb[Cc:], dres, dtoken, None, None, None, None, None
+        return dx, dgamma, dbeta, dres, dtoken, None, None, None, None, None, None
 
 
-def masked_norm(x, gamma, beta, eps, m: MaskCtx, act=L.ACT_NONE, residual=None):
-    return NormFn.apply(x, gamma, beta, residual, None, eps, act, m, None, 0.0)
+def masked_norm(x, gamma, beta, eps, m: MaskCtx, act=L.ACT_NONE, residual=None, running=None, momentum=0.0,
+                group=None):
+    return NormFn.apply(x, gamma, beta, residual, None, eps, act, m, running, momentum, group)
 
 
-def densify_norm_fill(x, gamma, beta, token, eps, m: MaskCtx):
-    return NormFn.apply(x, gamma, beta, None, token, eps, L.ACT_NONE, m, None, 0.0)
+def densify_norm_fill(x, gamma, beta, token, eps, m: MaskCtx, running=None, momentum=0.0, group=None):
+    return NormFn.apply(x, gamma, beta, None, token, eps, L.ACT_NONE, m, running, momentum, group)
 
 
-def batch_norm_train(x, gamma, beta, eps, act, running, momentum):
-    return NormFn.apply(x, gamma, beta, None, None, eps, act, None, running, momentum)
+def batch_norm_train(x, gamma, beta, eps, act, running, momentum, group=None):
+    return NormFn.apply(x, gamma, beta, None, None, eps, act, None, running, momentum, group)
 
 
-def batch_norm_eval(x, gamma, beta, rm, rv, eps, act):
-    """Inference-mode BatchNorm (teacher forward, P/pretrain_AntoMask.py:422): running statistics, no grad."""
+def norm_eval(x, gamma, beta, rm, rv, eps, act, m: Optional[MaskCtx] = None, token=None):
+    """Inference-mode BatchNorm (teacher forward, P/pretrain_AntoMask.py:422): running statistics, no grad.
+    With m: visible voxels only (SparseBatchNorm3d in eval) and optionally the densify fill."""
     x = x.contiguous()
     Cc = x.shape[-1]
     ss = torch.empty(2 * Cc, dtype=torch.float32, device=x.device)
     L.call('amb_norm_eval', _p(gamma), _p(beta), _p(rm), _p(rv), eps, _p(ss[:Cc]), _p(ss[Cc:]), Cc, _stream())
-    out = torch.empty_like(x)
-    g = dense_geo(x)
-    L.call('amb_norm_apply', C.byref(g), _p(x), _p(ss[:Cc]), _p(ss[Cc:]), C.c_void_p(0), C.c_void_p(0), act, _p(out),
+    fill = token is not None
+    out = torch.zeros_like(x) if (m is not None and not fill) else torch.empty_like(x)
+    g = m.geo(x, True) if m is not None else dense_geo(x)
+    tok = token.reshape(-1).contiguous() if fill else None
+    L.call('amb_norm_apply', C.byref(g), _p(x), _p(ss[:Cc]), _p(ss[Cc:]), C.c_void_p(0), _p(tok), act, _p(out),
            _stream())
     return out
+
+
+def batch_norm_eval(x, gamma, beta, rm, rv, eps, act):
+    return norm_eval(x, gamma, beta, rm, rv, eps, act)
 
 
 class AddFn(torch.autograd.Function):
@@ -395,13 +420,17 @@ class PatchLossFn(torch.autograd.Function):
 
 
 def hard_mask(loss_pred: torch.Tensor, len_loss: int, len_keep: int, seed: int = 0, offset: int = 0,
-              want_mask: bool = True):
-    """Returns (hard indices (B,len_loss) int32 in ascending-loss order, mask (B,L) uint8 or None)."""
+              want_mask: bool = True, want_order: bool = False):
+    """Returns (hard (B,len_loss) int32 in ascending-loss order, mask (B,L) uint8 or None[, order (B,L) int32])."""
     loss_pred = loss_pred.float().contiguous()
     B, Lp = loss_pred.shape
     hard = torch.empty((B, max(len_loss, 1)), dtype=torch.int32, device=loss_pred.device)
     mask = torch.empty((B, Lp), dtype=torch.uint8, device=loss_pred.device) if want_mask else None
-    L.call('amb_hard_mask', _p(loss_pred), B, Lp, len_loss, len_keep, seed, offset, _p(hard), _p(mask), _stream())
+    order = torch.empty((B, Lp), dtype=torch.int32, device=loss_pred.device) if want_order else None
+    L.call('amb_hard_mask', _p(loss_pred), B, Lp, len_loss, len_keep, seed, offset, _p(hard), _p(order), _p(mask),
+           _stream())
+    if want_order:
+        return hard[:, :len_loss], mask, order
     return hard[:, :len_loss], mask
 
 
@@ -409,11 +438,11 @@ def ema_update_(ema_flat: torch.Tensor, model_flat: torch.Tensor, decay: float):
     L.call('amb_ema_update', _p(ema_flat), _p(model_flat), ema_flat.numel(), float(decay), _stream())
 
 
-def adamw_step_(p, g, m, v, lr, betas, eps, wd, step, max_norm: Optional[float]):
+def adamw_step_(p, g, m, v, lr, betas, eps, wd, step, max_norm: Optional[float], gscale: float = 1.0):
     gn = None
     if max_norm is not None:
         gn = torch.zeros(1, dtype=torch.float64, device=p.device)
         L.call('amb_sumsq', _p(g), g.numel(), _p(gn), _stream())
     L.call('amb_adamw_step', _p(p), _p(g), _p(m), _p(v), p.numel(), lr, betas[0], betas[1], eps, wd, step, _p(gn),
-           0.0 if max_norm is None else float(max_norm), _stream())
+           0.0 if max_norm is None else float(max_norm), float(gscale), _stream())
     return gn

@@ -1,0 +1,190 @@
+"""Step driver for the pre-training hot path: what P/pretrain.py:388-411 and P/pretrain_AntoMask.py:383-441 do per
+iteration, re-designed for one B200 per process.
+
+  * all float parameters and float buffers live in ONE fp32 arena ([live params | dead params | buffers]) and all live
+    gradients in another: the EMA teacher update, the global-norm clip and AdamW are each a single vectorised kernel
+    over the arena instead of 131 per-tensor chains, and the DDP gradient exchange is one NCCL all-reduce
+  * no host synchronisation inside a step (`mask_rng='device'`): masks, work-lists, loss, clip coefficient and the
+    hard-mask top-k all stay on the device
+  * data parallel: batch sharded across ranks, NCCL only for the gradient all-reduce (and SyncBN statistics when the
+    decoder was built with sbn=True) — P/pretrain_DDP.py:196-234
+"""
+from __future__ import annotations
+
+import copy
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from . import AnatoMask as anatomask_mod
+from . import spark3D
+from .decoder3D import LightDecoder
+from .encoder3D import SparseEncoder
+from .STUNet_head import STUNet
+
+STUNET_SIZES = {'S': (16, 1), 'B': (32, 1), 'L': (64, 2), 'H': (96, 3)}     # base width, blocks per stage
+
+
+def build_model(size: str = 'B', input_size=(128, 128, 128), anatomask: bool = True, mask_ratio: float = 0.6,
+                sbn: bool = False, device='cuda', base: Optional[int] = None, depth: Optional[int] = None) -> nn.Module:
+    """The construction of P/pretrain.py:180-212 (STUNet head → SparseEncoder → LightDecoder → SparK)."""
+    b, d = STUNET_SIZES[size] if base is None else (base, depth or 1)
+    head = STUNet(1, 1, depth=[d] * 6, dims=[b * x for x in (1, 2, 4, 8, 16, 16)],
+                  pool_op_kernel_sizes=[[2, 2, 2]] * 4 + [[1, 1, 1]], conv_kernel_sizes=[[3, 3, 3]] * 6)
+    enc = SparseEncoder(head, input_size=input_size, sbn=sbn)
+    dec = LightDecoder(enc.downsample_ratio, sbn=sbn, width=16 * b, out_channel=1)
+    cls = anatomask_mod.SparK if anatomask else spark3D.SparK
+    return cls(sparse_encoder=enc, dense_decoder=dec, mask_ratio=mask_ratio, densify_norm='in', sbn=sbn).to(device)
+
+
+def dead_parameter_names(model: spark3D.SparK) -> List[str]:
+    """Parameters the step never touches: densify levels the 4-block decoder does not consume."""
+    n_live = len(model.dense_decoder.dec)
+    pre = tuple(f'{grp}.{i}' for i in range(n_live, model.hierarchy) for grp in ('densify_norms', 'densify_projs', 'mask_tokens'))
+    return [n for n, _ in model.named_parameters() if n.startswith(pre)]
+
+
+class ParamArena:
+    """Re-homes a module's float parameters/buffers into one contiguous fp32 buffer (views keep their names/shapes)."""
+
+    def __init__(self, module: nn.Module, dead: List[str], with_grads: bool):
+        dev = next(module.parameters()).device
+        named_p = list(module.named_parameters())
+        live = [(n, p) for n, p in named_p if n not in dead]
+        deadp = [(n, p) for n, p in named_p if n in dead]
+        fbuf = [(n, b) for n, b in module.named_buffers() if b.is_floating_point()]
+        self.int_buffers = [(n, b) for n, b in module.named_buffers() if not b.is_floating_point()]
+        pad = lambda k: (k + 3) // 4 * 4
+        self.n_live = pad(sum(p.numel() for _, p in live))
+        total = self.n_live + pad(sum(p.numel() for _, p in deadp)) + pad(sum(b.numel() for _, b in fbuf))
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.offsets: Dict[str, Tuple[int, int]] = {}
+        starts = (0, self.n_live, self.n_live + pad(sum(p.numel() for _, p in deadp)))
+        for group, off in zip((live, deadp, fbuf), starts):
+            for n, t in group:
+                k = t.numel()
+                view = self.flat[off:off + k].view(t.shape)
+                view.copy_(t.data)
+                t.data = view
+                self.offsets[n] = (off, k)
+                off += k
+        self.grad = None
+        if with_grads:
+            self.grad = torch.zeros(self.n_live, dtype=torch.float32, device=dev)
+            for n, p in live:
+                o, k = self.offsets[n]
+                p.grad = self.grad[o:o + k].view(p.shape)
+        if self.int_buffers:
+            self.iflat = torch.zeros(len(self.int_buffers), dtype=torch.int64, device=dev)
+            for i, (_, b) in enumerate(self.int_buffers):
+                self.iflat[i] = b
+                b.data = self.iflat[i]
+        else:
+            self.iflat = None
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+
+def lr_at_epoch(epoch: int, base_lr: float, warmup: int = 20, max_epochs: int = 1000, warmup_start_lr: float = 1e-6,
+                eta_min: float = 0.0) -> float:
+    """Closed form of N/training/lr_scheduler/LinearWarmupCosine.py as the scripts use it (stepped per epoch)."""
+    if epoch < warmup:
+        return warmup_start_lr + epoch * (base_lr - warmup_start_lr) / max(1, warmup - 1)
+    return eta_min + 0.5 * (base_lr - eta_min) * (1 + math.cos(math.pi * (epoch - warmup) / (max_epochs - warmup)))
+
+
+def ema_decay_at_epoch(epoch: int, epochs: int) -> float:
+    """P/pretrain_AntoMask.py:383-386."""
+    q = epochs // 4
+    return 0.999 + epoch / q * (0.9999 - 0.999) if epoch < q else 0.9999
+
+
+class PretrainEngine:
+    """One process = one GPU.  `step()` is the AnatoMask iteration (teacher fwd → hard mask → student fwd/bwd → clip +
+    AdamW → EMA), `spark_step()` the plain SparK iteration."""
+
+    def __init__(self, model: spark3D.SparK, lr: float = 1e-4, weight_decay: float = 1e-5, clip: float = 12.0,
+                 betas=(0.9, 0.999), eps: float = 1e-8, epochs: int = 1000, anatomask: bool = True,
+                 mask_rng: str = 'device', process_group=None):
+        self.model = model
+        self.lr, self.wd, self.clip, self.betas, self.eps, self.epochs = lr, weight_decay, clip, betas, eps, epochs
+        self.dead = dead_parameter_names(model)
+        self.teacher = None
+        if anatomask:
+            self.teacher = copy.deepcopy(model)          # timm ModelEma: deepcopy → eval → no grad
+            self.teacher.eval()
+            for p in self.teacher.parameters():
+                p.requires_grad_(False)
+            self.teacher.mask_rng = mask_rng
+            self.tarena = ParamArena(self.teacher, self.dead, with_grads=False)
+        self.arena = ParamArena(model, self.dead, with_grads=True)
+        self.m = torch.zeros_like(self.arena.grad)
+        self.v = torch.zeros_like(self.arena.grad)
+        self.t = 0
+        self.group = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+        self.mask_rng = mask_rng
+        self._rng_calls = 0
+
+    # ---- pieces ---------------------------------------------------------------------------------------------
+    def random_mask(self, B: int, device) -> torch.Tensor:
+        m = self.model
+        if self.mask_rng == 'device':                    # len_keep smallest of B×L counter-based uniforms, on device
+            self._rng_calls += 1
+            L = m.fmap_h * m.fmap_w * m.fmap_d
+            zeros = torch.zeros(B, L, dtype=torch.float32, device=device)
+            _, mk = ops.hard_mask(zeros, 0, m.len_keep, seed=0xA11CE, offset=self._rng_calls * B * L)
+            return mk.bool().view(B, 1, m.fmap_h, m.fmap_w, m.fmap_d)
+        return m.mask(B, device)
+
+    def _optimise(self, lr: float):
+        a = self.arena
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(a.grad, group=self.group)
+        self.t += 1
+        ops.adamw_step_(a.flat[:a.n_live], a.grad, self.m, self.v, lr, self.betas, self.eps, self.wd, self.t,
+                        self.clip, 1.0 / self.world)
+
+    def ema_update(self, decay: float):
+        ops.ema_update_(self.tarena.flat, self.arena.flat, decay)
+        if self.tarena.iflat is not None:                # int64 num_batches_tracked: lerp then truncate (timm copy_)
+            ti, si = self.tarena.iflat, self.arena.iflat
+            ti.copy_(ti * decay + (1. - decay) * si)
+
+    # ---- steps ----------------------------------------------------------------------------------------------
+    def spark_step(self, inp: torch.Tensor, active: Optional[torch.Tensor] = None, epoch: int = 0) -> torch.Tensor:
+        self.model.train()
+        if active is None:
+            active = self.random_mask(inp.shape[0], inp.device)
+        rec = self.model.reconstruct(inp, active)
+        loss, _ = ops.PatchLossFn.apply(inp, rec, active[:, 0].to(torch.uint8).contiguous(), True)
+        self.arena.zero_grad()
+        loss.backward()
+        self._optimise(lr_at_epoch(epoch, self.lr, max_epochs=self.epochs))
+        return loss.detach()
+
+    def step(self, inp: torch.Tensor, epoch: int = 0, mask1: Optional[torch.Tensor] = None):
+        """P/pretrain_AntoMask.py:419-440.  Returns (loss, hard mask, teacher per-patch loss) — all on device."""
+        self.model.train()
+        B = inp.shape[0]
+        if mask1 is None:
+            mask1 = self.random_mask(B, inp.device)
+        with torch.no_grad():
+            rec1 = self.teacher.reconstruct(inp, mask1)
+            recon = self.teacher.teacher_loss(inp, rec1, mask1)
+        mask, _ = self.teacher.generate_mask(recon, guide=True, epoch=epoch, total_epoch=self.epochs - 1)
+        rec = self.model.reconstruct(inp, mask)
+        loss, _ = self.model.forward_loss(inp, rec, mask)
+        self.arena.zero_grad()
+        loss.backward()
+        self._optimise(lr_at_epoch(epoch, self.lr, max_epochs=self.epochs))
+        self.ema_update(ema_decay_at_epoch(epoch, self.epochs))
+        return loss.detach(), mask, recon

@@ -150,7 +150,7 @@ typedef struct amb_geo {
 int amb_norm_stats(const amb_geo* g, const void* x, double* sums, void* stream);
 int amb_norm_finalize(const amb_geo* g, const double* sums, const float* gamma, const float* beta, float eps,
                       float* scale, float* shift, float* saved, float* running_mean, float* running_var,
-                      long* num_batches_tracked, float momentum, void* stream);
+                      long* num_batches_tracked, float momentum, const double* n_total, void* stream);
 int amb_norm_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                   float eps, float* scale, float* shift, int C, void* stream);
 int amb_norm_apply(const amb_geo* g, const void* x, const float* scale, const float* shift, const void* residual,
@@ -160,7 +160,12 @@ int amb_norm_bwd_reduce(const amb_geo* g, const void* dout, const void* x, const
                         double* sums, double* dtoken, void* stream);
 int amb_norm_bwd_apply(const amb_geo* g, const void* dout, const void* x, const void* residual,
                        const float* scale, const float* shift, const float* saved, const double* sums, int act,
-                       int fill, void* dx, void* dres, float* dgamma, float* dbeta, void* stream);
+                       int fill, void* dx, void* dres, float* dgamma, float* dbeta, const double* n_total,
+                       void* stream);
+/* n_total (optional, device): number of voxels the statistics in `sums` were pooled over when they were summed
+ * across ranks (SparseSyncBatchNorm3d / nn.SyncBatchNorm, P/encoder3D.py:43, P/decoder3D.py:42-43); NULL = local.
+ * amb_count_voxels writes the local count (as double) so that it can ride in the same all-reduce as the sums.   */
+int amb_count_voxels(const amb_geo* g, double* out, void* stream);
 /* plain elementwise add (decoder skip: x + to_dec[i], P/decoder3D.py:58): out = a + b, n bf16 elements */
 int amb_add(const void* a, const void* b, void* out, long n, void* stream);
 
@@ -181,13 +186,15 @@ int amb_patch_loss_bwd(const float* inp, const float* rec, const uint8_t* active
  * mask_out (B, L) uint8: len_keep visible patches drawn uniformly from the non-hard ones with a counter-based
  * device RNG (seed, offset) — "throughput mode"; parity mode replays numpy's shuffle on the host from `hard`.  */
 int amb_hard_mask(const float* loss_pred, int B, int L, int len_loss, int len_keep, unsigned long long seed,
-                  unsigned long long offset, int* hard, uint8_t* mask_out, void* stream);
+                  unsigned long long offset, int* hard, int* order /* optional (B,L): full ascending argsort */,
+                  uint8_t* mask_out, void* stream);
 
 /* ---- flat-arena optimiser pieces: EMA teacher (timm ModelEma.update), grad-norm clip + AdamW ------------------- */
 int amb_ema_update(float* ema, const float* model, long n, double decay, void* stream);   /* ema = ema*d + (1-d)*model, fp32 products rounded separately like torch */
 int amb_sumsq(const float* g, long n, double* out, void* stream);                 /* out[0] += Σ g² */
 int amb_adamw_step(float* p, const float* g, float* m, float* v, long n, double lr, double beta1, double beta2,
-                   double eps, double weight_decay, int step, const double* gnorm_sq, double max_norm, void* stream);
+                   double eps, double weight_decay, int step, const double* gnorm_sq, double max_norm,
+                   double gscale /* g is multiplied by this first: 1/world after a SUM all-reduce */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,81 @@
+"""CPU-only checks: C-ABI library loads and exports every symbol of include/anatomask_b200.h; the host mirror keeps the
+reference's checkpoint-key contract; arena / schedules / loud failure without a GPU."""
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import reference_port as rp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from anatomask_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'anatomask_b200.h')).read()
+    declared = set(re.findall(r'\b(amb_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations parsed'
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in the header but not exported'
+    assert declared == set(_lib.EXPORTED), declared ^ set(_lib.EXPORTED)
+    assert lib.amb_version() == 100 and lib.amb_sm_arch() == 100
+
+
+@pytest.mark.parametrize('name', ['tiny', 'S64', 'B64'])
+def test_state_dict_contract_matches_reference(name):
+    from anatomask_b200.trainer import build_model
+    cfg = rp.CONFIGS[name]
+    model = build_model(base=cfg.base, depth=cfg.depth, input_size=cfg.input_size, device='cpu')
+    sd = model.state_dict()
+    shapes = rp.param_shapes(cfg)
+    assert set(sd.keys()) == set(shapes.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == shapes[k][0], k
+    model.load_state_dict(rp.make_state(cfg, 1))          # loads both ways
+    assert (model.len_keep, model.fmap_h) == (cfg.len_keep, cfg.fmap[0])
+
+
+def test_arena_views_and_dead_parameters():
+    from anatomask_b200.trainer import build_model, ParamArena, dead_parameter_names
+    cfg = rp.CONFIGS['tiny']
+    model = build_model(base=cfg.base, input_size=cfg.input_size, device='cpu')
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    dead = dead_parameter_names(model)
+    assert sorted(dead) == sorted(k for k in rp.param_shapes(cfg)
+                                  if k.startswith(('densify_norms.4', 'densify_projs.4', 'mask_tokens.4')))
+    arena = ParamArena(model, dead, with_grads=True)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    live = [n for n in rp.live_param_names(cfg)]
+    assert arena.n_live >= sum(before[n].numel() for n in live)
+    for n, p in model.named_parameters():
+        assert (p.grad is None) == (n in dead), n
+        o, k = arena.offsets[n]
+        assert p.data_ptr() == arena.flat.data_ptr() + 4 * o
+    arena.flat.mul_(2)
+    assert torch.allclose(model.mask_tokens[0], 2 * before['mask_tokens.0'])
+
+
+def test_schedules():
+    from anatomask_b200.trainer import lr_at_epoch, ema_decay_at_epoch
+    assert lr_at_epoch(0, 1e-4) == pytest.approx(1e-6)
+    assert lr_at_epoch(20, 1e-4) == pytest.approx(1e-4)
+    assert lr_at_epoch(1000, 1e-4) == pytest.approx(0.0, abs=1e-12)
+    assert ema_decay_at_epoch(0, 1000) == 0.999 and ema_decay_at_epoch(500, 1000) == 0.9999
+    assert ema_decay_at_epoch(125, 1000) == pytest.approx(rp.ema_decay(125, 1000))
+
+
+def test_cpu_tensors_fail_loudly():
+    from anatomask_b200.trainer import build_model
+    cfg = rp.CONFIGS['tiny']
+    model = build_model(base=cfg.base, input_size=cfg.input_size, device='cpu')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        model(torch.zeros(1, 1, 32, 32, 32), active_b1ff=torch.ones(1, 1, 2, 2, 2, dtype=torch.bool))
+
+
+def test_unsupported_layers_raise_like_the_reference():
+    from anatomask_b200 import encoder3D
+    with pytest.raises(NotImplementedError):
+        encoder3D.SparseEncoder.dense_model_to_sparse(torch.nn.Conv1d(1, 1, 1))
