@@ -23,6 +23,29 @@ def _p(t: Optional[torch.Tensor]):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+# bench.py sets PROFILE to a list: every conv-family launch is then bracketed by CUDA events on the launching stream
+# and recorded as (kind, algorithmic FLOPs, start, end) — the live roofline measurement (no effect when None).
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, kind: str, flops: float):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
+        return False
+
+
 def require_cuda(t: torch.Tensor):
     if not t.is_cuda:
         raise RuntimeError('anatomask_b200 runs on a B200 only: got a CPU tensor (there is no CPU fallback)')
@@ -40,6 +63,7 @@ class MaskCtx:
             a = a[:, 0]
         self.active = a.to(torch.uint8).contiguous()
         self.N, self.fd, self.fh, self.fw = self.active.shape
+        self.frac_hint = 1.0          # visible fraction, host-side hint for FLOP accounting only (never synchronises)
         n = self.active.numel()
         self.list = torch.empty(n, dtype=torch.int32, device=a.device)
         self.count = torch.empty(1, dtype=torch.int32, device=a.device)
@@ -146,15 +170,21 @@ class ConvFn(torch.autograd.Function):
             Cout = weight.shape[1]
             wp = _pack(weight, 64, Cout, Cin, 1, 64, Cout * 64)
             y = torch.empty((N, 2 * D, 2 * H, 2 * W, Cout), dtype=bf16, device=x.device)
-            _conv_call(L.OP_CONVT, impl, (N, D, H, W), Cin, Cout, 4, 2, x, y, wp, bias)
+            flops = 2.0 * N * D * H * W * 64 * Cin * Cout
+            with _Timed('convT_fwd', flops):
+                _conv_call(L.OP_CONVT, impl, (N, D, H, W), Cin, Cout, 4, 2, x, y, wp, bias)
         else:
             Cout = weight.shape[0]
             wp = _pack(weight, k3, Cout, Cin, 1, Cin * k3, k3)
             shape = (N, D // stride, H // stride, W // stride, Cout)
             y = torch.zeros(shape, dtype=bf16, device=x.device) if m is not None else \
                 torch.empty(shape, dtype=bf16, device=x.device)
-            _conv_call(L.OP_CONV, impl, (N, D, H, W), Cin, Cout, k, stride, x, y, wp, bias, m, sparse=m is not None)
+            flops = 2.0 * N * (D // stride) * (H // stride) * (W // stride) * k3 * Cin * Cout * \
+                (m.frac_hint if m is not None else 1.0)
+            with _Timed('conv_fwd', flops):
+                _conv_call(L.OP_CONV, impl, (N, D, H, W), Cin, Cout, k, stride, x, y, wp, bias, m, sparse=m is not None)
         ctx.save_for_backward(x, weight)
+        ctx.flops = flops
         ctx.cfg = (k, stride, m, transposed, impl, bias is not None)
         return y
 
@@ -171,12 +201,14 @@ class ConvFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 wp = _pack(weight, 64, Cin, Cout, 1, Cout * 64, 64)
                 dx = torch.empty_like(x)
-                _conv_call(L.OP_CONVT_DGRAD, impl, (N, D, H, W), Cin, Cout, 4, 2, dy, dx, wp)
+                with _Timed('convT_dgrad', ctx.flops):
+                    _conv_call(L.OP_CONVT_DGRAD, impl, (N, D, H, W), Cin, Cout, 4, 2, dy, dx, wp)
             if ctx.needs_input_grad[1]:
                 dwp = torch.zeros((64, Cout, Cin), dtype=torch.float32, device=x.device)
                 a = L.WgradArgs(L.OP_CONVT, impl, N, D, H, W, Cin, Cout, 4, 2, x.data_ptr(), dy.data_ptr(),
                                 dwp.data_ptr(), 1, 1, 1, 0, 0, torch.cuda.current_stream().cuda_stream)
-                L.call('amb_conv_wgrad', C.byref(a))
+                with _Timed('convT_wgrad', ctx.flops):
+                    L.call('amb_conv_wgrad', C.byref(a))
                 dw = torch.empty_like(weight)
                 L.call('amb_unpack_wgrad', _p(dwp), _p(dw), 64, Cout, Cin, 1, 64, Cout * 64, _stream())
         else:
@@ -185,15 +217,17 @@ class ConvFn(torch.autograd.Function):
                 wp = _pack(weight, k3, Cin, Cout, 1, k3, Cin * k3)
                 need_zero = m is not None or (k == 1 and stride == 2)
                 dx = torch.zeros_like(x) if need_zero else torch.empty_like(x)
-                _conv_call(L.OP_CONV_DGRAD, impl, (N, D, H, W), Cin, Cout, k, stride, dy, dx, wp, None, m,
-                           sparse=m is not None)
+                with _Timed('conv_dgrad', ctx.flops):
+                    _conv_call(L.OP_CONV_DGRAD, impl, (N, D, H, W), Cin, Cout, k, stride, dy, dx, wp, None, m,
+                               sparse=m is not None)
             if ctx.needs_input_grad[1]:
                 dwp = torch.zeros((k3, Cout, Cin), dtype=torch.float32, device=x.device)
                 a = L.WgradArgs(L.OP_CONV, impl, N, D, H, W, Cin, Cout, k, stride, x.data_ptr(), dy.data_ptr(),
                                 dwp.data_ptr(), 1 if m is None else m.fd, 1 if m is None else m.fh,
                                 1 if m is None else m.fw, 0 if m is None else m.list.data_ptr(),
                                 0 if m is None else m.count.data_ptr(), torch.cuda.current_stream().cuda_stream)
-                L.call('amb_conv_wgrad', C.byref(a))
+                with _Timed('conv_wgrad', ctx.flops):
+                    L.call('amb_conv_wgrad', C.byref(a))
                 dw = torch.empty_like(weight)
                 L.call('amb_unpack_wgrad', _p(dwp), _p(dw), k3, Cout, Cin, 1, Cin * k3, k3, _stream())
         if has_bias and ctx.needs_input_grad[2]:

@@ -100,6 +100,7 @@ class SparK(nn.Module):
         ops.require_cuda(inp_bchwd)
         encoder3D._cur_active = active_b1ff
         m = encoder3D._mask_ctx()
+        m.frac_hint = self.len_keep / float(self.fmap_h * self.fmap_w * self.fmap_d)
         # the stem kernel applies the visibility mask to the raw input itself (P/spark3D.py:104-107 folded in)
         fea_bcffs: List[torch.Tensor] = self.sparse_encoder(inp_bchwd)
         fea_bcffs = list(reversed(fea_bcffs))
