@@ -51,11 +51,16 @@ class BasicResBlock(nn.Module):
             y, sc = ops.StemFn.apply(x, c1.weight, c1.bias, c3.weight, c3.bias, m)
         else:
             xi = ops.to_internal(x)
-            y = ops.conv3d(xi, c1.weight, c1.bias, c1.kernel_size[0], stride, m)
+            # Σy / Σy² of the visible outputs come out of the conv epilogue (no separate statistics pass)
+            s1 = ops.new_stats(c1.out_channels, xi.device) if ops.fused_stats_ok(c1.in_channels, c1.out_channels) else None
+            y = ops.conv3d(xi, c1.weight, c1.bias, c1.kernel_size[0], stride, m, stats=s1)
             sc = ops.conv3d(xi, c3.weight, c3.bias, 1, stride, m) if c3 is not None else xi
-        y = ops.masked_norm(y, self.norm1.weight, self.norm1.bias, self.norm1.eps, m, ACT_LRELU)
-        y = ops.conv3d(y, c2.weight, c2.bias, c2.kernel_size[0], 1, m)
-        y = ops.masked_norm(y, self.norm2.weight, self.norm2.bias, self.norm2.eps, m, ACT_LRELU, residual=sc)
+        if c1.in_channels == 1:
+            s1 = None
+        y = ops.masked_norm(y, self.norm1.weight, self.norm1.bias, self.norm1.eps, m, ACT_LRELU, sums=s1)
+        s2 = ops.new_stats(c2.out_channels, y.device) if ops.fused_stats_ok(c2.in_channels, c2.out_channels) else None
+        y = ops.conv3d(y, c2.weight, c2.bias, c2.kernel_size[0], 1, m, stats=s2)
+        y = ops.masked_norm(y, self.norm2.weight, self.norm2.bias, self.norm2.eps, m, ACT_LRELU, residual=sc, sums=s2)
         return ops.to_external(y)
 
 

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libanatomask_b200.so')
 vp, i32, i64, f32, f64, u64 = C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_double, C.c_ulonglong
 
 OP_CONV, OP_CONV_DGRAD, OP_CONVT, OP_CONVT_DGRAD = 0, 1, 2, 3
-IMPL_AUTO, IMPL_DIRECT, IMPL_TCGEN05 = 0, 1, 2
+IMPL_AUTO, IMPL_DIRECT, IMPL_TCGEN05, IMPL_TCGEN05_V1 = 0, 1, 2, 3
 ACT_NONE, ACT_LRELU, ACT_RELU6 = 0, 1, 2
 
 

@@ -197,10 +197,18 @@ extern "C" int amb_conv(const amb_conv_args* a) {
     AMB_CHECK((a->active_list == nullptr) == (a->active_count == nullptr), AMB_ERR_ARG, "amb_conv: list and count go together");
     AMB_CHECK(a->active_list == nullptr || a->active != nullptr, AMB_ERR_ARG, "amb_conv: active_list needs active");
     if (a->impl != AMB_IMPL_DIRECT) {
+        // halo-plane kernel (v2) for dense 3x3x3 s1; the per-tap kernel (v1) everywhere else, and wherever the
+        // active-patch work-list lets it skip masked tiles outright (patch edge >= 8 at the output resolution)
+        const bool list_pays = a->active_list != nullptr && p.lgPv >= 3;
+        if (a->impl != AMB_IMPL_TCGEN05_V1 && !list_pays) {
+            int r2 = igemm2_conv(p, a);
+            if (r2 < 0) return r2;
+            if (r2 == 1) return 0;
+        }
         int r = igemm_conv(p, a);
         if (r < 0) return r;
         if (r == 1) return 0;
-        AMB_CHECK(a->impl != AMB_IMPL_TCGEN05, AMB_ERR_UNSUPPORTED,
+        AMB_CHECK(a->impl == AMB_IMPL_AUTO, AMB_ERR_UNSUPPORTED,
                   "amb_conv: shape not supported by the tcgen05 kernel (Cx=%d Cy=%d): %s", p.Cx, p.Cy, amb_last_error());
     }
     return direct_conv(p, a);

@@ -78,9 +78,9 @@ __global__ void __launch_bounds__(512) reduce_kernel(Geo g, const bf16* __restri
                                                      const float* __restrict__ shift, const float* __restrict__ saved,
                                                      int act, int fill, double* __restrict__ sums,
                                                      double* __restrict__ dtoken) {
-    extern __shared__ double sacc[];          // [C][2] (+ [C] for dtoken)
+    extern __shared__ float sacc[];           // [3][C]: Σ, Σ·, Σ_inactive — per-CTA fp32 partials, fp64 across CTAs
     const int CG = g.C / 8;
-    for (int i = threadIdx.x; i < g.C * 3; i += blockDim.x) sacc[i] = 0.0;
+    for (int i = threadIdx.x; i < g.C * 3; i += blockDim.x) sacc[i] = 0.f;
     __syncthreads();
     float a0[8], a1[8], a2[8];
 #pragma unroll
@@ -127,17 +127,31 @@ __global__ void __launch_bounds__(512) reduce_kernel(Geo g, const bf16* __restri
             }
         }
     }
+    // lanes of a warp that share a channel group (lane % CG equal) are combined with shuffles first
+    const bool shfl = CG < 32 && (CG & (CG - 1)) == 0 && (blockDim.x & 31) == 0;
+    if (shfl) {
+        for (int o = CG; o < 32; o <<= 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sacc[(cg * 8 + j) * 2 + 0], (double)a0[j]);
-        atomicAdd(&sacc[(cg * 8 + j) * 2 + 1], (double)a1[j]);
-        if (MODE == 1 && fill) atomicAdd(&sacc[g.C * 2 + cg * 8 + j], (double)a2[j]);
+            for (int j = 0; j < 8; ++j) {
+                a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], o);
+                a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], o);
+                if (MODE == 1) a2[j] += __shfl_xor_sync(0xffffffffu, a2[j], o);
+            }
+        }
+    }
+    if (!shfl || (threadIdx.x & 31) < CG) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&sacc[cg * 8 + j], a0[j]);
+            atomicAdd(&sacc[g.C + cg * 8 + j], a1[j]);
+            if (MODE == 1 && fill) atomicAdd(&sacc[2 * g.C + cg * 8 + j], a2[j]);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < g.C; i += blockDim.x) {
-        atomicAdd(&sums[i], sacc[i * 2]);
-        atomicAdd(&sums[g.C + i], sacc[i * 2 + 1]);
-        if (MODE == 1 && fill && dtoken) atomicAdd(&dtoken[i], sacc[g.C * 2 + i]);
+        atomicAdd(&sums[i], (double)sacc[i]);
+        atomicAdd(&sums[g.C + i], (double)sacc[g.C + i]);
+        if (MODE == 1 && fill && dtoken) atomicAdd(&dtoken[i], (double)sacc[2 * g.C + i]);
     }
 }
 
@@ -377,7 +391,7 @@ extern "C" int amb_norm_stats(const amb_geo* a, const void* x, double* sums, voi
     if (int e = make_geo(a, g)) return e;
     int CG = g.C / 8, block = pick_block(CG);
     if (block < 0) return block;
-    reduce_kernel<0><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(double), (cudaStream_t)stream>>>(
+    reduce_kernel<0><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>(
         g, (const bf16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, sums, nullptr);
     AMB_LAUNCH_CHECK();
     return 0;
@@ -423,7 +437,7 @@ extern "C" int amb_norm_bwd_reduce(const amb_geo* a, const void* dout, const voi
     AMB_CHECK(!fill || g.active, AMB_ERR_ARG, "densify backward needs the active mask");
     int CG = g.C / 8, block = pick_block(CG);
     if (block < 0) return block;
-    reduce_kernel<1><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(double), (cudaStream_t)stream>>>(
+    reduce_kernel<1><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>(
         g, (const bf16*)x, (const bf16*)dout, (const bf16*)residual, scale, shift, saved, act, fill, sums, dtoken);
     AMB_LAUNCH_CHECK();
     return 0;

@@ -17,7 +17,7 @@ def is_pow2n(x):
     return x > 0 and (x & (x - 1) == 0)
 
 
-def _bn(bn: nn.Module, x, act):
+def _bn(bn: nn.Module, x, act, sums=None):
     """BatchNorm3d / SyncBatchNorm forward in the module's current mode."""
     if isinstance(bn, nn.InstanceNorm3d):
         raise NotImplementedError('LightDecoder(use_IN=True) has no sm_100a kernel (no shipped script uses it)')
@@ -29,7 +29,7 @@ def _bn(bn: nn.Module, x, act):
                 group = bn.process_group if bn.process_group is not None else dist.group.WORLD
         mom = 0.1 if bn.momentum is None else bn.momentum
         return ops.batch_norm_train(x, bn.weight, bn.bias, bn.eps, act,
-                                    (bn.running_mean, bn.running_var, bn.num_batches_tracked), mom, group)
+                                    (bn.running_mean, bn.running_var, bn.num_batches_tracked), mom, group, sums)
     return ops.batch_norm_eval(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, act)
 
 
@@ -44,10 +44,14 @@ class UNetBlock(nn.Module):
 
     def forward_internal(self, x):
         x = ops.conv_transpose3d(x, self.up_sample.weight, self.up_sample.bias)
-        x = ops.conv3d(x, self.conv[0].weight, None, 3, 1)
-        x = _bn(self.conv[1], x, ACT_RELU6)
-        x = ops.conv3d(x, self.conv[3].weight, None, 3, 1)
-        return _bn(self.conv[4], x, ACT_NONE)
+        c0, c3 = self.conv[0], self.conv[3]
+        # training-mode BN statistics come out of the conv epilogue (Σy, Σy² per channel)
+        s0 = ops.new_stats(c0.out_channels, x.device) if (self.conv[1].training and ops.fused_stats_ok(c0.in_channels, c0.out_channels)) else None
+        x = ops.conv3d(x, c0.weight, None, 3, 1, stats=s0)
+        x = _bn(self.conv[1], x, ACT_RELU6, s0)
+        s3 = ops.new_stats(c3.out_channels, x.device) if (self.conv[4].training and ops.fused_stats_ok(c3.in_channels, c3.out_channels)) else None
+        x = ops.conv3d(x, c3.weight, None, 3, 1, stats=s3)
+        return _bn(self.conv[4], x, ACT_NONE, s3)
 
     def forward(self, x):
         return ops.to_external(self.forward_internal(ops.to_internal(x)))

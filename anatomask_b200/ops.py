@@ -161,7 +161,7 @@ class ConvFn(torch.autograd.Function):
     2×8×8 tile fits a patch — masked tiles are never computed."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, k, stride, m, transposed, impl):
+    def forward(ctx, x, weight, bias, k, stride, m, transposed, impl, stats=None):
         require_cuda(x)
         x = x.contiguous()
         N, D, H, W, Cin = x.shape
@@ -172,7 +172,7 @@ class ConvFn(torch.autograd.Function):
             y = torch.empty((N, 2 * D, 2 * H, 2 * W, Cout), dtype=bf16, device=x.device)
             flops = 2.0 * N * D * H * W * 64 * Cin * Cout
             with _Timed('convT_fwd', flops):
-                _conv_call(L.OP_CONVT, impl, (N, D, H, W), Cin, Cout, 4, 2, x, y, wp, bias)
+                _conv_call(L.OP_CONVT, impl, (N, D, H, W), Cin, Cout, 4, 2, x, y, wp, bias, stats=stats)
         else:
             Cout = weight.shape[0]
             wp = _pack(weight, k3, Cout, Cin, 1, Cin * k3, k3)
@@ -182,7 +182,8 @@ class ConvFn(torch.autograd.Function):
             flops = 2.0 * N * (D // stride) * (H // stride) * (W // stride) * k3 * Cin * Cout * \
                 (m.frac_hint if m is not None else 1.0)
             with _Timed('conv_fwd', flops):
-                _conv_call(L.OP_CONV, impl, (N, D, H, W), Cin, Cout, k, stride, x, y, wp, bias, m, sparse=m is not None)
+                _conv_call(L.OP_CONV, impl, (N, D, H, W), Cin, Cout, k, stride, x, y, wp, bias, m, sparse=m is not None,
+                           stats=stats)
         ctx.save_for_backward(x, weight)
         ctx.flops = flops
         ctx.cfg = (k, stride, m, transposed, impl, bias is not None)
@@ -232,11 +233,21 @@ class ConvFn(torch.autograd.Function):
                 L.call('amb_unpack_wgrad', _p(dwp), _p(dw), k3, Cout, Cin, 1, Cin * k3, k3, _stream())
         if has_bias and ctx.needs_input_grad[2]:
             db = column_sums(dy, m if not transposed else None)
-        return dx, dw, db, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None
 
 
-def conv3d(x, weight, bias=None, k=3, stride=1, m: Optional[MaskCtx] = None, impl=L.IMPL_AUTO):
-    return ConvFn.apply(x, weight, bias, k, stride, m, False, impl)
+def fused_stats_ok(cin: int, cout: int) -> bool:
+    """The Σy/Σy² epilogue exists in the tcgen05 kernel only (channel counts it takes: multiples of 16)."""
+    return cin % 16 == 0 and cout % 16 == 0
+
+
+def new_stats(channels: int, device) -> torch.Tensor:
+    """(Σy[C], Σy²[C], n) accumulator handed to a conv (fused epilogue) and then to the norm that follows it."""
+    return torch.zeros(2 * channels + 1, dtype=torch.float64, device=device)
+
+
+def conv3d(x, weight, bias=None, k=3, stride=1, m: Optional[MaskCtx] = None, impl=L.IMPL_AUTO, stats=None):
+    return ConvFn.apply(x, weight, bias, k, stride, m, False, impl, stats)
 
 
 def conv_transpose3d(x, weight, bias=None, impl=L.IMPL_AUTO):
@@ -311,14 +322,15 @@ class NormFn(torch.autograd.Function):
     and one of (Σg, Σg·x̂) backward — SparseSyncBatchNorm3d / nn.SyncBatchNorm (P/encoder3D.py:43, P/decoder3D.py:42)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, token, eps, act, m, running, momentum, group=None):
+    def forward(ctx, x, gamma, beta, residual, token, eps, act, m, running, momentum, group=None, sums=None):
         x = x.contiguous()
         Cc = x.shape[-1]
         dev = x.device
         sparse = m is not None
         g = m.geo(x, True) if sparse else dense_geo(x)
-        sums = torch.zeros(2 * Cc + 1, dtype=torch.float64, device=dev)
-        L.call('amb_norm_stats', C.byref(g), _p(x), _p(sums), _stream())
+        if sums is None:            # not produced by the conv epilogue: one read pass over the visited voxels
+            sums = torch.zeros(2 * Cc + 1, dtype=torch.float64, device=dev)
+            L.call('amb_norm_stats', C.byref(g), _p(x), _p(sums), _stream())
         ntot = None
         if group is not None:
             import torch.distributed as dist
@@ -371,20 +383,20 @@ class NormFn(torch.autograd.Function):
         else:
             dgamma, dbeta = gb[:Cc], gb[Cc:]
         dtoken = sums[2 * Cc:].float().view(tshape) if fill else None
-        return dx, dgamma, dbeta, dres, dtoken, None, None, None, None, None, None
+        return dx, dgamma, dbeta, dres, dtoken, None, None, None, None, None, None, None
 
 
 def masked_norm(x, gamma, beta, eps, m: MaskCtx, act=L.ACT_NONE, residual=None, running=None, momentum=0.0,
-                group=None):
-    return NormFn.apply(x, gamma, beta, residual, None, eps, act, m, running, momentum, group)
+                group=None, sums=None):
+    return NormFn.apply(x, gamma, beta, residual, None, eps, act, m, running, momentum, group, sums)
 
 
 def densify_norm_fill(x, gamma, beta, token, eps, m: MaskCtx, running=None, momentum=0.0, group=None):
     return NormFn.apply(x, gamma, beta, None, token, eps, L.ACT_NONE, m, running, momentum, group)
 
 
-def batch_norm_train(x, gamma, beta, eps, act, running, momentum, group=None):
-    return NormFn.apply(x, gamma, beta, None, None, eps, act, None, running, momentum, group)
+def batch_norm_train(x, gamma, beta, eps, act, running, momentum, group=None, sums=None):
+    return NormFn.apply(x, gamma, beta, None, None, eps, act, None, running, momentum, group, sums)
 
 
 def norm_eval(x, gamma, beta, rm, rv, eps, act, m: Optional[MaskCtx] = None, token=None):

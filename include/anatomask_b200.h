@@ -46,7 +46,8 @@ extern "C" {
 
 #define AMB_IMPL_AUTO 0        /* tcgen05 implicit GEMM when the shape allows it, CUDA-core gather kernel otherwise */
 #define AMB_IMPL_DIRECT 1      /* force the CUDA-core gather kernel (differential testing)                          */
-#define AMB_IMPL_TCGEN05 2     /* force the tcgen05 kernel, error when the shape is unsupported                     */
+#define AMB_IMPL_TCGEN05 2     /* force a tcgen05 kernel (halo-plane v2 when it applies, else per-tap v1)          */
+#define AMB_IMPL_TCGEN05_V1 3  /* force the per-tap tcgen05 kernel (differential testing of v2)                    */
 
 const char* amb_last_error(void);
 int amb_version(void);

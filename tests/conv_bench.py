@@ -1,0 +1,67 @@
+"""Isolated conv-kernel timings (CUDA events, L2 flushed between iterations) for the layer shapes of STUNet-B @128³.
+   python tests/conv_bench.py [v1|v2|all]      → TFLOP/s per layer and pass (fwd / dgrad / wgrad)"""
+import ctypes as C
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from anatomask_b200 import ops, _lib as L  # noqa: E402
+
+bf16 = torch.bfloat16
+LAYERS = [  # name, Cin, Cout, S, N
+    ('dec3.conv0 64->64 @128', 64, 64, 128, 2), ('dec3.conv3 64->32 @128', 64, 32, 128, 2),
+    ('dec2.conv0 128->128 @64', 128, 128, 64, 2), ('dec2.conv3 128->64 @64', 128, 64, 64, 2),
+    ('dec1.conv0 256->256 @32', 256, 256, 32, 2), ('dec0.conv0 512->512 @16', 512, 512, 16, 2),
+]
+
+
+def time_it(fn, flush, iters=5):
+    fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return sorted(ms)[len(ms) // 2]
+
+
+def main(which):
+    dev = torch.device('cuda:0')
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    impls = {'v1': L.IMPL_TCGEN05_V1, 'v2': L.IMPL_TCGEN05}
+    if which != 'all':
+        impls = {which: impls[which]}
+    out = []
+    for name, ci, co, S, N in LAYERS:
+        x = torch.randn(N, S, S, S, ci, device=dev).to(bf16)
+        dy = torch.randn(N, S, S, S, co, device=dev).to(bf16)
+        w = torch.randn(co, ci, 3, 3, 3, device=dev) / (27 * ci) ** 0.5
+        wf = ops._pack(w, 27, co, ci, 1, ci * 27, 27)
+        wd = ops._pack(w, 27, ci, co, 1, 27, ci * 27)
+        y = torch.empty(N, S, S, S, co, dtype=bf16, device=dev)
+        dx = torch.empty_like(x)
+        dw = torch.zeros(27, co, ci, device=dev)
+        flops = 2.0 * N * S ** 3 * 27 * ci * co
+        row = {'layer': name}
+        for tag, impl in impls.items():
+            t = time_it(lambda: ops._conv_call(L.OP_CONV, impl, (N, S, S, S), ci, co, 3, 1, x, y, wf), flush)
+            row[f'fwd_{tag}'] = round(flops / t / 1e9, 1)
+            t = time_it(lambda: ops._conv_call(L.OP_CONV_DGRAD, impl, (N, S, S, S), ci, co, 3, 1, dy, dx, wd), flush)
+            row[f'dgrad_{tag}'] = round(flops / t / 1e9, 1)
+        a = L.WgradArgs(L.OP_CONV, L.IMPL_TCGEN05, N, S, S, S, ci, co, 3, 1, x.data_ptr(), dy.data_ptr(), dw.data_ptr(),
+                        1, 1, 1, 0, 0, torch.cuda.current_stream().cuda_stream)
+        t = time_it(lambda: L.call('amb_conv_wgrad', C.byref(a)), flush)
+        row['wgrad'] = round(flops / t / 1e9, 1)
+        print(json.dumps(row), flush=True)
+        out.append(row)
+    return out
+
+
+if __name__ == '__main__':
+    main(sys.argv[1] if len(sys.argv) > 1 else 'all')

@@ -29,6 +29,12 @@ CASES = [
     ('convT', dict(Cin=64, Cout=64, S=8, impl=T)), ('convT', dict(Cin=512, Cout=512, S=4, impl=T)),
     ('convT', dict(Cin=128, Cout=128, S=8, impl=T)), ('convT', dict(Cin=32, Cout=32, S=8, impl=T)),
     ('conv_stats', {}),
+    # halo-plane kernel (v2): dense 3x3x3 s1, Cin % 64 == 0, H >= 16
+    ('conv', dict(Cin=64, Cout=64, S=16, impl=T)), ('conv', dict(Cin=64, Cout=64, S=32, impl=T)),
+    ('conv', dict(Cin=128, Cout=64, S=16, impl=T)), ('conv', dict(Cin=64, Cout=128, S=32, impl=T, bias=False)),
+    ('conv', dict(Cin=256, Cout=256, S=16, impl=T)), ('conv', dict(Cin=64, Cout=32, S=24, impl=T)),
+    ('conv', dict(Cin=64, Cout=64, S=32, impl=T, masked=True, f=8)), ('conv', dict(Cin=512, Cout=512, S=16, N=1, impl=T)),
+    ('conv_stats', dict(Cin=64, Cout=64, S=32)),
 ]
 
 if __name__ == '__main__':
