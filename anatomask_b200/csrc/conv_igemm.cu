@@ -88,6 +88,7 @@ struct IgemmParams {
     int lgbn, lgbd, lgbh, lgbw;      // log2 of the tile box
     int Tn, Tz, Ty, Tx;              // dense tiling of an out view
     int n_ntiles, NT;
+    int T;                           // spatial tiles (independent TMEM accumulators) interleaved per CTA iteration
     int kchunks;                     // Cx / KC
     int stages;
     uint32_t stage_bytes, a_bytes, b_bytes;
@@ -96,34 +97,38 @@ struct IgemmParams {
 };
 
 struct TileCoord {
-    int g, n0, z0, y0, x0, nt;
+    int n0, z0, y0, x0;
+};
+struct SuperTile {
+    int g, nt;
+    long s0;            // first spatial tile; tiles s0 .. s0+T-1 (those < n_spatial) share group and N tile
 };
 
-__device__ __forceinline__ long num_tiles(const IgemmParams& P) {
+__device__ __forceinline__ long num_spatial(const IgemmParams& P) {
     const Plan& p = P.plan;
-    long per_group;
     if (P.list) {
         const int Pv = 1 << p.lgPv;
-        per_group = (long)(*P.count) * (Pv >> P.lgbd) * (Pv >> P.lgbh) * (Pv >> P.lgbw);
-    } else {
-        per_group = (long)P.Tn * P.Tz * P.Ty * P.Tx;
+        return (long)(*P.count) * (Pv >> P.lgbd) * (Pv >> P.lgbh) * (Pv >> P.lgbw);
     }
-    return per_group * p.n_groups * P.n_ntiles;
+    return (long)P.Tn * P.Tz * P.Ty * P.Tx;
 }
 
-__device__ __forceinline__ void decode_tile(const IgemmParams& P, long t, TileCoord& c) {
+__device__ __forceinline__ void decode_super(const IgemmParams& P, long w, long n_super, SuperTile& st) {
+    st.s0 = (w % n_super) * P.T;
+    w /= n_super;
+    st.nt = (int)(w % P.n_ntiles);
+    st.g = (int)(w / P.n_ntiles);
+}
+
+__device__ __forceinline__ void decode_spatial(const IgemmParams& P, long t, TileCoord& c) {
     const Plan& p = P.plan;
-    c.nt = (int)(t % P.n_ntiles);
-    t /= P.n_ntiles;
     if (P.list) {
         const int Pv = 1 << p.lgPv;
         const int sx = Pv >> P.lgbw, sy = Pv >> P.lgbh, sz = Pv >> P.lgbd;
         int ix = (int)(t % sx); t /= sx;
         int iy = (int)(t % sy); t /= sy;
         int iz = (int)(t % sz); t /= sz;
-        const long cnt = *P.count;
-        int pid = P.list[t % cnt];
-        c.g = (int)(t / cnt);
+        int pid = P.list[t];
         const int L = p.fd * p.fh * p.fw;
         c.n0 = pid / L;
         int l = pid % L;
@@ -134,8 +139,7 @@ __device__ __forceinline__ void decode_tile(const IgemmParams& P, long t, TileCo
         c.x0 = (int)(t % P.Tx) << P.lgbw; t /= P.Tx;
         c.y0 = (int)(t % P.Ty) << P.lgbh; t /= P.Ty;
         c.z0 = (int)(t % P.Tz) << P.lgbd; t /= P.Tz;
-        c.n0 = (int)(t % P.Tn) << P.lgbn;
-        c.g = (int)(t / P.Tn);
+        c.n0 = (int)t << P.lgbn;
     }
 }
 
@@ -187,27 +191,34 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const long ntiles = num_tiles(P);
+    const long n_spatial = num_spatial(P);
+    const long n_super = (n_spatial + P.T - 1) / P.T;
+    const long nwork = n_super * p.n_groups * P.n_ntiles;
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
             uint32_t it = 0;
-            for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-                TileCoord c;
-                decode_tile(P, t, c);
-                const Group& G = p.groups[c.g];
+            for (long w = blockIdx.x; w < nwork; w += gridDim.x) {
+                SuperTile st;
+                decode_super(P, w, n_super, st);
+                TileCoord c[4];
+                int nv = 0;
+                for (int t = 0; t < P.T; ++t)
+                    if (st.s0 + t < n_spatial) { decode_spatial(P, st.s0 + t, c[t]); nv = t + 1; }
+                const Group& G = p.groups[st.g];
                 for (int ti = G.tap_begin; ti < G.tap_begin + G.tap_count; ++ti) {
                     const Tap T = p.taps[ti];
                     for (int kc = 0; kc < P.kchunks; ++kc, ++it) {
                         const int s = it % P.stages;
                         mbar_wait(&empty_bar[s], ((it / P.stages) & 1) ^ 1, 1);
                         uint8_t* a_dst = smem + (size_t)s * P.stage_bytes;
-                        uint8_t* b_dst = a_dst + P.a_bytes;
-                        mbar_expect_tx(&full_bar[s], P.a_bytes + P.b_bytes);
-                        tma_load_5d(a_dst, &P.in_maps[T.view], &full_bar[s], kc * KC, c.x0 + T.dx, c.y0 + T.dy,
-                                    c.z0 + T.dz, c.n0);
-                        tma_load_3d(b_dst, &P.w_map, &full_bar[s], kc * KC, c.nt * P.NT, T.w);
+                        uint8_t* b_dst = a_dst + (size_t)P.T * P.a_bytes;
+                        mbar_expect_tx(&full_bar[s], (uint32_t)nv * P.a_bytes + P.b_bytes);
+                        for (int t = 0; t < nv; ++t)
+                            tma_load_5d(a_dst + (size_t)t * P.a_bytes, &P.in_maps[T.view], &full_bar[s], kc * KC,
+                                        c[t].x0 + T.dx, c[t].y0 + T.dy, c[t].z0 + T.dz, c[t].n0);
+                        tma_load_3d(b_dst, &P.w_map, &full_bar[s], kc * KC, st.nt * P.NT, T.w);
                     }
                 }
             }
@@ -215,97 +226,107 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
-            uint32_t it = 0, tile_iter = 0;
-            for (long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tile_iter) {
-                TileCoord c;
-                decode_tile(P, t, c);
-                const Group& G = p.groups[c.g];
-                const int acc = tile_iter & 1;
-                mbar_wait(&tempty_bar[acc], ((tile_iter >> 1) & 1) ^ 1, 2);
+            uint32_t it = 0, iter = 0;
+            for (long w = blockIdx.x; w < nwork; w += gridDim.x, ++iter) {
+                SuperTile st;
+                decode_super(P, w, n_super, st);
+                const long left = n_spatial - st.s0;
+                const int nv = left < P.T ? (int)left : P.T;
+                const Group& G = p.groups[st.g];
+                const int acc = iter & 1;
+                mbar_wait(&tempty_bar[acc], ((iter >> 1) & 1) ^ 1, 2);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.NT);
+                const uint32_t d_base = tmem_base + (uint32_t)(acc * P.T * P.NT);
                 const int kblocks = G.tap_count * P.kchunks;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % P.stages;
                     mbar_wait(&full_bar[s], (it / P.stages) & 1, 3);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + (size_t)s * P.stage_bytes);
-                    const uint32_t b_addr = a_addr + P.a_bytes;
-                    const uint64_t adesc = umma_desc(a_addr, 16, SBO, LAYOUT);
+                    const uint32_t b_addr = a_addr + (uint32_t)P.T * P.a_bytes;
                     const uint64_t bdesc = umma_desc(b_addr, 16, SBO, LAYOUT);
+                    // the T accumulators are independent: consecutive MMAs never wait on each other's accumulate
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k) {
-                        // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
-                        mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc, (kb | k) != 0);
+                        for (int t = 0; t < nv; ++t) {
+                            const uint64_t adesc = umma_desc(a_addr + (uint32_t)t * P.a_bytes, 16, SBO, LAYOUT);
+                            mma_bf16(d_base + (uint32_t)(t * P.NT), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                                     P.idesc, (kb | k) != 0);
+                        }
                     }
                     mma_commit(&empty_bar[s]);          // smem slot free once these MMAs retire
                 }
-                mma_commit(&tfull_bar[acc]);            // accumulator complete
+                mma_commit(&tfull_bar[acc]);            // accumulators complete
             }
         }
     } else if (warp >= 4) {
         // =============================== epilogue ===============================
         const int q = warp - 4;                         // TMEM lane quadrant == warp % 4
         const int row = q * 32 + lane;
-        uint32_t tile_iter = 0;
-        for (long t = blockIdx.x; t < ntiles; t += gridDim.x, ++tile_iter) {
-            TileCoord c;
-            decode_tile(P, t, c);
-            const Group& G = p.groups[c.g];
+        uint32_t iter = 0;
+        for (long w = blockIdx.x; w < nwork; w += gridDim.x, ++iter) {
+            SuperTile st;
+            decode_super(P, w, n_super, st);
+            const Group& G = p.groups[st.g];
             const View& ov = p.out_views[G.out_view];
-            const int acc = tile_iter & 1;
-            // row → voxel of the out view (same linearisation as the TMA box: n, z, y, x with x fastest)
-            const int x = c.x0 + (row & ((1 << P.lgbw) - 1));
-            const int y = c.y0 + ((row >> P.lgbw) & ((1 << P.lgbh) - 1));
-            const int z = c.z0 + ((row >> (P.lgbw + P.lgbh)) & ((1 << P.lgbd) - 1));
-            const int n = c.n0 + (row >> (P.lgbw + P.lgbh + P.lgbd));
-            const bool valid = n < p.oN && z < p.oD && y < p.oH && x < p.oW;
-            bool on = valid;
-            if (valid && P.active && p.lgPv >= 0)
-                on = P.active[((n * p.fd + (z >> p.lgPv)) * p.fh + (y >> p.lgPv)) * p.fw + (x >> p.lgPv)] != 0;
-            bf16* yrow = P.y + ov.base + (long)n * ov.sN + (long)z * ov.sD + (long)y * ov.sH + (long)x * ov.sW +
-                         (long)c.nt * P.NT;
-            mbar_wait(&tfull_bar[acc], (tile_iter >> 1) & 1, 4);
+            const int acc = iter & 1;
+            mbar_wait(&tfull_bar[acc], (iter >> 1) & 1, 4);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P.NT);
-            for (int col = 0; col < P.NT; col += 32) {
-                uint32_t r[32];
-                const bool wide = (P.NT - col) >= 32;
-                if (wide) tmem_ld_x32(t_addr + col, r);
-                else tmem_ld_x16(t_addr + col, r);
-                tmem_ld_wait();
-                const int ncol = wide ? 32 : 16;
-                float v[32];
+            for (int t = 0; t < P.T; ++t) {
+                if (st.s0 + t >= n_spatial) break;
+                TileCoord c;
+                decode_spatial(P, st.s0 + t, c);
+                // row → voxel of the out view (same linearisation as the TMA box: n, z, y, x with x fastest)
+                const int x = c.x0 + (row & ((1 << P.lgbw) - 1));
+                const int y = c.y0 + ((row >> P.lgbw) & ((1 << P.lgbh) - 1));
+                const int z = c.z0 + ((row >> (P.lgbw + P.lgbh)) & ((1 << P.lgbd) - 1));
+                const int n = c.n0 + (row >> (P.lgbw + P.lgbh + P.lgbd));
+                const bool valid = n < p.oN && z < p.oD && y < p.oH && x < p.oW;
+                bool on = valid;
+                if (valid && P.active && p.lgPv >= 0)
+                    on = P.active[((n * p.fd + (z >> p.lgPv)) * p.fh + (y >> p.lgPv)) * p.fw + (x >> p.lgPv)] != 0;
+                bf16* yrow = P.y + ov.base + (long)n * ov.sN + (long)z * ov.sD + (long)y * ov.sH + (long)x * ov.sW +
+                             (long)st.nt * P.NT;
+                const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * P.T + t) * P.NT);
+                for (int col = 0; col < P.NT; col += 32) {
+                    uint32_t r[32];
+                    const bool wide = (P.NT - col) >= 32;
+                    if (wide) tmem_ld_x32(t_addr + col, r);
+                    else tmem_ld_x16(t_addr + col, r);
+                    tmem_ld_wait();
+                    const int ncol = wide ? 32 : 16;
+                    float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float f = 0.f;
-                    if (j < ncol) {
-                        f = __uint_as_float(r[j]);
-                        if (P.bias) f += __ldg(P.bias + c.nt * P.NT + col + j);
-                        if (!on) f = 0.f;
-                    }
-                    v[j] = f;
-                }
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
+                    for (int j = 0; j < 32; ++j) {
+                        float f = 0.f;
                         if (j < ncol) {
-                            uint4 o;
-                            o.x = pack2(v[j], v[j + 1]); o.y = pack2(v[j + 2], v[j + 3]);
-                            o.z = pack2(v[j + 4], v[j + 5]); o.w = pack2(v[j + 6], v[j + 7]);
-                            *reinterpret_cast<uint4*>(yrow + col + j) = o;
+                            f = __uint_as_float(r[j]);
+                            if (P.bias) f += __ldg(P.bias + st.nt * P.NT + col + j);
+                            if (!on) f = 0.f;
+                        }
+                        v[j] = f;
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            if (j < ncol) {
+                                uint4 o;
+                                o.x = pack2(v[j], v[j + 1]); o.y = pack2(v[j + 2], v[j + 3]);
+                                o.z = pack2(v[j + 4], v[j + 5]); o.w = pack2(v[j + 6], v[j + 7]);
+                                *reinterpret_cast<uint4*>(yrow + col + j) = o;
+                            }
                         }
                     }
-                }
-                if (P.stats) {
-                    float sq[32];
+                    if (P.stats) {
+                        float sq[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { if (!valid) v[j] = 0.f; sq[j] = v[j] * v[j]; }
-                    float s1 = warp_column_sums(v);
-                    float s2 = warp_column_sums(sq);
-                    if (lane < ncol) {
-                        atomicAdd(&s_stats[c.nt * P.NT + col + lane], s1);
-                        atomicAdd(&s_stats[p.Cy + c.nt * P.NT + col + lane], s2);
+                        for (int j = 0; j < 32; ++j) { if (!valid) v[j] = 0.f; sq[j] = v[j] * v[j]; }
+                        float s1 = warp_column_sums(v);
+                        float s2 = warp_column_sums(sq);
+                        if (lane < ncol) {
+                            atomicAdd(&s_stats[st.nt * P.NT + col + lane], s1);
+                            atomicAdd(&s_stats[p.Cy + st.nt * P.NT + col + lane], s2);
+                        }
                     }
                 }
             }
@@ -369,13 +390,22 @@ int igemm_conv(const Plan& p, const amb_conv_args* a) {
     P.NT = NT; P.n_ntiles = p.Cy / NT;
     P.kchunks = p.Cx / KC;
     P.a_bytes = 128u * KC * 2u;
-    P.b_bytes = (uint32_t)NT * KC * 2u;
-    P.stage_bytes = (P.a_bytes + P.b_bytes + 1023u) & ~1023u;
-    int stages = (int)((196u * 1024u) / P.stage_bytes);
+    P.b_bytes = ((uint32_t)NT * KC * 2u + 1023u) & ~1023u;
+    // T independent accumulators per CTA iteration: dependent tcgen05.mma on ONE accumulator are latency-bound
+    // (~100 ns each, measured), so narrow-N layers interleave up to 4 tiles; the weight slab is shared by all of them.
+    int T = 256 / NT;                 // 2 buffers x T x NT TMEM columns <= 512
+    if (T > 4) T = 4;
+    if (T < 1) T = 1;
+    const char* tenv = getenv("AMB_IGEMM_T");
+    if (tenv && atoi(tenv) >= 1 && atoi(tenv) <= T) T = atoi(tenv);
+    while (T > 1 && 3u * (T * P.a_bytes + P.b_bytes) > 200u * 1024u) T >>= 1;     // keep >= 3 pipeline stages
+    P.T = T;
+    P.stage_bytes = (uint32_t)T * P.a_bytes + P.b_bytes;
+    int stages = (int)((200u * 1024u) / P.stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) { set_error("tile does not fit shared memory"); return 0; }
     P.stages = stages;
-    P.tmem_cols = (uint32_t)pow2_ceil(2 * NT);
+    P.tmem_cols = (uint32_t)pow2_ceil(2 * T * NT);
     if (P.tmem_cols < 32) P.tmem_cols = 32;
     P.idesc = umma_idesc_bf16(128, NT, 0, 0);
     P.y = (bf16*)a->y; P.bias = a->bias; P.active = a->active;
@@ -386,15 +416,15 @@ int igemm_conv(const Plan& p, const amb_conv_args* a) {
     const int box[4] = {bn, bd, bh, bw};
     for (int i = 0; i < p.n_in_views; ++i)
         if (int e = encode_view_map(&P.in_maps[i], a->x, p.in_views[i], p.Cx, KC, box)) return e;
-    int T = 0;
-    for (int i = 0; i < p.n_taps; ++i) if (p.taps[i].w + 1 > T) T = p.taps[i].w + 1;
+    int n_slabs = 0;
+    for (int i = 0; i < p.n_taps; ++i) if (p.taps[i].w + 1 > n_slabs) n_slabs = p.taps[i].w + 1;
     // the packed weight tensor always holds k³ (or 64) slabs even when a plan uses a subset
-    int T_full = (a->op == AMB_OP_CONVT || a->op == AMB_OP_CONVT_DGRAD) ? 64 : a->k * a->k * a->k;
-    if (T_full > T) T = T_full;
-    if (int e = encode_weight_map(&P.w_map, a->w, T, p.Cy, p.Cx, KC, NT)) return e;
+    int slabs_full = (a->op == AMB_OP_CONVT || a->op == AMB_OP_CONVT_DGRAD) ? 64 : a->k * a->k * a->k;
+    if (slabs_full > n_slabs) n_slabs = slabs_full;
+    if (int e = encode_weight_map(&P.w_map, a->w, n_slabs, p.Cy, p.Cx, KC, NT)) return e;
 
     size_t smem = (size_t)P.stages * P.stage_bytes + 1024 + 256 + (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0);
-    long tiles_upper = (long)P.Tn * P.Tz * P.Ty * P.Tx * p.n_groups * P.n_ntiles;
+    long tiles_upper = (((long)P.Tn * P.Tz * P.Ty * P.Tx + T - 1) / T) * p.n_groups * P.n_ntiles;
     int grid = (int)(tiles_upper < (long)num_sms() ? tiles_upper : (long)num_sms());
     cudaStream_t st = (cudaStream_t)a->stream;
     if (KC == 64) {

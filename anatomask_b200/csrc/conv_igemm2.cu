@@ -288,6 +288,9 @@ typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 
 // returns 1 when handled, 0 when the shape is not for this kernel, <0 on error
 int igemm2_conv(const Plan& p, const amb_conv_args* a) {
+    // opt-in: measured no faster than the T-interleaved per-tap kernel (the limit was MMA latency, not L2 traffic)
+    const char* en = getenv("AMB_ENABLE_V2");
+    if (!(en && atoi(en) == 1)) return 0;
     if (!((a->op == AMB_OP_CONV || a->op == AMB_OP_CONV_DGRAD) && a->k == 3 && a->stride == 1)) return 0;
     if (p.Cx % 64 != 0 || p.Cy % 16 != 0 || p.n_taps != 27 || p.n_in_views != 1 || p.n_groups != 1) return 0;
     if (p.oH < 16 || p.oW < 8 || p.oD < 2) return 0;
@@ -299,7 +302,7 @@ int igemm2_conv(const Plan& p, const amb_conv_args* a) {
     static Igemm2Params P;
     memset(&P, 0, sizeof(P));
     const char* bo = getenv("AMB_V2_BO_MODE");
-    P.bo_mode = bo ? atoi(bo) : 0;
+    P.bo_mode = bo ? atoi(bo) : 1;     // measured: the swizzle phase comes from absolute smem address bits; field stays 0
     P.y = (bf16*)a->y;
     const View& ov = p.out_views[0];
     P.sN = ov.sN; P.sD = ov.sD; P.sH = ov.sH; P.sW = ov.sW;

@@ -177,18 +177,24 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
                 tc_fence_after();
                 const uint32_t b_addr = smem_u32(b_ring + bs * WG_SLOT_BYTES);
                 const uint64_t bdesc = umma_desc(b_addr, P.b_slab_bytes, P.b_sbo, P.b_layout);
-                for (int u = 0; u < B.unit_count; ++u, ++ai) {
-                    const int as = ai % WG_A_SLOTS;
-                    mbar_wait(&a_full[as], (ai / WG_A_SLOTS) & 1, 14);
+                // units are processed in pairs: their accumulators are independent, so the two 8-deep chains of
+                // dependent tcgen05.mma interleave instead of each waiting out the accumulate latency (~100 ns)
+                for (int u = 0; u < B.unit_count; u += 2) {
+                    const int nu = (B.unit_count - u) < 2 ? (B.unit_count - u) : 2;
+                    uint64_t adesc[2];
+                    int slot[2];
+                    for (int j = 0; j < nu; ++j, ++ai) {
+                        slot[j] = ai % WG_A_SLOTS;
+                        mbar_wait(&a_full[slot[j]], (ai / WG_A_SLOTS) & 1, 14);
+                        adesc[j] = umma_desc(smem_u32(a_ring + slot[j] * WG_SLOT_BYTES), P.a_slab_bytes, P.a_sbo, P.a_layout);
+                    }
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(a_ring + as * WG_SLOT_BYTES);
-                    const uint64_t adesc = umma_desc(a_addr, P.a_slab_bytes, P.a_sbo, P.a_layout);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(u * P.NTw);
 #pragma unroll
                     for (int k = 0; k < 8; ++k)      // 128 voxels per tile = 8 × K16
-                        mma_bf16(d_tmem, adesc + (uint64_t)((P.a_kstep * k) >> 4), bdesc + (uint64_t)((P.b_kstep * k) >> 4),
-                                 P.idesc, (kt != k_begin) || (k != 0));
-                    mma_commit(&a_empty[as]);
+                        for (int j = 0; j < nu; ++j)
+                            mma_bf16(tmem_base + (uint32_t)((u + j) * P.NTw), adesc[j] + (uint64_t)((P.a_kstep * k) >> 4),
+                                     bdesc + (uint64_t)((P.b_kstep * k) >> 4), P.idesc, (kt != k_begin) || (k != 0));
+                    for (int j = 0; j < nu; ++j) mma_commit(&a_empty[slot[j]]);
                 }
                 mma_commit(&b_empty[bs]);
             }

@@ -15,6 +15,7 @@ LAYERS = [  # name, Cin, Cout, S, N
     ('dec3.conv0 64->64 @128', 64, 64, 128, 2), ('dec3.conv3 64->32 @128', 64, 32, 128, 2),
     ('dec2.conv0 128->128 @64', 128, 128, 64, 2), ('dec2.conv3 128->64 @64', 128, 64, 64, 2),
     ('dec1.conv0 256->256 @32', 256, 256, 32, 2), ('dec0.conv0 512->512 @16', 512, 512, 16, 2),
+    ('enc0.conv2 32->32 @128', 32, 32, 128, 1),
 ]
 
 
@@ -34,7 +35,8 @@ def time_it(fn, flush, iters=5):
 def main(which):
     dev = torch.device('cuda:0')
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    impls = {'v1': L.IMPL_TCGEN05_V1, 'v2': L.IMPL_TCGEN05}
+    # T1 = one accumulator per CTA iteration (dependent-MMA chain), T = interleaved accumulators (default)
+    impls = {'T1': (L.IMPL_TCGEN05_V1, '1'), 'T': (L.IMPL_TCGEN05_V1, None)}
     if which != 'all':
         impls = {which: impls[which]}
     out = []
@@ -49,7 +51,11 @@ def main(which):
         dw = torch.zeros(27, co, ci, device=dev)
         flops = 2.0 * N * S ** 3 * 27 * ci * co
         row = {'layer': name}
-        for tag, impl in impls.items():
+        for tag, (impl, tenv) in impls.items():
+            if tenv is None:
+                os.environ.pop('AMB_IGEMM_T', None)
+            else:
+                os.environ['AMB_IGEMM_T'] = tenv
             t = time_it(lambda: ops._conv_call(L.OP_CONV, impl, (N, S, S, S), ci, co, 3, 1, x, y, wf), flush)
             row[f'fwd_{tag}'] = round(flops / t / 1e9, 1)
             t = time_it(lambda: ops._conv_call(L.OP_CONV_DGRAD, impl, (N, S, S, S), ci, co, 3, 1, dy, dx, wd), flush)
