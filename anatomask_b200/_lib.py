@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libanatomask_b200.so')
+LIB_PATH = os.environ.get('AMB_LIB_PATH') or os.path.join(_HERE, 'libanatomask_b200.so')   # override: A/B kernel builds
 
 vp, i32, i64, f32, f64, u64 = C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_double, C.c_ulonglong
 

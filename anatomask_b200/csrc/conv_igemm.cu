@@ -99,48 +99,58 @@ struct IgemmParams {
 struct TileCoord {
     int n0, z0, y0, x0;
 };
+
+// all tile arithmetic is 32-bit (tile counts are far below 2^31); the per-k-block loops below contain no division at
+// all: ring stage / phase and the smem addresses advance incrementally.  (v1 of these loops spent ~430 ns per k-block
+// in runtime div/mod, 64-bit division calls and parameter reloads — more than the MMAs themselves for N <= 128.)
+__device__ __forceinline__ uint32_t num_spatial(const IgemmParams& P) {
+    const Plan& p = P.plan;
+    if (P.list) {
+        const int Pv = 1 << p.lgPv;
+        return (uint32_t)(*P.count) * (uint32_t)((Pv >> P.lgbd) * (Pv >> P.lgbh) * (Pv >> P.lgbw));
+    }
+    return (uint32_t)(P.Tn * P.Tz * P.Ty * P.Tx);
+}
+
+__device__ __forceinline__ void decode_spatial(const IgemmParams& P, uint32_t t, TileCoord& c) {
+    const Plan& p = P.plan;
+    if (P.list) {
+        // sub-tile counts inside a patch are powers of two
+        const int lx = p.lgPv - P.lgbw, ly = p.lgPv - P.lgbh, lz = p.lgPv - P.lgbd;
+        const uint32_t ix = t & ((1u << lx) - 1); t >>= lx;
+        const uint32_t iy = t & ((1u << ly) - 1); t >>= ly;
+        const uint32_t iz = t & ((1u << lz) - 1); t >>= lz;
+        const uint32_t pid = (uint32_t)P.list[t];
+        const uint32_t L = (uint32_t)(p.fd * p.fh * p.fw);
+        const uint32_t n = pid / L, l = pid - n * L;
+        const uint32_t hw = (uint32_t)(p.fh * p.fw);
+        const uint32_t pz = l / hw, r2 = l - pz * hw;
+        const uint32_t py = r2 / (uint32_t)p.fw, px = r2 - py * (uint32_t)p.fw;
+        c.n0 = (int)n;
+        c.z0 = (int)((pz << p.lgPv) + (iz << P.lgbd));
+        c.y0 = (int)((py << p.lgPv) + (iy << P.lgbh));
+        c.x0 = (int)((px << p.lgPv) + (ix << P.lgbw));
+    } else {
+        const uint32_t tx = t % (uint32_t)P.Tx; t /= (uint32_t)P.Tx;
+        const uint32_t ty = t % (uint32_t)P.Ty; t /= (uint32_t)P.Ty;
+        const uint32_t tz = t % (uint32_t)P.Tz; t /= (uint32_t)P.Tz;
+        c.x0 = (int)(tx << P.lgbw);
+        c.y0 = (int)(ty << P.lgbh);
+        c.z0 = (int)(tz << P.lgbd);
+        c.n0 = (int)(t << P.lgbn);
+    }
+}
+
+// work item w → (group, N tile, first spatial tile); spatial fastest so that concurrently running CTAs share weights
 struct SuperTile {
     int g, nt;
-    long s0;            // first spatial tile; tiles s0 .. s0+T-1 (those < n_spatial) share group and N tile
+    uint32_t s0;
 };
-
-__device__ __forceinline__ long num_spatial(const IgemmParams& P) {
-    const Plan& p = P.plan;
-    if (P.list) {
-        const int Pv = 1 << p.lgPv;
-        return (long)(*P.count) * (Pv >> P.lgbd) * (Pv >> P.lgbh) * (Pv >> P.lgbw);
-    }
-    return (long)P.Tn * P.Tz * P.Ty * P.Tx;
-}
-
-__device__ __forceinline__ void decode_super(const IgemmParams& P, long w, long n_super, SuperTile& st) {
-    st.s0 = (w % n_super) * P.T;
-    w /= n_super;
-    st.nt = (int)(w % P.n_ntiles);
-    st.g = (int)(w / P.n_ntiles);
-}
-
-__device__ __forceinline__ void decode_spatial(const IgemmParams& P, long t, TileCoord& c) {
-    const Plan& p = P.plan;
-    if (P.list) {
-        const int Pv = 1 << p.lgPv;
-        const int sx = Pv >> P.lgbw, sy = Pv >> P.lgbh, sz = Pv >> P.lgbd;
-        int ix = (int)(t % sx); t /= sx;
-        int iy = (int)(t % sy); t /= sy;
-        int iz = (int)(t % sz); t /= sz;
-        int pid = P.list[t];
-        const int L = p.fd * p.fh * p.fw;
-        c.n0 = pid / L;
-        int l = pid % L;
-        c.z0 = ((l / (p.fh * p.fw)) << p.lgPv) + (iz << P.lgbd);
-        c.y0 = (((l / p.fw) % p.fh) << p.lgPv) + (iy << P.lgbh);
-        c.x0 = ((l % p.fw) << p.lgPv) + (ix << P.lgbw);
-    } else {
-        c.x0 = (int)(t % P.Tx) << P.lgbw; t /= P.Tx;
-        c.y0 = (int)(t % P.Ty) << P.lgbh; t /= P.Ty;
-        c.z0 = (int)(t % P.Tz) << P.lgbd; t /= P.Tz;
-        c.n0 = (int)t << P.lgbn;
-    }
+__device__ __forceinline__ void decode_super(const IgemmParams& P, uint32_t w, uint32_t n_super, SuperTile& st) {
+    const uint32_t q = w / n_super;
+    st.s0 = (w - q * n_super) * (uint32_t)P.T;
+    st.g = (int)(q / (uint32_t)P.n_ntiles);
+    st.nt = (int)(q - (uint32_t)st.g * (uint32_t)P.n_ntiles);
 }
 
 // transpose-reduce: every lane holds v[0..31] (one row, 32 columns); afterwards lane L holds Σ_rows column L in v[0]
@@ -191,34 +201,46 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const long n_spatial = num_spatial(P);
-    const long n_super = (n_spatial + P.T - 1) / P.T;
-    const long nwork = n_super * p.n_groups * P.n_ntiles;
+    const uint32_t n_spatial = num_spatial(P);
+    const uint32_t Tn_ = (uint32_t)P.T;
+    const uint32_t n_super = (n_spatial + Tn_ - 1) / Tn_;
+    const uint32_t nwork = n_super * (uint32_t)(p.n_groups * P.n_ntiles);
+    // loop-invariant parameters, hoisted into registers
+    const uint32_t stages = (uint32_t)P.stages, stage_bytes = P.stage_bytes, a_bytes = P.a_bytes, b_bytes = P.b_bytes;
+    const uint32_t NT = (uint32_t)P.NT, kchunks = (uint32_t)P.kchunks, idesc = P.idesc;
+    const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
-            uint32_t it = 0;
-            for (long w = blockIdx.x; w < nwork; w += gridDim.x) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t w = blockIdx.x; w < nwork; w += gridDim.x) {
                 SuperTile st;
                 decode_super(P, w, n_super, st);
                 TileCoord c[4];
-                int nv = 0;
-                for (int t = 0; t < P.T; ++t)
-                    if (st.s0 + t < n_spatial) { decode_spatial(P, st.s0 + t, c[t]); nv = t + 1; }
-                const Group& G = p.groups[st.g];
-                for (int ti = G.tap_begin; ti < G.tap_begin + G.tap_count; ++ti) {
-                    const Tap T = p.taps[ti];
-                    for (int kc = 0; kc < P.kchunks; ++kc, ++it) {
-                        const int s = it % P.stages;
-                        mbar_wait(&empty_bar[s], ((it / P.stages) & 1) ^ 1, 1);
-                        uint8_t* a_dst = smem + (size_t)s * P.stage_bytes;
-                        uint8_t* b_dst = a_dst + (size_t)P.T * P.a_bytes;
-                        mbar_expect_tx(&full_bar[s], (uint32_t)nv * P.a_bytes + P.b_bytes);
-                        for (int t = 0; t < nv; ++t)
-                            tma_load_5d(a_dst + (size_t)t * P.a_bytes, &P.in_maps[T.view], &full_bar[s], kc * KC,
-                                        c[t].x0 + T.dx, c[t].y0 + T.dy, c[t].z0 + T.dz, c[t].n0);
-                        tma_load_3d(b_dst, &P.w_map, &full_bar[s], kc * KC, st.nt * P.NT, T.w);
+                uint32_t nv = 0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    c[t].n0 = c[t].z0 = c[t].y0 = c[t].x0 = 0;
+                    if ((uint32_t)t < Tn_ && st.s0 + t < n_spatial) { decode_spatial(P, st.s0 + t, c[t]); nv = t + 1; }
+                }
+                const uint32_t tx_bytes = nv * a_bytes + b_bytes;
+                const int ncol = st.nt * (int)NT;
+                const int tap_end = p.groups[st.g].tap_begin + p.groups[st.g].tap_count;
+                for (int ti = p.groups[st.g].tap_begin; ti < tap_end; ++ti) {
+                    const Tap tap = p.taps[ti];
+                    const CUtensorMap* amap = &P.in_maps[tap.view];
+                    for (uint32_t kc = 0; kc < kchunks; ++kc) {
+                        const uint32_t fb = full0 + stage * 8u, a_dst = smem_base + stage * stage_bytes;
+                        mbar_wait_u32(empty0 + stage * 8u, phase ^ 1u, 1);
+                        mbar_expect_tx_u32(fb, tx_bytes);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if ((uint32_t)t < nv)
+                                tma_load_5d_u32(a_dst + (uint32_t)t * a_bytes, amap, fb, (int)(kc * KC), c[t].x0 + tap.dx,
+                                                c[t].y0 + tap.dy, c[t].z0 + tap.dz, c[t].n0);
+                        tma_load_3d_u32(a_dst + Tn_ * a_bytes, &P.w_map, fb, (int)(kc * KC), ncol, tap.w);
+                        if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
@@ -226,53 +248,57 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
-            uint32_t it = 0, iter = 0;
-            for (long w = blockIdx.x; w < nwork; w += gridDim.x, ++iter) {
-                SuperTile st;
-                decode_super(P, w, n_super, st);
-                const long left = n_spatial - st.s0;
-                const int nv = left < P.T ? (int)left : P.T;
-                const Group& G = p.groups[st.g];
-                const int acc = iter & 1;
-                mbar_wait(&tempty_bar[acc], ((iter >> 1) & 1) ^ 1, 2);
+            uint32_t stage = 0, phase = 0, iter = 0;
+            const uint32_t desc_hi = (uint32_t)(umma_desc(0, 16, SBO, LAYOUT) >> 32);
+            const uint32_t desc_lo_const = (uint32_t)(umma_desc(0, 16, SBO, LAYOUT) & 0xFFFFFFFFu);
+            for (uint32_t w = blockIdx.x; w < nwork; w += gridDim.x, ++iter) {
+                const uint32_t q = w / n_super;
+                const uint32_t s0 = (w - q * n_super) * Tn_;
+                const uint32_t left = n_spatial - s0;
+                const uint32_t nv = left < Tn_ ? left : Tn_;
+                const int g = (int)(q / (uint32_t)P.n_ntiles);
+                const uint32_t acc = iter & 1u;
+                mbar_wait_u32(smem_u32(&tempty_bar[acc]), ((iter >> 1) & 1u) ^ 1u, 2);
                 tc_fence_after();
-                const uint32_t d_base = tmem_base + (uint32_t)(acc * P.T * P.NT);
-                const int kblocks = G.tap_count * P.kchunks;
-                for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                    const int s = it % P.stages;
-                    mbar_wait(&full_bar[s], (it / P.stages) & 1, 3);
+                const uint32_t d_base = tmem_base + acc * Tn_ * NT;
+                const uint32_t kblocks = (uint32_t)p.groups[g].tap_count * kchunks;
+                for (uint32_t kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait_u32(full0 + stage * 8u, phase, 3);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + (size_t)s * P.stage_bytes);
-                    const uint32_t b_addr = a_addr + (uint32_t)P.T * P.a_bytes;
-                    const uint64_t bdesc = umma_desc(b_addr, 16, SBO, LAYOUT);
+                    const uint32_t a_lo = desc_lo_const | (((smem_base + stage * stage_bytes) & 0x3FFFFu) >> 4);
+                    const uint32_t b_lo = a_lo + ((Tn_ * a_bytes) >> 4);
                     // the T accumulators are independent: consecutive MMAs never wait on each other's accumulate
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k) {
-                        for (int t = 0; t < nv; ++t) {
-                            const uint64_t adesc = umma_desc(a_addr + (uint32_t)t * P.a_bytes, 16, SBO, LAYOUT);
-                            mma_bf16(d_base + (uint32_t)(t * P.NT), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
-                                     P.idesc, (kb | k) != 0);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            if ((uint32_t)t < nv) {
+                                const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)t * (a_bytes >> 4) + 2u * k);
+                                const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
+                                mma_bf16(d_base + (uint32_t)t * NT, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
+                            }
                         }
                     }
-                    mma_commit(&empty_bar[s]);          // smem slot free once these MMAs retire
+                    mma_commit_u32(empty0 + stage * 8u);        // smem slot free once these MMAs retire
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
-                mma_commit(&tfull_bar[acc]);            // accumulators complete
+                mma_commit_u32(smem_u32(&tfull_bar[acc]));      // accumulators complete
             }
         }
     } else if (warp >= 4) {
         // =============================== epilogue ===============================
-        const int q = warp - 4;                         // TMEM lane quadrant == warp % 4
-        const int row = q * 32 + lane;
+        const int q4 = warp - 4;                         // TMEM lane quadrant == warp % 4
+        const int row = q4 * 32 + lane;
         uint32_t iter = 0;
-        for (long w = blockIdx.x; w < nwork; w += gridDim.x, ++iter) {
+        for (uint32_t w = blockIdx.x; w < nwork; w += gridDim.x, ++iter) {
             SuperTile st;
             decode_super(P, w, n_super, st);
             const Group& G = p.groups[st.g];
             const View& ov = p.out_views[G.out_view];
-            const int acc = iter & 1;
-            mbar_wait(&tfull_bar[acc], (iter >> 1) & 1, 4);
+            const uint32_t acc = iter & 1u;
+            mbar_wait(&tfull_bar[acc], (iter >> 1) & 1u, 4);
             tc_fence_after();
-            for (int t = 0; t < P.T; ++t) {
+            for (uint32_t t = 0; t < Tn_; ++t) {
                 if (st.s0 + t >= n_spatial) break;
                 TileCoord c;
                 decode_spatial(P, st.s0 + t, c);
@@ -287,7 +313,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                     on = P.active[((n * p.fd + (z >> p.lgPv)) * p.fh + (y >> p.lgPv)) * p.fw + (x >> p.lgPv)] != 0;
                 bf16* yrow = P.y + ov.base + (long)n * ov.sN + (long)z * ov.sD + (long)y * ov.sH + (long)x * ov.sW +
                              (long)st.nt * P.NT;
-                const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * P.T + t) * P.NT);
+                const uint32_t t_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (acc * Tn_ + t) * NT;
                 for (int col = 0; col < P.NT; col += 32) {
                     uint32_t r[32];
                     const bool wide = (P.NT - col) >= 32;
