@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
-        if (lane == 0) {
+        {
             uint32_t stage = 0, phase = 0;
             for (uint32_t w = blockIdx.x; w < nwork; w += gridDim.x) {
                 SuperTile st;
@@ -233,13 +233,16 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                     for (uint32_t kc = 0; kc < kchunks; ++kc) {
                         const uint32_t fb = full0 + stage * 8u, a_dst = smem_base + stage * stage_bytes;
                         mbar_wait_u32(empty0 + stage * 8u, phase ^ 1u, 1);
-                        mbar_expect_tx_u32(fb, tx_bytes);
+                        if (elect_one()) {
+                            mbar_expect_tx_u32(fb, tx_bytes);
 #pragma unroll
-                        for (int t = 0; t < 4; ++t)
-                            if ((uint32_t)t < nv)
-                                tma_load_5d_u32(a_dst + (uint32_t)t * a_bytes, amap, fb, (int)(kc * KC), c[t].x0 + tap.dx,
-                                                c[t].y0 + tap.dy, c[t].z0 + tap.dz, c[t].n0);
-                        tma_load_3d_u32(a_dst + Tn_ * a_bytes, &P.w_map, fb, (int)(kc * KC), ncol, tap.w);
+                            for (int t = 0; t < 4; ++t)
+                                if ((uint32_t)t < nv)
+                                    tma_load_5d_u32(a_dst + (uint32_t)t * a_bytes, amap, fb, (int)(kc * KC), c[t].x0 + tap.dx,
+                                                    c[t].y0 + tap.dy, c[t].z0 + tap.dz, c[t].n0);
+                            tma_load_3d_u32(a_dst + Tn_ * a_bytes, &P.w_map, fb, (int)(kc * KC), ncol, tap.w);
+                        }
+                        __syncwarp();
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
+        {
             uint32_t stage = 0, phase = 0, iter = 0;
             const uint32_t desc_hi = (uint32_t)(umma_desc(0, 16, SBO, LAYOUT) >> 32);
             const uint32_t desc_lo_const = (uint32_t)(umma_desc(0, 16, SBO, LAYOUT) & 0xFFFFFFFFu);
@@ -268,21 +271,25 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                     const uint32_t a_lo = desc_lo_const | (((smem_base + stage * stage_bytes) & 0x3FFFFu) >> 4);
                     const uint32_t b_lo = a_lo + ((Tn_ * a_bytes) >> 4);
                     // the T accumulators are independent: consecutive MMAs never wait on each other's accumulate
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < KC / 16; ++k) {
+                        for (int k = 0; k < KC / 16; ++k) {
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            if ((uint32_t)t < nv) {
-                                const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)t * (a_bytes >> 4) + 2u * k);
-                                const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
-                                mma_bf16(d_base + (uint32_t)t * NT, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
+                            for (int t = 0; t < 4; ++t) {
+                                if ((uint32_t)t < nv) {
+                                    const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)t * (a_bytes >> 4) + 2u * k);
+                                    const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
+                                    mma_bf16(d_base + (uint32_t)t * NT, adesc, bdesc, idesc, (kb | (uint32_t)k) != 0u);
+                                }
                             }
                         }
+                        mma_commit_u32(empty0 + stage * 8u);        // smem slot free once these MMAs retire
                     }
-                    mma_commit_u32(empty0 + stage * 8u);        // smem slot free once these MMAs retire
+                    __syncwarp();
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
-                mma_commit_u32(smem_u32(&tfull_bar[acc]));      // accumulators complete
+                if (elect_one()) mma_commit_u32(smem_u32(&tfull_bar[acc]));      // accumulators complete
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {

@@ -131,21 +131,25 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     const long k_begin = ktiles * ks / P.ksplit, k_end = ktiles * (ks + 1) / P.ksplit;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t ai = 0, bi = 0;
-            for (long kt = k_begin; kt < k_end; ++kt, ++bi) {
-                int n0, z0, y0, x0;
-                wg_decode(P, kt, n0, z0, y0, x0);
-                const int bs = bi % WG_B_SLOTS;
-                mbar_wait(&b_empty[bs], ((bi / WG_B_SLOTS) & 1) ^ 1, 11);
+        // producer: warp-uniform loops, one elected lane issues (keeps addresses/descriptors in uniform registers)
+        uint32_t ai = 0, bi = 0;
+        for (long kt = k_begin; kt < k_end; ++kt, ++bi) {
+            int n0, z0, y0, x0;
+            wg_decode(P, kt, n0, z0, y0, x0);
+            const int bs = bi % WG_B_SLOTS;
+            mbar_wait(&b_empty[bs], ((bi / WG_B_SLOTS) & 1) ^ 1, 11);
+            if (elect_one()) {
                 mbar_expect_tx(&b_full[bs], P.b_slab_bytes * P.b_slabs);
                 for (int j = 0; j < P.b_slabs; ++j)
                     tma_load_5d(b_ring + bs * WG_SLOT_BYTES + j * P.b_slab_bytes, &P.b_maps[B.bview], &b_full[bs],
                                 nchunk * P.NTw + j * P.nslabW, x0, y0, z0, n0);
-                for (int u = B.unit_begin; u < B.unit_begin + B.unit_count; ++u, ++ai) {
-                    const int as = ai % WG_A_SLOTS;
-                    mbar_wait(&a_empty[as], ((ai / WG_A_SLOTS) & 1) ^ 1, 12);
-                    uint8_t* dst = a_ring + as * WG_SLOT_BYTES;
+            }
+            __syncwarp();
+            for (int u = B.unit_begin; u < B.unit_begin + B.unit_count; ++u, ++ai) {
+                const int as = ai % WG_A_SLOTS;
+                mbar_wait(&a_empty[as], ((ai / WG_A_SLOTS) & 1) ^ 1, 12);
+                uint8_t* dst = a_ring + as * WG_SLOT_BYTES;
+                if (elect_one()) {
                     if (P.stacked) {
                         int real = 0;
                         for (int j = 0; j < P.a_slabs; ++j) real += P.unit_taps[u][j] >= 0;
@@ -166,40 +170,48 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
                                         ms * 128 + j * P.slabW, x0 + T.sx, y0 + T.sy, z0 + T.sz, n0);
                     }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            uint32_t ai = 0, bi = 0;
-            for (long kt = k_begin; kt < k_end; ++kt, ++bi) {
-                const int bs = bi % WG_B_SLOTS;
-                mbar_wait(&b_full[bs], (bi / WG_B_SLOTS) & 1, 13);
+        uint32_t ai = 0, bi = 0;
+        const uint32_t a_kstep16 = P.a_kstep >> 4, b_kstep16 = P.b_kstep >> 4, NTw = (uint32_t)P.NTw, idesc = P.idesc;
+        for (long kt = k_begin; kt < k_end; ++kt, ++bi) {
+            const int bs = bi % WG_B_SLOTS;
+            mbar_wait(&b_full[bs], (bi / WG_B_SLOTS) & 1, 13);
+            tc_fence_after();
+            const uint64_t bdesc = umma_desc(smem_u32(b_ring + bs * WG_SLOT_BYTES), P.b_slab_bytes, P.b_sbo, P.b_layout);
+            // units are processed in pairs: their accumulators are independent, so the two 8-deep chains of
+            // dependent tcgen05.mma interleave instead of each waiting out the accumulate latency
+            for (int u = 0; u < B.unit_count; u += 2) {
+                const int nu = (B.unit_count - u) < 2 ? (B.unit_count - u) : 2;
+                const int slot0 = ai % WG_A_SLOTS, slot1 = (ai + 1) % WG_A_SLOTS;
+                mbar_wait(&a_full[slot0], (ai / WG_A_SLOTS) & 1, 14);
+                if (nu == 2) mbar_wait(&a_full[slot1], ((ai + 1) / WG_A_SLOTS) & 1, 14);
                 tc_fence_after();
-                const uint32_t b_addr = smem_u32(b_ring + bs * WG_SLOT_BYTES);
-                const uint64_t bdesc = umma_desc(b_addr, P.b_slab_bytes, P.b_sbo, P.b_layout);
-                // units are processed in pairs: their accumulators are independent, so the two 8-deep chains of
-                // dependent tcgen05.mma interleave instead of each waiting out the accumulate latency (~100 ns)
-                for (int u = 0; u < B.unit_count; u += 2) {
-                    const int nu = (B.unit_count - u) < 2 ? (B.unit_count - u) : 2;
-                    uint64_t adesc[2];
-                    int slot[2];
-                    for (int j = 0; j < nu; ++j, ++ai) {
-                        slot[j] = ai % WG_A_SLOTS;
-                        mbar_wait(&a_full[slot[j]], (ai / WG_A_SLOTS) & 1, 14);
-                        adesc[j] = umma_desc(smem_u32(a_ring + slot[j] * WG_SLOT_BYTES), P.a_slab_bytes, P.a_sbo, P.a_layout);
-                    }
-                    tc_fence_after();
+                const uint64_t adesc0 = umma_desc(smem_u32(a_ring + slot0 * WG_SLOT_BYTES), P.a_slab_bytes, P.a_sbo, P.a_layout);
+                const uint64_t adesc1 = umma_desc(smem_u32(a_ring + slot1 * WG_SLOT_BYTES), P.a_slab_bytes, P.a_sbo, P.a_layout);
+                const bool accum = kt != k_begin;
+                if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)      // 128 voxels per tile = 8 × K16
-                        for (int j = 0; j < nu; ++j)
-                            mma_bf16(tmem_base + (uint32_t)((u + j) * P.NTw), adesc[j] + (uint64_t)((P.a_kstep * k) >> 4),
-                                     bdesc + (uint64_t)((P.b_kstep * k) >> 4), P.idesc, (kt != k_begin) || (k != 0));
-                    for (int j = 0; j < nu; ++j) mma_commit(&a_empty[slot[j]]);
+                    for (int k = 0; k < 8; ++k) {      // 128 voxels per tile = 8 × K16
+                        mma_bf16(tmem_base + (uint32_t)u * NTw, adesc0 + (uint64_t)(a_kstep16 * k), bdesc + (uint64_t)(b_kstep16 * k),
+                                 idesc, accum || (k != 0));
+                        if (nu == 2)
+                            mma_bf16(tmem_base + (uint32_t)(u + 1) * NTw, adesc1 + (uint64_t)(a_kstep16 * k),
+                                     bdesc + (uint64_t)(b_kstep16 * k), idesc, accum || (k != 0));
+                    }
+                    mma_commit(&a_empty[slot0]);
+                    if (nu == 2) mma_commit(&a_empty[slot1]);
                 }
-                mma_commit(&b_empty[bs]);
+                __syncwarp();
+                ai += nu;
             }
-            mma_commit(acc_full);
+            if (elect_one()) mma_commit(&b_empty[bs]);
+            __syncwarp();
         }
+        if (elect_one()) mma_commit(acc_full);
+        __syncwarp();
     } else if (warp >= 4) {
         const int q = warp - 4;
         const int m = q * 32 + lane;
