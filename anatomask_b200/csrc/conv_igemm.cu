@@ -91,7 +91,7 @@ struct IgemmParams {
     int T;                           // spatial tiles (independent TMEM accumulators) interleaved per CTA iteration
     int kchunks;                     // Cx / KC
     int stages;
-    uint32_t stage_bytes, a_bytes, b_bytes;
+    uint32_t stage_bytes, a_bytes, b_bytes, b_tx;   // b_bytes: smem footprint (1 KB aligned), b_tx: bytes the TMA delivers
     uint32_t tmem_cols;
     uint32_t idesc;
 };
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                     c[t].n0 = c[t].z0 = c[t].y0 = c[t].x0 = 0;
                     if ((uint32_t)t < Tn_ && st.s0 + t < n_spatial) { decode_spatial(P, st.s0 + t, c[t]); nv = t + 1; }
                 }
-                const uint32_t tx_bytes = nv * a_bytes + b_bytes;
+                const uint32_t tx_bytes = nv * a_bytes + P.b_tx;
                 const int ncol = st.nt * (int)NT;
                 const int tap_end = p.groups[st.g].tap_begin + p.groups[st.g].tap_count;
                 for (int ti = p.groups[st.g].tap_begin; ti < tap_end; ++ti) {
@@ -423,7 +423,8 @@ int igemm_conv(const Plan& p, const amb_conv_args* a) {
     P.NT = NT; P.n_ntiles = p.Cy / NT;
     P.kchunks = p.Cx / KC;
     P.a_bytes = 128u * KC * 2u;
-    P.b_bytes = ((uint32_t)NT * KC * 2u + 1023u) & ~1023u;
+    P.b_tx = (uint32_t)NT * KC * 2u;
+    P.b_bytes = (P.b_tx + 1023u) & ~1023u;
     // T independent accumulators per CTA iteration: dependent tcgen05.mma on ONE accumulator are latency-bound
     // (~100 ns each, measured), so narrow-N layers interleave up to 4 tiles; the weight slab is shared by all of them.
     int T = 256 / NT;                 // 2 buffers x T x NT TMEM columns <= 512
