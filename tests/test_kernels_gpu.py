@@ -1,0 +1,143 @@
+"""GPU parity tests (pytest -m gpu): every kernel through the C ABI against fp32 torch / the oracle on identical inputs,
+then the whole SparK / AnatoMask path through the reference-named modules against the oracle port."""
+import pytest
+import torch
+
+from tests import kernel_checks as kc
+from tests import model_checks as mc
+
+pytestmark = pytest.mark.gpu
+D, T, V1 = 1, 2, 3      # AMB_IMPL_DIRECT, AMB_IMPL_TCGEN05, AMB_IMPL_TCGEN05_V1
+
+
+def test_library_loaded_and_no_cpu_path():
+    from anatomask_b200 import _lib
+    assert _lib.load().amb_sm_arch() == 100
+    assert torch.cuda.is_available()
+
+
+@pytest.mark.parametrize('name', ['layout', 'loss', 'hard_mask', 'ema_adamw', 'proj', 'stem'])
+def test_hbm_bound_kernels(name):
+    kc.CHECKS[name]()
+
+
+@pytest.mark.parametrize('kw', [
+    dict(mode='sparse', act=1, residual=True), dict(mode='sparse', act=0, residual=False, Cc=32, S=32),
+    dict(mode='dense', act=2, residual=False), dict(mode='dense', act=0, residual=False, Cc=512, S=8),
+    dict(mode='fill', act=0, residual=False)])
+def test_norm_family(kw):
+    kc.check_norm(**kw)
+
+
+@pytest.mark.parametrize('kw', [
+    dict(Cin=16, Cout=16, S=8, impl=D), dict(Cin=16, Cout=24, S=8, stride=2, impl=D),
+    dict(Cin=8, Cout=16, S=8, k=1, stride=2, impl=D), dict(Cin=16, Cout=16, S=16, impl=D, masked=True),
+    # tcgen05 implicit GEMM: 128B / 64B / 32B swizzle, N tiles, box clipping, stride 2, 1x1
+    dict(Cin=64, Cout=64, S=16, impl=T), dict(Cin=32, Cout=32, S=16, impl=T), dict(Cin=16, Cout=16, S=16, impl=T),
+    dict(Cin=128, Cout=256, S=8, impl=T), dict(Cin=512, Cout=512, S=8, impl=T),
+    dict(Cin=64, Cout=32, S=16, impl=T, bias=False), dict(Cin=64, Cout=64, S=12, impl=T),
+    dict(Cin=256, Cout=128, S=4, impl=T), dict(Cin=64, Cout=128, S=16, stride=2, impl=T),
+    dict(Cin=32, Cout=64, S=16, k=1, stride=2, impl=T), dict(Cin=64, Cout=64, S=16, k=1, impl=T),
+    dict(Cin=64, Cout=64, S=32, impl=T), dict(Cin=64, Cout=32, S=24, impl=T),
+    # masked: active-tile work-list (patch edge >= 8) and dense tiles + epilogue mask (patch edge 4)
+    dict(Cin=32, Cout=32, S=32, impl=T, masked=True), dict(Cin=64, Cout=64, S=16, impl=T, masked=True),
+    dict(Cin=128, Cout=128, S=8, impl=T, masked=True), dict(Cin=32, Cout=64, S=32, stride=2, impl=T, masked=True),
+    dict(Cin=32, Cout=64, S=32, k=1, stride=2, impl=T, masked=True),
+    dict(Cin=64, Cout=64, S=32, impl=T, masked=True, f=8)])
+def test_conv_fwd_dgrad_wgrad(kw):
+    kc.check_conv(**kw)
+
+
+@pytest.mark.parametrize('kw', [dict(Cin=16, Cout=8, S=4, impl=D), dict(Cin=64, Cout=64, S=8, impl=T),
+                                dict(Cin=512, Cout=512, S=4, impl=T), dict(Cin=32, Cout=32, S=8, impl=T)])
+def test_conv_transpose(kw):
+    kc.check_convT(**kw)
+
+
+@pytest.mark.parametrize('kw', [dict(), dict(Cin=64, Cout=64, S=32)])
+def test_conv_epilogue_statistics(kw):
+    kc.check_conv_stats(**kw)
+
+
+def test_direct_and_tcgen05_agree_exactly_on_integers():
+    """Differential check with small-integer data (every product and partial sum is exact in bf16/fp32): the CUDA-core
+    gather kernel and the tcgen05 kernel must agree bit-for-bit, independently of summation order."""
+    from anatomask_b200 import ops, _lib as L
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(0)
+    x = torch.randint(-3, 4, (2, 16, 16, 16, 64), generator=g).to(torch.bfloat16).to(dev)
+    w = torch.randint(-2, 3, (64, 64, 3, 3, 3), generator=g).float().to(dev)
+    wp = ops._pack(w, 27, 64, 64, 1, 64 * 27, 27)
+    ys = []
+    for impl in (L.IMPL_DIRECT, L.IMPL_TCGEN05_V1):
+        y = torch.empty(2, 16, 16, 16, 64, dtype=torch.bfloat16, device=dev)
+        ops._conv_call(L.OP_CONV, impl, (2, 16, 16, 16), 64, 64, 3, 1, x, y, wp)
+        ys.append(y)
+    torch.cuda.synchronize()
+    assert torch.equal(ys[0], ys[1])
+
+
+@pytest.mark.parametrize('name,seed', [('tiny', 3), ('S64', 5), ('B64', 5)])
+def test_spark_step_matches_oracle(name, seed):
+    mc.check_spark(name=name, seed=seed, verbose=False)
+
+
+def test_anatomask_steps_match_oracle():
+    mc.check_anatomask_steps()
+
+
+def test_golden_fixture_from_the_unmodified_reference(golden_dir):
+    """The CUDA path against the committed fixture produced by the reference itself (oracle/make_golden.py)."""
+    import os
+    from oracle import reference_port as rp
+    g = torch.load(os.path.join(golden_dir, 'spark_S64.pt'), weights_only=False)
+    cfg = rp.Cfg(**g['cfg'])
+    model = mc.build(cfg, g['seed'], anatomask=True)
+    model.train()
+    inp = rp.make_input(cfg, g['batch'], g['seed']).cuda()
+    rec = model.reconstruct(inp, g['active'].cuda())
+    loss, pp = model.forward_loss(inp, rec, g['active'].cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - g['loss']) <= 1e-3 * abs(g['loss'])          # north-star tolerance: loss 1e-3 relative
+    assert float((pp.cpu() - g['per_patch']).norm() / g['per_patch'].norm()) < 5e-3
+    for k in ('dense_decoder.proj.weight', 'dense_decoder.dec.3.conv.3.weight', 'dense_decoder.dec.3.conv.4.weight'):
+        d = g['grads'][k]
+        got = dict(model.named_parameters())[k].grad.flatten()[:64].cpu().double()
+        err = float((got - d['head'].double()).norm() / d['head'].double().norm())
+        assert err < 2e-2, (k, err)                                       # bf16: 1e-2-class on well-conditioned tensors
+
+
+def test_device_rng_step_runs_without_host_sync():
+    mc.check_device_step()
+
+
+def test_full_size_properties_B128():
+    """BASELINE size (STUNet-B, 128^3, batch 2): size-independent properties of one AnatoMask step."""
+    from oracle import reference_port as rp
+    from anatomask_b200.trainer import PretrainEngine, build_model
+    cfg = rp.CONFIGS['B128']
+    model = build_model('B', cfg.input_size, anatomask=True)
+    eng = PretrainEngine(model, epochs=1000, anatomask=True, mask_rng='device')
+    inp = torch.randn(2, 1, 128, 128, 128, device='cuda')
+    loss, mask, recon = eng.step(inp, epoch=500)
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss)
+    assert mask.shape == (2, 1, 8, 8, 8) and int(mask.sum()) == 2 * cfg.len_keep          # exactly len_keep visible
+    ll, _ = rp.hard_mask_lengths(cfg, 500, 999)
+    order = torch.argsort(recon, dim=1)
+    hard = order[:, cfg.L - ll:]
+    assert not mask.view(2, -1).gather(1, hard).any()                                       # hard patches are masked
+    assert (recon.view(2, -1) >= 0).all()
+    # dead densify level keeps grad None; every live parameter received a finite gradient
+    for n, p in model.named_parameters():
+        if n.startswith(('densify_norms.4', 'densify_projs.4', 'mask_tokens.4')):
+            assert p.grad is None
+        else:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    # encoder features are exactly zero outside visible patches (the zero-invariant of SURVEY.md §7.2)
+    from anatomask_b200 import encoder3D
+    feats = model.sparse_encoder(inp)
+    m1 = encoder3D._cur_active
+    up = m1.repeat_interleave(16, 2).repeat_interleave(16, 3).repeat_interleave(16, 4)
+    assert float(feats[0].float().abs().mul((~up).float()).max()) == 0.0

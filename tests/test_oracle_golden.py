@@ -74,11 +74,14 @@ def test_anatomask_steps_match_reference(golden_dir, name):
             t = have[k].detach().double().flatten()[:64]
             err = float((t - d['head'].double()).abs().max())
             zero_grad_bias = 'sparse_encoder' in k and k.endswith(('conv1.bias', 'conv2.bias'))
-            bound = 2.2 * nsteps * lr if zero_grad_bias else 1.5 * lr
+            # any element whose gradient is at noise level can flip sign under Adam: bounded by the step size only
+            bound = 2.2 * nsteps * lr
             if which == 'teacher':
                 bound *= 0.01        # EMA decay >= 0.999 scales student jitter by <= 1e-3 per step
                 bound += 1e-6
             assert err <= bound, (which, k, err, bound)
+            if not zero_grad_bias and d['norm'] > 1e-3:
+                assert abs(float(have[k].detach().double().norm()) - d['norm']) <= 5e-3 * d['norm'], (which, k)
 
 
 def test_hard_mask_schedule_lengths():
