@@ -18,6 +18,7 @@ from .spark3D import SparK as _SparKBase
 class SparK(_SparKBase):
     mask_rng = 'numpy'            # 'numpy' (reference RNG replay, host sync) | 'device' (no host sync)
     _rng_offset = 0
+    rng_counter = None            # optional device uint64 step counter (CUDA-graph replay: the RNG stream must not be baked in)
 
     @torch.no_grad()
     def generate_mask(self, loss_pred, guide=True, epoch=0, total_epoch=200, generator=None, original_mask=None):
@@ -30,7 +31,8 @@ class SparK(_SparKBase):
         if len_loss <= 0:
             if self.mask_rng == 'device':
                 type(self)._rng_offset += 1
-                _, mk = ops.hard_mask(loss_pred, 0, self.len_keep, seed=0x5EED, offset=type(self)._rng_offset * B * L)
+                off = 0 if self.rng_counter is not None else type(self)._rng_offset * B * L
+                _, mk = ops.hard_mask(loss_pred, 0, self.len_keep, seed=0x5EED, offset=off, offset_dev=self.rng_counter)
                 mk = mk.bool().view(B, 1, h, w, d)
                 return mk, mk
             noise = torch.randn(B, L, device=dev)            # P/AnatoMask.py:99-103 (device RNG in the reference too)
@@ -40,8 +42,9 @@ class SparK(_SparKBase):
         easy_len = nm - len_loss
         if self.mask_rng == 'device':
             type(self)._rng_offset += 1
-            _, mk = ops.hard_mask(loss_pred, len_loss, self.len_keep, seed=0x5EED,
-                                  offset=type(self)._rng_offset * B * L)
+            off = 0 if self.rng_counter is not None else type(self)._rng_offset * B * L
+            _, mk = ops.hard_mask(loss_pred, len_loss, self.len_keep, seed=0x5EED, offset=off,
+                                  offset_dev=self.rng_counter)
             mk = mk.bool().view(B, 1, h, w, d)
             return mk, mk
         # parity mode: device top-k, then numpy's shuffles replayed in the reference's order (two per sample)

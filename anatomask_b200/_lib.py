@@ -62,7 +62,8 @@ _SIGNATURES = {
     'amb_add': (i32, [vp, vp, vp, i64, vp]),
     'amb_patch_loss_fwd': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
     'amb_patch_loss_bwd': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
-    'amb_hard_mask': (i32, [vp, i32, i32, i32, i32, u64, u64, vp, vp, vp, vp]),
+    'amb_hard_mask': (i32, [vp, i32, i32, i32, i32, u64, u64, vp, vp, vp, vp, vp]),
+    'amb_step_dev': (i32, [vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, i32, i32, vp]),
     'amb_ema_update': (i32, [vp, vp, i64, f64, vp]),
     'amb_sumsq': (i32, [vp, i64, vp, vp]),
     'amb_adamw_step': (i32, [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i32, vp, f64, f64, vp]),

@@ -173,8 +173,9 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 
 __global__ void __launch_bounds__(512)
 hard_mask_kernel(const float* __restrict__ loss_pred, int L, int Lp2, int len_loss, int len_keep,
-                 unsigned long long seed, unsigned long long offset, int* __restrict__ hard,
-                 int* __restrict__ order, uint8_t* __restrict__ mask_out) {
+                 unsigned long long seed, unsigned long long offset, const unsigned long long* __restrict__ offset_dev,
+                 int* __restrict__ hard, int* __restrict__ order, uint8_t* __restrict__ mask_out) {
+    if (offset_dev) offset += *offset_dev * (unsigned long long)(gridDim.x * L);     // graph-replay safe RNG stream
     extern __shared__ unsigned char smraw[];
     float* key = reinterpret_cast<float*>(smraw);
     int* idx = reinterpret_cast<int*>(key + Lp2);
@@ -232,6 +233,25 @@ __global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ mo
         ema[i] = __fadd_rn(__fmul_rn(ema[i], d), __fmul_rn(omd, model[i]));
 }
 
+// device-scalar variants (CUDA-graph replay: the per-step scalars live in a small device buffer refreshed by the host)
+__global__ void ema_dev_kernel(float* __restrict__ ema, const float* __restrict__ model, long n,
+                               const float* __restrict__ hyper) {
+    const float d = hyper[0], omd = hyper[1];
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long n4 = n >> 2;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 e = reinterpret_cast<float4*>(ema)[i];
+        float4 m = reinterpret_cast<const float4*>(model)[i];
+        e.x = __fadd_rn(__fmul_rn(e.x, d), __fmul_rn(omd, m.x));
+        e.y = __fadd_rn(__fmul_rn(e.y, d), __fmul_rn(omd, m.y));
+        e.z = __fadd_rn(__fmul_rn(e.z, d), __fmul_rn(omd, m.z));
+        e.w = __fadd_rn(__fmul_rn(e.w, d), __fmul_rn(omd, m.w));
+        reinterpret_cast<float4*>(ema)[i] = e;
+    }
+    for (long i = (n4 << 2) + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        ema[i] = __fadd_rn(__fmul_rn(ema[i], d), __fmul_rn(omd, model[i]));
+}
+
 __global__ void sumsq_kernel(const float* __restrict__ g, long n, double* __restrict__ out) {
     __shared__ double sh[32];
     const long stride = (long)gridDim.x * blockDim.x;
@@ -263,6 +283,31 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                              float gscale) {
     float coef = gscale;   // gscale = 1/world when g holds the all-reduced SUM of the ranks' gradients
     if (gnorm_sq) {   // torch.nn.utils.clip_grad_norm_: coef = clamp(max_norm / (norm + 1e-6), max=1)
+        float norm = (float)sqrt(*gnorm_sq) * gscale;
+        coef = fminf(max_norm / (norm + 1e-6f), 1.f) * gscale;
+    }
+    const float step_size = lr / bc1;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float gi = g[i] * coef;
+        float pi = p[i] * (1.f - lr * wd);
+        float mi = m[i] + (gi - m[i]) * (1.f - b1);
+        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - step_size * (mi / denom);
+        m[i] = mi;
+        v[i] = vi;
+    }
+}
+
+// hyper = {lr, beta1, beta2, eps, wd, bc1, sqrt(bc2), max_norm, gscale}
+__global__ void adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long n, const float* __restrict__ hyper,
+                                 const double* __restrict__ gnorm_sq) {
+    const float lr = hyper[2 + 0], b1 = hyper[2 + 1], b2 = hyper[2 + 2], eps = hyper[2 + 3], wd = hyper[2 + 4],
+                bc1 = hyper[2 + 5], bc2_sqrt = hyper[2 + 6], max_norm = hyper[2 + 7], gscale = hyper[2 + 8];
+    float coef = gscale;
+    if (gnorm_sq) {
         float norm = (float)sqrt(*gnorm_sq) * gscale;
         coef = fminf(max_norm / (norm + 1e-6f), 1.f) * gscale;
     }
@@ -510,16 +555,17 @@ extern "C" int amb_patch_loss_bwd(const float* inp, const float* rec, const uint
 }
 
 extern "C" int amb_hard_mask(const float* loss_pred, int B, int L, int len_loss, int len_keep,
-                             unsigned long long seed, unsigned long long offset, int* hard, int* order,
-                             uint8_t* mask_out, void* stream) {
+                             unsigned long long seed, unsigned long long offset,
+                             const unsigned long long* offset_dev, int* hard, int* order, uint8_t* mask_out,
+                             void* stream) {
     AMB_CHECK(L >= 1 && L <= 4096, AMB_ERR_ARG, "hard mask: L=%d out of range (1..4096)", L);
     AMB_CHECK(len_loss >= 0 && len_loss <= L && len_keep >= 0 && len_keep + len_loss <= L, AMB_ERR_ARG,
               "hard mask: len_loss=%d len_keep=%d L=%d", len_loss, len_keep, L);
     int Lp2 = 1;
     while (Lp2 < L) Lp2 <<= 1;
     size_t smem = (size_t)Lp2 * 8 + L;
-    hard_mask_kernel<<<B, 512, smem, (cudaStream_t)stream>>>(loss_pred, L, Lp2, len_loss, len_keep, seed, offset, hard,
-                                                             order, mask_out);
+    hard_mask_kernel<<<B, 512, smem, (cudaStream_t)stream>>>(loss_pred, L, Lp2, len_loss, len_keep, seed, offset,
+                                                             offset_dev, hard, order, mask_out);
     AMB_LAUNCH_CHECK();
     return 0;
 }
@@ -529,6 +575,21 @@ extern "C" int amb_ema_update(float* ema, const float* model, long n, double dec
     ema_kernel<<<grid_cap(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(ema, model, n, (float)decay,
                                                                               (float)(1.0 - decay));
     AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_step_dev(float* ema, const float* model, long n_ema, float* p, const float* g, float* m, float* v,
+                            long n_live, const float* hyper, const double* gnorm_sq, int do_adamw, int do_ema,
+                            void* stream) {
+    if (do_adamw) {
+        adamw_dev_kernel<<<grid_cap(n_live, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n_live, hyper, gnorm_sq);
+        AMB_LAUNCH_CHECK();
+    }
+    if (do_ema) {
+        AMB_CHECK(((uintptr_t)ema % 16 == 0) && ((uintptr_t)model % 16 == 0), AMB_ERR_ARG, "ema: 16B alignment required");
+        ema_dev_kernel<<<grid_cap(n_ema / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(ema, model, n_ema, hyper);
+        AMB_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -466,15 +466,15 @@ class PatchLossFn(torch.autograd.Function):
 
 
 def hard_mask(loss_pred: torch.Tensor, len_loss: int, len_keep: int, seed: int = 0, offset: int = 0,
-              want_mask: bool = True, want_order: bool = False):
+              want_mask: bool = True, want_order: bool = False, offset_dev: Optional[torch.Tensor] = None):
     """Returns (hard (B,len_loss) int32 in ascending-loss order, mask (B,L) uint8 or None[, order (B,L) int32])."""
     loss_pred = loss_pred.float().contiguous()
     B, Lp = loss_pred.shape
     hard = torch.empty((B, max(len_loss, 1)), dtype=torch.int32, device=loss_pred.device)
     mask = torch.empty((B, Lp), dtype=torch.uint8, device=loss_pred.device) if want_mask else None
     order = torch.empty((B, Lp), dtype=torch.int32, device=loss_pred.device) if want_order else None
-    L.call('amb_hard_mask', _p(loss_pred), B, Lp, len_loss, len_keep, seed, offset, _p(hard), _p(order), _p(mask),
-           _stream())
+    L.call('amb_hard_mask', _p(loss_pred), B, Lp, len_loss, len_keep, seed, offset, _p(offset_dev), _p(hard), _p(order),
+           _p(mask), _stream())
     if want_order:
         return hard[:, :len_loss], mask, order
     return hard[:, :len_loss], mask

@@ -132,6 +132,16 @@ class PretrainEngine:
             self.world = dist.get_world_size(process_group)
         self.mask_rng = mask_rng
         self._rng_calls = 0
+        # CUDA-graph mode (no host sync in the step): per-step scalars live in `hyper` on the device, the RNG stream is
+        # driven by a device step counter, and the whole step (teacher fwd, hard mask, student fwd/bwd, all-reduce,
+        # clip + AdamW, EMA — ~430 launches) is replayed as ONE graph launch
+        dev = self.arena.flat.device
+        self.hyper = torch.zeros(16, dtype=torch.float32, device=dev)
+        self._hyper_host = torch.zeros(16, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else torch.zeros(16)
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._graphs = {}
+        self._static_inp = None
+        self._static_out = None
 
     # ---- pieces ---------------------------------------------------------------------------------------------
     def random_mask(self, B: int, device) -> torch.Tensor:
@@ -158,6 +168,88 @@ class PretrainEngine:
         if self.tarena.iflat is not None:                # int64 num_batches_tracked: lerp then truncate (timm copy_)
             ti, si = self.tarena.iflat, self.arena.iflat
             ti.copy_(ti * decay + (1. - decay) * si)
+
+    # ---- CUDA-graph path --------------------------------------------------------------------------------------
+    def _set_hyper(self, epoch: int):
+        b1, b2 = self.betas
+        t = self.t + 1
+        d = ema_decay_at_epoch(epoch, self.epochs)
+        h = self._hyper_host
+        h[0], h[1] = d, 1.0 - d
+        h[2], h[3], h[4], h[5], h[6] = lr_at_epoch(epoch, self.lr, max_epochs=self.epochs), b1, b2, self.eps, self.wd
+        h[7], h[8], h[9], h[10] = 1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t), self.clip, 1.0 / self.world
+        self.hyper.copy_(h, non_blocking=True)
+
+    def _device_step(self, inp: torch.Tensor, len_loss_epoch: int):
+        """The AnatoMask iteration with every per-step scalar read from device memory (graph-capturable)."""
+        from . import _lib as L
+        B = inp.shape[0]
+        m = self.model
+        Lp = m.fmap_h * m.fmap_w * m.fmap_d
+        self.step_counter.add_(1)
+        zeros = torch.zeros(B, Lp, dtype=torch.float32, device=inp.device)
+        _, mk = ops.hard_mask(zeros, 0, m.len_keep, seed=0xA11CE, offset=0, offset_dev=self.step_counter)
+        mask1 = mk.bool().view(B, 1, m.fmap_h, m.fmap_w, m.fmap_d)
+        with torch.no_grad():
+            rec1 = self.teacher.reconstruct(inp, mask1)
+            recon = self.teacher.teacher_loss(inp, rec1, mask1)
+        mask, _ = self.teacher.generate_mask(recon, guide=True, epoch=len_loss_epoch, total_epoch=self.epochs - 1)
+        rec = m.reconstruct(inp, mask)
+        loss, _ = m.forward_loss(inp, rec, mask)
+        self.arena.zero_grad()
+        loss.backward()
+        a, ta = self.arena, self.tarena
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(a.grad, group=self.group)
+        gn = torch.zeros(1, dtype=torch.float64, device=inp.device)
+        L.call('amb_sumsq', ops._p(a.grad), a.grad.numel(), ops._p(gn), ops._stream())
+        L.call('amb_step_dev', ops._p(ta.flat), ops._p(a.flat), ta.flat.numel(), ops._p(a.flat), ops._p(a.grad),
+               ops._p(self.m), ops._p(self.v), a.n_live, ops._p(self.hyper), ops._p(gn), 1, 1, ops._stream())
+        if ta.iflat is not None:
+            ta.iflat.copy_(ta.iflat * self.hyper[0] + self.hyper[1] * a.iflat)
+        return loss.detach(), mask, recon
+
+    def _state_snapshot(self):
+        keep = [self.arena.flat, self.m, self.v, self.tarena.flat, self.step_counter]
+        if self.arena.iflat is not None:
+            keep += [self.arena.iflat, self.tarena.iflat]
+        return keep, [t.clone() for t in keep]
+
+    def graph_step(self, inp: torch.Tensor, epoch: int = 0):
+        """Same semantics as step() in device-RNG mode, replayed from a CUDA graph.  Graphs are keyed by the number of
+        hard patches (a launch parameter of the top-k kernel that changes every few epochs)."""
+        from .AnatoMask import SparK as _AM
+        m = self.model
+        nm = m.fmap_h * m.fmap_w * m.fmap_d - m.len_keep
+        len_loss = int(nm * (float((epoch + 1) / (self.epochs - 1)) * 0.5))
+        self.model.train()
+        if self._static_inp is None or self._static_inp.shape != inp.shape:
+            self._static_inp = torch.empty_like(inp)
+            self._graphs.clear()
+        self._static_inp.copy_(inp, non_blocking=True)
+        self._set_hyper(epoch)
+        if len_loss not in self._graphs:
+            self._graphs.clear()                         # one resident graph (its private pool holds a full step)
+            self.teacher.mask_rng = 'device'
+            self.teacher.rng_counter = self.step_counter
+            tensors, saved = self._state_snapshot()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                # warm-up on a side stream (allocator, function attributes)
+                for _ in range(2):
+                    self._device_step(self._static_inp, epoch)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._device_step(self._static_inp, epoch)
+            for t, s0 in zip(tensors, saved):            # warm-up / capture must not count as training steps
+                t.copy_(s0)
+            self._graphs[len_loss] = (g, out)
+        g, out = self._graphs[len_loss]
+        g.replay()
+        self.t += 1
+        return out
 
     # ---- steps ----------------------------------------------------------------------------------------------
     def spark_step(self, inp: torch.Tensor, active: Optional[torch.Tensor] = None, epoch: int = 0) -> torch.Tensor:

@@ -170,25 +170,47 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
+    # The step runs as ONE CUDA-graph launch (no host sync inside: device RNG, device-side scalars); --no-graph or a
+    # failed capture falls back to eager launches of the same kernels.
+    use_graph = not args.no_graph
+    graph_err = None
+    if use_graph:
+        try:
+            eng.graph_step(inp, epoch)
+            torch.cuda.synchronize()
+        except Exception as e:                                   # noqa: BLE001
+            use_graph, graph_err = False, f'{type(e).__name__}: {e}'[:200]
+            torch.cuda.synchronize()
+    run = (lambda x: eng.graph_step(x, epoch)) if use_graph else (lambda x: eng.step(x, epoch))
     for _ in range(args.warmup):
-        eng.step(inp, epoch)
+        run(inp)
     barrier()
     # ---- timed region 1: inputs resident in HBM -----------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
-    ops.PROFILE = []
-    lib.amb_reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        eng.step(inp, epoch)
+        run(inp)
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = int(lib.amb_launch_count())
-    prof, ops.PROFILE = ops.PROFILE, None
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
     value = B * world / (ms_step / 1e3)
+    # ---- the same K steps launched eagerly with a CUDA-event pair around every conv launch: per-kernel durations for
+    #      the roofline and the launch count (a graph replay issues exactly these launches) ---------------------------
+    ops.PROFILE = []
+    lib.amb_reset_launch_count()
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(args.steps):
+        eng.step(inp, epoch)
+    p1.record()
+    barrier()
+    ms_eager_total = p0.elapsed_time(p1)
+    launches = int(lib.amb_launch_count())
+    prof, ops.PROFILE = ops.PROFILE, None
     # ---- roofline of the dominant kernel family (live CUDA-event timing of every launch in the timed region) ----
     fam = {}
     for kind, flops, a, b in prof:
@@ -206,7 +228,7 @@ def run_ours(args):
                 'peak_source': f'{peak_src} bf16_tflops_sustained (kernel timed inside a long step)', 'traffic': None,
                 'launches_timed': n_k, 'avg_launch_ms': ms_k / max(1, n_k),
                 'all_conv_kernels': {'achieved': conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0,
-                                     'share_of_step': conv_ms / ms_total,
+                                     'share_of_step': conv_ms / ms_total, 'eager_pass_ms_per_step': ms_eager_total / args.steps,
                                      'per_family_tflops': {k: v[0] / (v[1] * 1e-3) / 1e12 for k, v in fam.items() if v[1] > 0}},
                 'algorithmic_flops_per_step': conv_fl / args.steps}
     # ---- timed region 2: end to end through the public API, host buffers -----------------------------------
@@ -214,7 +236,7 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         x = host.to(dev, non_blocking=True)
-        loss, _, _ = eng.step(x, epoch)
+        loss, _, _ = run(x)
         lv = loss.item()                       # device → host read of the step's result
     e1.record()
     barrier()
@@ -227,6 +249,7 @@ def run_ours(args):
            'config': {'workload': f'STUNet-{args.model} AnatoMask step (teacher fwd + hard mask + student fwd/bwd + clip + '
                                   f'AdamW + EMA), 1x{S}^3 volumes, batch {B}/GPU, mask 0.6, epoch 500/1000 (len_loss 76)',
                       'global_batch': B * world, 'parallelism': f'dp{world}',
+                      'cuda_graph': use_graph, 'graph_error': graph_err,
                       'l2': 'per-step working set (multi-GB activations) >> 126 MB L2; no flush needed',
                       'algorithmic_tflop_per_volume': 4 * F_FWD_GF / 1e3 if (args.model == 'B' and S == 128) else None},
            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline}
@@ -248,6 +271,7 @@ if __name__ == '__main__':
     ap.add_argument('--size', type=int, default=128)
     ap.add_argument('--batch', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true')
     a = ap.parse_args()
     if a.impl == 'reference':
         run_reference(a)

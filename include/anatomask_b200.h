@@ -187,8 +187,8 @@ int amb_patch_loss_bwd(const float* inp, const float* rec, const uint8_t* active
  * mask_out (B, L) uint8: len_keep visible patches drawn uniformly from the non-hard ones with a counter-based
  * device RNG (seed, offset) — "throughput mode"; parity mode replays numpy's shuffle on the host from `hard`.  */
 int amb_hard_mask(const float* loss_pred, int B, int L, int len_loss, int len_keep, unsigned long long seed,
-                  unsigned long long offset, int* hard, int* order /* optional (B,L): full ascending argsort */,
-                  uint8_t* mask_out, void* stream);
+                  unsigned long long offset, const unsigned long long* offset_dev /* optional device step counter */,
+                  int* hard, int* order /* optional (B,L): full ascending argsort */, uint8_t* mask_out, void* stream);
 
 /* ---- flat-arena optimiser pieces: EMA teacher (timm ModelEma.update), grad-norm clip + AdamW ------------------- */
 int amb_ema_update(float* ema, const float* model, long n, double decay, void* stream);   /* ema = ema*d + (1-d)*model, fp32 products rounded separately like torch */
@@ -196,6 +196,11 @@ int amb_sumsq(const float* g, long n, double* out, void* stream);               
 int amb_adamw_step(float* p, const float* g, float* m, float* v, long n, double lr, double beta1, double beta2,
                    double eps, double weight_decay, int step, const double* gnorm_sq, double max_norm,
                    double gscale /* g is multiplied by this first: 1/world after a SUM all-reduce */, void* stream);
+
+/* CUDA-graph-replayable optimiser tail: the per-step scalars are read from device memory,
+ * hyper = {ema_decay, 1-ema_decay, lr, beta1, beta2, eps, weight_decay, 1-beta1^t, sqrt(1-beta2^t), max_norm, gscale}. */
+int amb_step_dev(float* ema, const float* model, long n_ema, float* p, const float* g, float* m, float* v, long n_live,
+                 const float* hyper, const double* gnorm_sq, int do_adamw, int do_ema, void* stream);
 
 #ifdef __cplusplus
 }
