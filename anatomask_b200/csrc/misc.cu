@@ -416,26 +416,47 @@ stem_wgrad_kernel(Geo g, const float* __restrict__ inp, const bf16* __restrict__
     const int slot = threadIdx.x & 31;
     const int cg = (threadIdx.x >> 5) % CG;
     const int lane = (threadIdx.x >> 5) / CG;
-    const long nvox = geo_num_runs(g) << g.lgP;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     if (slot < 30) {
         const int dz = slot < 27 ? slot / 9 - 1 : 0, dy = slot < 27 ? (slot / 3) % 3 - 1 : 0,
                   dx = slot < 27 ? slot % 3 - 1 : 0;
-        for (long t = (long)blockIdx.x * lanes + lane; t < nvox; t += (long)gridDim.x * lanes) {
-            const int v = (int)(t & (g.P - 1));
-            RunPos r = decode_run(g, t >> g.lgP);
-            const long voxel = r.voxel + v;
-            const int x = (int)(voxel % g.W);
-            const int y = (int)((voxel / g.W) % g.H);
-            const int z = (int)((voxel / ((long)g.W * g.H)) % g.D);
-            float d[8];
-            unpack8(*reinterpret_cast<const bf16x8*>((slot >= 28 ? dy3 : dy1) + voxel * C + cg * 8), d);
-            float xv = 1.f;
-            if (slot < 27 || slot == 28) xv = masked_input(g, inp, r.n, z + dz, y + dy, x + dx);
+        const bool needs_x = slot < 27 || slot == 28;
+        const bf16* __restrict__ dsrc = slot >= 28 ? dy3 : dy1;
+        const long nruns = geo_num_runs(g);
+        // one run = P consecutive voxels along x inside one visible patch: all index arithmetic is per run, the inner
+        // loop is one 4-byte and one 16-byte load plus 8 FMAs per voxel
+        for (long run = (long)blockIdx.x * lanes + lane; run < nruns; run += (long)gridDim.x * lanes) {
+            RunPos r = decode_run(g, run);
+            const int x0 = (int)(r.voxel % g.W);
+            const int y = (int)((r.voxel / g.W) % g.H);
+            const int z = (int)((r.voxel / ((long)g.W * g.H)) % g.D);
+            const int iz = z + dz, iy = y + dy;
+            const bool row_ok = (unsigned)iz < (unsigned)g.D && (unsigned)iy < (unsigned)g.H;
+            bool a_lo = false, a_mid = false, a_hi = false;
+            const float* row = inp;
+            if (needs_x && row_ok) {
+                const int px = x0 >> g.lgP;
+                const uint8_t* arow = g.active + ((r.n * g.fd + (iz >> g.lgP)) * g.fh + (iy >> g.lgP)) * g.fw;
+                a_mid = arow[px] != 0;
+                a_lo = px > 0 && arow[px - 1] != 0;
+                a_hi = px + 1 < g.fw && arow[px + 1] != 0;
+                row = inp + (((long)r.n * g.D + iz) * g.H + iy) * g.W;
+            }
+            const bf16* dptr = dsrc + r.voxel * C + cg * 8;
+            for (int v = 0; v < g.P; ++v) {
+                float xv = 1.f;
+                if (needs_x) {
+                    const int x = x0 + v + dx;
+                    const bool ok = row_ok && (v + dx < 0 ? a_lo : (v + dx >= g.P ? a_hi : a_mid));
+                    xv = ok ? row[x] : 0.f;
+                }
+                float d[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(dptr + (long)v * C), d);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(d[j], xv, acc[j]);
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(d[j], xv, acc[j]);
+            }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) atomicAdd(&sacc[slot * C + cg * 8 + j], acc[j]);

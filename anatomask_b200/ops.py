@@ -29,8 +29,8 @@ PROFILE = None
 
 
 class _Timed:
-    def __init__(self, kind: str, flops: float):
-        self.kind, self.flops = kind, flops
+    def __init__(self, kind: str, flops: float, tag: str = ''):
+        self.kind, self.flops = kind + tag, flops
 
     def __enter__(self):
         if PROFILE is not None:

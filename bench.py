@@ -216,6 +216,11 @@ def run_ours(args):
     for kind, flops, a, b in prof:
         d = fam.setdefault(kind, [0.0, 0.0, 0])
         d[0] += flops; d[1] += a.elapsed_time(b); d[2] += 1
+    if os.environ.get('AMB_BENCH_DUMP') and rank == 0:           # per-launch table of the last profiled step
+        n_per = len(prof) // args.steps
+        rows = [(k, f, a.elapsed_time(b)) for k, f, a, b in prof[-n_per:]]
+        for i, (k, f, ms) in enumerate(rows):
+            print(f'#LAUNCH {i:3d} {k:12s} {f / 1e9:9.1f} GF {ms:7.3f} ms {f / ms / 1e9:8.1f} TF/s', file=sys.stderr)
     peaks, peak_src = _peaks()
     peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1400.0)))
     igemm = [v for k, v in fam.items() if not k.endswith('wgrad')]
