@@ -132,6 +132,11 @@ def cpu_baseline_sample():
             'sample': f'1 AnatoMask step of 1 volume (1x128^3) with the oracle port (PyTorch fp32, {cores} threads): {dt:.1f} s'}
 
 
+def _mark(msg):
+    if os.environ.get('AMB_BENCH_VERBOSE'):
+        print(f'[bench r{os.environ.get("RANK", "0")}] {msg} t={time.time():.1f}', file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     import torch.distributed as dist
     from anatomask_b200 import ops, _lib
@@ -146,6 +151,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
         group = dist.group.WORLD
+    _mark('pg up')
     lib = _lib.load()
     B, S = args.batch, args.size
     torch.manual_seed(1234 + rank)
@@ -153,6 +159,7 @@ def run_ours(args):
     if world > 1:                                    # identical initial weights on every rank (DDP broadcast)
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
+    _mark('model built + broadcast')
     eng = PretrainEngine(model, lr=1e-4, epochs=1000, anatomask=True, mask_rng='device', process_group=group)
     inp = torch.randn(B, 1, S, S, S, device=dev)
     host = torch.randn(B, 1, S, S, S).pin_memory()
@@ -173,6 +180,7 @@ def run_ours(args):
     # The step runs as ONE CUDA-graph launch (no host sync inside: device RNG, device-side scalars); --no-graph or a
     # failed capture falls back to eager launches of the same kernels.
     use_graph = not args.no_graph
+    _mark('engine up')
     graph_err = None
     if use_graph:
         try:
@@ -181,6 +189,7 @@ def run_ours(args):
         except Exception as e:                                   # noqa: BLE001
             use_graph, graph_err = False, f'{type(e).__name__}: {e}'[:200]
             torch.cuda.synchronize()
+    _mark(f'graph={use_graph} err={graph_err}')
     run = (lambda x: eng.graph_step(x, epoch)) if use_graph else (lambda x: eng.step(x, epoch))
     for _ in range(args.warmup):
         run(inp)
@@ -194,6 +203,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+    _mark(f'timed region done {ms_total:.1f} ms')
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
     value = B * world / (ms_step / 1e3)
