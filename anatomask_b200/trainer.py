@@ -180,9 +180,8 @@ class PretrainEngine:
         h[7], h[8], h[9], h[10] = 1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t), self.clip, 1.0 / self.world
         self.hyper.copy_(h, non_blocking=True)
 
-    def _device_step(self, inp: torch.Tensor, len_loss_epoch: int):
-        """The AnatoMask iteration with every per-step scalar read from device memory (graph-capturable)."""
-        from . import _lib as L
+    def _device_front(self, inp: torch.Tensor, len_loss_epoch: int):
+        """Teacher forward → hard mask → student forward/backward, every per-step scalar read from device memory."""
         B = inp.shape[0]
         m = self.model
         Lp = m.fmap_h * m.fmap_w * m.fmap_d
@@ -198,17 +197,29 @@ class PretrainEngine:
         loss, _ = m.forward_loss(inp, rec, mask)
         self.arena.zero_grad()
         loss.backward()
+        return loss.detach(), mask, recon
+
+    def _device_tail(self):
+        """Global-norm clip + AdamW + EMA from the (already all-reduced) gradient arena; scalars from `hyper`."""
+        from . import _lib as L
         a, ta = self.arena, self.tarena
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(a.grad, group=self.group)
-        gn = torch.zeros(1, dtype=torch.float64, device=inp.device)
+        gn = torch.zeros(1, dtype=torch.float64, device=a.flat.device)
         L.call('amb_sumsq', ops._p(a.grad), a.grad.numel(), ops._p(gn), ops._stream())
         L.call('amb_step_dev', ops._p(ta.flat), ops._p(a.flat), ta.flat.numel(), ops._p(a.flat), ops._p(a.grad),
                ops._p(self.m), ops._p(self.v), a.n_live, ops._p(self.hyper), ops._p(gn), 1, 1, ops._stream())
         if ta.iflat is not None:
             ta.iflat.copy_(ta.iflat * self.hyper[0] + self.hyper[1] * a.iflat)
-        return loss.detach(), mask, recon
+
+    def _allreduce_grads(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.arena.grad, group=self.group)
+
+    def _device_step(self, inp: torch.Tensor, len_loss_epoch: int):
+        out = self._device_front(inp, len_loss_epoch)
+        self._allreduce_grads()
+        self._device_tail()
+        return out
 
     def _state_snapshot(self):
         keep = [self.arena.flat, self.m, self.v, self.tarena.flat, self.step_counter]
@@ -240,14 +251,19 @@ class PretrainEngine:
                 for _ in range(2):
                     self._device_step(self._static_inp, epoch)
             torch.cuda.current_stream().wait_stream(side)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                out = self._device_step(self._static_inp, epoch)
+            # the NCCL all-reduce stays OUTSIDE the captured region (front graph → eager all-reduce → tail graph)
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                out = self._device_front(self._static_inp, epoch)
+            with torch.cuda.graph(g2):
+                self._device_tail()
             for t, s0 in zip(tensors, saved):            # warm-up / capture must not count as training steps
                 t.copy_(s0)
-            self._graphs[len_loss] = (g, out)
-        g, out = self._graphs[len_loss]
-        g.replay()
+            self._graphs[len_loss] = (g1, g2, out)
+        g1, g2, out = self._graphs[len_loss]
+        g1.replay()
+        self._allreduce_grads()
+        g2.replay()
         self.t += 1
         return out
 
