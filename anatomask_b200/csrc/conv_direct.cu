@@ -201,6 +201,9 @@ extern "C" int amb_conv(const amb_conv_args* a) {
         // active-patch work-list lets it skip masked tiles outright (patch edge >= 8 at the output resolution)
         const bool list_pays = a->active_list != nullptr && p.lgPv >= 3;
         if (a->impl != AMB_IMPL_TCGEN05_V1 && !list_pays) {
+            int r3 = igemm3_conv(p, a);          // halo planes + 4 interleaved tiles: narrow dense 3x3x3 layers
+            if (r3 < 0) return r3;
+            if (r3 == 1) return 0;
             int r2 = igemm2_conv(p, a);
             if (r2 < 0) return r2;
             if (r2 == 1) return 0;

@@ -185,6 +185,7 @@ static inline int plan_set_mask(Plan& p, int full_oD, int full_oH, int full_oW, 
 // not supported by it (caller falls back to the CUDA-core kernel), <0 on error.
 int igemm_conv(const Plan& p, const amb_conv_args* a);
 int igemm2_conv(const Plan& p, const amb_conv_args* a);
+int igemm3_conv(const Plan& p, const amb_conv_args* a);
 int igemm_wgrad(const Plan& p, const amb_wgrad_args* a);
 
 }  // namespace amb

@@ -36,7 +36,7 @@ def main(which):
     dev = torch.device('cuda:0')
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     # T1 = one accumulator per CTA iteration (dependent-MMA chain), T = interleaved accumulators (default)
-    impls = {'T1': (L.IMPL_TCGEN05_V1, '1'), 'T': (L.IMPL_TCGEN05_V1, None)}
+    impls = {'v1': (L.IMPL_TCGEN05_V1, None), 'v3': (L.IMPL_TCGEN05, None)}
     if which != 'all':
         impls = {which: impls[which]}
     out = []

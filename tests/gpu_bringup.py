@@ -35,6 +35,8 @@ CASES = [
     ('conv', dict(Cin=256, Cout=256, S=16, impl=T)), ('conv', dict(Cin=64, Cout=32, S=24, impl=T)),
     ('conv', dict(Cin=64, Cout=64, S=32, impl=T, masked=True, f=8)), ('conv', dict(Cin=512, Cout=512, S=16, N=1, impl=T)),
     ('conv_stats', dict(Cin=64, Cout=64, S=32)),
+    ('conv', dict(Cin=32, Cout=32, S=32, impl=T)), ('conv', dict(Cin=64, Cout=16, S=20, impl=T)),
+    ('conv', dict(Cin=128, Cout=64, S=32, N=1, impl=T)),
 ]
 
 if __name__ == '__main__':
