@@ -52,10 +52,13 @@ struct WgradParams {
     float* dw;
     uint32_t idesc;
     uint32_t a_layout, b_layout, a_sbo, b_sbo, a_kstep, b_kstep;
+    int a_slots;                  // dY ring depth (5 or 6 x 32 KB, what fits beside the X ring)
+    uint32_t b_slot_bytes;
 };
 
-#define WG_A_SLOTS 4
+#define WG_A_SLOTS_MAX 6
 #define WG_B_SLOTS 2
+#define WG_G 4                       // accumulator units (independent MMA chains) interleaved per K tile
 #define WG_SLOT_BYTES 32768u
 
 __device__ __forceinline__ long wg_num_ktiles(const WgradParams& P) {
@@ -92,18 +95,19 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int A_SLOTS = P.a_slots;
     uint8_t* a_ring = smem;
-    uint8_t* b_ring = smem + WG_A_SLOTS * WG_SLOT_BYTES;
-    uint8_t* ctrl = b_ring + WG_B_SLOTS * WG_SLOT_BYTES;
+    uint8_t* b_ring = smem + A_SLOTS * WG_SLOT_BYTES;
+    uint8_t* ctrl = b_ring + WG_B_SLOTS * P.b_slot_bytes;
     uint64_t* a_full = (uint64_t*)ctrl;
-    uint64_t* a_empty = a_full + WG_A_SLOTS;
-    uint64_t* b_full = a_empty + WG_A_SLOTS;
+    uint64_t* a_empty = a_full + WG_A_SLOTS_MAX;
+    uint64_t* b_full = a_empty + WG_A_SLOTS_MAX;
     uint64_t* b_empty = b_full + WG_B_SLOTS;
     uint64_t* acc_full = b_empty + WG_B_SLOTS;
     uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < WG_A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < WG_B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
 
     if (warp == 0) {
         // producer: warp-uniform loops, one elected lane issues (keeps addresses/descriptors in uniform registers)
-        uint32_t ai = 0, bi = 0;
+        uint32_t a_slot = 0, a_phase = 0, bi = 0;
         for (long kt = k_begin; kt < k_end; ++kt, ++bi) {
             int n0, z0, y0, x0;
             wg_decode(P, kt, n0, z0, y0, x0);
@@ -141,71 +145,82 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
             if (elect_one()) {
                 mbar_expect_tx(&b_full[bs], P.b_slab_bytes * P.b_slabs);
                 for (int j = 0; j < P.b_slabs; ++j)
-                    tma_load_5d(b_ring + bs * WG_SLOT_BYTES + j * P.b_slab_bytes, &P.b_maps[B.bview], &b_full[bs],
+                    tma_load_5d(b_ring + bs * P.b_slot_bytes + j * P.b_slab_bytes, &P.b_maps[B.bview], &b_full[bs],
                                 nchunk * P.NTw + j * P.nslabW, x0, y0, z0, n0);
             }
             __syncwarp();
-            for (int u = B.unit_begin; u < B.unit_begin + B.unit_count; ++u, ++ai) {
-                const int as = ai % WG_A_SLOTS;
-                mbar_wait(&a_empty[as], ((ai / WG_A_SLOTS) & 1) ^ 1, 12);
-                uint8_t* dst = a_ring + as * WG_SLOT_BYTES;
+            for (int u = B.unit_begin; u < B.unit_begin + B.unit_count; ++u) {
+                mbar_wait(&a_empty[a_slot], a_phase ^ 1u, 12);
+                uint8_t* dst = a_ring + a_slot * WG_SLOT_BYTES;
                 if (elect_one()) {
                     if (P.stacked) {
                         int real = 0;
                         for (int j = 0; j < P.a_slabs; ++j) real += P.unit_taps[u][j] >= 0;
-                        mbar_expect_tx(&a_full[as], P.a_slab_bytes * real);
+                        mbar_expect_tx(&a_full[a_slot], P.a_slab_bytes * real);
                         for (int j = 0; j < P.a_slabs; ++j) {
                             const int ti = P.unit_taps[u][j];
                             if (ti < 0) continue;
                             const WTap T = P.taps[ti];
-                            tma_load_5d(dst + j * P.a_slab_bytes, &P.a_maps[T.aview], &a_full[as], 0, x0 + T.sx,
+                            tma_load_5d(dst + j * P.a_slab_bytes, &P.a_maps[T.aview], &a_full[a_slot], 0, x0 + T.sx,
                                         y0 + T.sy, z0 + T.sz, n0);
                         }
                     } else {
                         const WTap T = P.taps[u / P.mslabs];
                         const int ms = u % P.mslabs;
-                        mbar_expect_tx(&a_full[as], P.a_slab_bytes * P.a_slabs);
+                        mbar_expect_tx(&a_full[a_slot], P.a_slab_bytes * P.a_slabs);
                         for (int j = 0; j < P.a_slabs; ++j)
-                            tma_load_5d(dst + j * P.a_slab_bytes, &P.a_maps[T.aview], &a_full[as],
+                            tma_load_5d(dst + j * P.a_slab_bytes, &P.a_maps[T.aview], &a_full[a_slot],
                                         ms * 128 + j * P.slabW, x0 + T.sx, y0 + T.sy, z0 + T.sz, n0);
                     }
                 }
                 __syncwarp();
+                if (++a_slot == (uint32_t)A_SLOTS) { a_slot = 0; a_phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        uint32_t ai = 0, bi = 0;
+        uint32_t a_slot = 0, a_phase = 0, bi = 0;
         const uint32_t a_kstep16 = P.a_kstep >> 4, b_kstep16 = P.b_kstep >> 4, NTw = (uint32_t)P.NTw, idesc = P.idesc;
+        const uint32_t a_ring_u32 = smem_u32(a_ring);
+        const uint64_t adesc0 = umma_desc(0, P.a_slab_bytes, P.a_sbo, P.a_layout);
         for (long kt = k_begin; kt < k_end; ++kt, ++bi) {
             const int bs = bi % WG_B_SLOTS;
             mbar_wait(&b_full[bs], (bi / WG_B_SLOTS) & 1, 13);
             tc_fence_after();
-            const uint64_t bdesc = umma_desc(smem_u32(b_ring + bs * WG_SLOT_BYTES), P.b_slab_bytes, P.b_sbo, P.b_layout);
-            // units are processed in pairs: their accumulators are independent, so the two 8-deep chains of
-            // dependent tcgen05.mma interleave instead of each waiting out the accumulate latency
-            for (int u = 0; u < B.unit_count; u += 2) {
-                const int nu = (B.unit_count - u) < 2 ? (B.unit_count - u) : 2;
-                const int slot0 = ai % WG_A_SLOTS, slot1 = (ai + 1) % WG_A_SLOTS;
-                mbar_wait(&a_full[slot0], (ai / WG_A_SLOTS) & 1, 14);
-                if (nu == 2) mbar_wait(&a_full[slot1], ((ai + 1) / WG_A_SLOTS) & 1, 14);
+            const uint64_t bdesc = umma_desc(smem_u32(b_ring + bs * P.b_slot_bytes), P.b_slab_bytes, P.b_sbo, P.b_layout);
+            const bool accum = kt != k_begin;
+            // units are processed WG_G at a time: their accumulators are independent, so the 8-deep chains of dependent
+            // tcgen05.mma interleave instead of each waiting out the accumulate latency
+            for (int u = 0; u < B.unit_count; u += WG_G) {
+                const int nu = (B.unit_count - u) < WG_G ? (B.unit_count - u) : WG_G;
+                uint32_t slot[WG_G];
+#pragma unroll
+                for (int j = 0; j < WG_G; ++j) {
+                    slot[j] = 0;
+                    if (j < nu) {
+                        slot[j] = a_slot;
+                        mbar_wait(&a_full[a_slot], a_phase, 14);
+                        if (++a_slot == (uint32_t)A_SLOTS) { a_slot = 0; a_phase ^= 1u; }
+                    }
+                }
                 tc_fence_after();
-                const uint64_t adesc0 = umma_desc(smem_u32(a_ring + slot0 * WG_SLOT_BYTES), P.a_slab_bytes, P.a_sbo, P.a_layout);
-                const uint64_t adesc1 = umma_desc(smem_u32(a_ring + slot1 * WG_SLOT_BYTES), P.a_slab_bytes, P.a_sbo, P.a_layout);
-                const bool accum = kt != k_begin;
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {      // 128 voxels per tile = 8 × K16
-                        mma_bf16(tmem_base + (uint32_t)u * NTw, adesc0 + (uint64_t)(a_kstep16 * k), bdesc + (uint64_t)(b_kstep16 * k),
-                                 idesc, accum || (k != 0));
-                        if (nu == 2)
-                            mma_bf16(tmem_base + (uint32_t)(u + 1) * NTw, adesc1 + (uint64_t)(a_kstep16 * k),
-                                     bdesc + (uint64_t)(b_kstep16 * k), idesc, accum || (k != 0));
+#pragma unroll
+                        for (int j = 0; j < WG_G; ++j) {
+                            if (j < nu) {
+                                const uint64_t ad = adesc0 + (uint64_t)(((a_ring_u32 + slot[j] * WG_SLOT_BYTES) & 0x3FFFFu) >> 4) +
+                                                    (uint64_t)(a_kstep16 * k);
+                                mma_bf16(tmem_base + (uint32_t)(u + j) * NTw, ad, bdesc + (uint64_t)(b_kstep16 * k), idesc,
+                                         accum || (k != 0));
+                            }
+                        }
                     }
-                    mma_commit(&a_empty[slot0]);
-                    if (nu == 2) mma_commit(&a_empty[slot1]);
+#pragma unroll
+                    for (int j = 0; j < WG_G; ++j)
+                        if (j < nu) mma_commit(&a_empty[slot[j]]);
                 }
                 __syncwarp();
-                ai += nu;
             }
             if (elect_one()) mma_commit(&b_empty[bs]);
             __syncwarp();
@@ -237,7 +252,11 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
                     tmem_ld_wait();
                     if (dst) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) atomicAdd(dst + col + j, __uint_as_float(rr[j]));
+                        for (int j = 0; j < 16; j += 4)       // 128-bit reductions: 4x fewer L2 atomic transactions
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + col + j),
+                                         "f"(__uint_as_float(rr[j])), "f"(__uint_as_float(rr[j + 1])),
+                                         "f"(__uint_as_float(rr[j + 2])), "f"(__uint_as_float(rr[j + 3]))
+                                         : "memory");
                     }
                 }
             }
@@ -352,7 +371,10 @@ int igemm_wgrad(const Plan& p, const amb_wgrad_args* a) {
     if (ksplit > ktiles_upper) ksplit = (int)ktiles_upper;
     if (ksplit < 1) ksplit = 1;
     P.ksplit = ksplit;
-    size_t smem = (size_t)(WG_A_SLOTS + WG_B_SLOTS) * WG_SLOT_BYTES + 1024 + 256;
+    P.b_slot_bytes = (P.b_slab_bytes * P.b_slabs + 1023u) & ~1023u;
+    P.a_slots = (int)((227u * 1024u - 1280u - WG_B_SLOTS * P.b_slot_bytes) / WG_SLOT_BYTES);
+    if (P.a_slots > WG_A_SLOTS_MAX) P.a_slots = WG_A_SLOTS_MAX;
+    size_t smem = (size_t)P.a_slots * WG_SLOT_BYTES + (size_t)WG_B_SLOTS * P.b_slot_bytes + 1024 + 256;
     AMB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wgrad_kernel<<<base_jobs * ksplit, 256, smem, (cudaStream_t)a->stream>>>(P);
     AMB_LAUNCH_CHECK();
