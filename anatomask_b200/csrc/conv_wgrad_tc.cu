@@ -52,14 +52,14 @@ struct WgradParams {
     float* dw;
     uint32_t idesc;
     uint32_t a_layout, b_layout, a_sbo, b_sbo, a_kstep, b_kstep;
-    int a_slots;                  // dY ring depth (5 or 6 x 32 KB, what fits beside the X ring)
-    uint32_t b_slot_bytes;
+    int a_slots;                  // dY ring depth (what fits beside the X ring)
+    uint32_t b_slot_bytes, a_slot_bytes;
+    int KV;                       // voxels per K tile (64 or 128): smaller tiles = deeper prefetch for the same smem
 };
 
-#define WG_A_SLOTS_MAX 6
+#define WG_A_SLOTS_MAX 12
 #define WG_B_SLOTS 2
 #define WG_G 4                       // accumulator units (independent MMA chains) interleaved per K tile
-#define WG_SLOT_BYTES 32768u
 
 __device__ __forceinline__ long wg_num_ktiles(const WgradParams& P) {
     if (P.list) {
@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int A_SLOTS = P.a_slots;
     uint8_t* a_ring = smem;
-    uint8_t* b_ring = smem + A_SLOTS * WG_SLOT_BYTES;
+    const uint32_t ASB = P.a_slot_bytes;
+    uint8_t* b_ring = smem + A_SLOTS * ASB;
     uint8_t* ctrl = b_ring + WG_B_SLOTS * P.b_slot_bytes;
     uint64_t* a_full = (uint64_t*)ctrl;
     uint64_t* a_empty = a_full + WG_A_SLOTS_MAX;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
             __syncwarp();
             for (int u = B.unit_begin; u < B.unit_begin + B.unit_count; ++u) {
                 mbar_wait(&a_empty[a_slot], a_phase ^ 1u, 12);
-                uint8_t* dst = a_ring + a_slot * WG_SLOT_BYTES;
+                uint8_t* dst = a_ring + a_slot * ASB;
                 if (elect_one()) {
                     if (P.stacked) {
                         int real = 0;
@@ -204,12 +205,12 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
                 }
                 tc_fence_after();
                 if (elect_one()) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {      // 128 voxels per tile = 8 × K16
+                    const int ksteps = P.KV >> 4;
+                    for (int k = 0; k < ksteps; ++k) {      // KV voxels per tile = KV/16 × K16
 #pragma unroll
                         for (int j = 0; j < WG_G; ++j) {
                             if (j < nu) {
-                                const uint64_t ad = adesc0 + (uint64_t)(((a_ring_u32 + slot[j] * WG_SLOT_BYTES) & 0x3FFFFu) >> 4) +
+                                const uint64_t ad = adesc0 + (uint64_t)(((a_ring_u32 + slot[j] * ASB) & 0x3FFFFu) >> 4) +
                                                     (uint64_t)(a_kstep16 * k);
                                 mma_bf16(tmem_base + (uint32_t)(u + j) * NTw, ad, bdesc + (uint64_t)(b_kstep16 * k), idesc,
                                          accum || (k != 0));
@@ -295,8 +296,10 @@ int igemm_wgrad(const Plan& p, const amb_wgrad_args* a) {
     P.nslabW = P.NTw < 64 ? P.NTw : 64;
     P.b_slabs = P.NTw / P.nslabW;
     P.n_nchunks = p.Cx / P.NTw;
-    P.a_slab_bytes = 128u * P.slabW * 2u;
-    P.b_slab_bytes = 128u * P.nslabW * 2u;
+    const char* kvenv = getenv("AMB_WG_KV");
+    P.KV = (kvenv && atoi(kvenv) == 128) ? 128 : 64;
+    P.a_slab_bytes = (uint32_t)P.KV * P.slabW * 2u;
+    P.b_slab_bytes = (uint32_t)P.KV * P.nslabW * 2u;
     auto layout_of = [](int w) { return w == 64 ? 2u : (w == 32 ? 4u : 6u); };
     P.a_layout = layout_of(P.slabW); P.b_layout = layout_of(P.nslabW);
     P.a_sbo = 8u * P.slabW * 2u; P.b_sbo = 8u * P.nslabW * 2u;       // 8 voxel rows
@@ -308,11 +311,12 @@ int igemm_wgrad(const Plan& p, const amb_wgrad_args* a) {
 
     int bw = pow2_ceilw(p.oW) < 8 ? pow2_ceilw(p.oW) : 8;
     int bh = pow2_ceilw(p.oH) < 8 ? pow2_ceilw(p.oH) : 8;
-    int rem = 128 / (bw * bh);
+    int rem = P.KV / (bw * bh);
+    if (rem < 1) rem = 1;
     int bd = pow2_ceilw(p.oD) < rem ? pow2_ceilw(p.oD) : rem;
     int bn = rem / bd;
     const bool use_list = a->active_list != nullptr && p.lgPv >= 0 && (1 << p.lgPv) >= 8 && bn == 1 && bw == 8 &&
-                          bh == 8 && bd == 2;
+                          bh == 8 && bd <= 2;
     P.list = use_list ? a->active_list : nullptr;
     P.count = use_list ? a->active_count : nullptr;
     P.lgbn = ilog2w(bn); P.lgbd = ilog2w(bd); P.lgbh = ilog2w(bh); P.lgbw = ilog2w(bw);
@@ -372,9 +376,10 @@ int igemm_wgrad(const Plan& p, const amb_wgrad_args* a) {
     if (ksplit < 1) ksplit = 1;
     P.ksplit = ksplit;
     P.b_slot_bytes = (P.b_slab_bytes * P.b_slabs + 1023u) & ~1023u;
-    P.a_slots = (int)((227u * 1024u - 1280u - WG_B_SLOTS * P.b_slot_bytes) / WG_SLOT_BYTES);
+    P.a_slot_bytes = (uint32_t)P.KV * 256u;           // 128 M rows x KV voxels x 2 B
+    P.a_slots = (int)((227u * 1024u - 1280u - WG_B_SLOTS * P.b_slot_bytes) / P.a_slot_bytes);
     if (P.a_slots > WG_A_SLOTS_MAX) P.a_slots = WG_A_SLOTS_MAX;
-    size_t smem = (size_t)P.a_slots * WG_SLOT_BYTES + (size_t)WG_B_SLOTS * P.b_slot_bytes + 1024 + 256;
+    size_t smem = (size_t)P.a_slots * P.a_slot_bytes + (size_t)WG_B_SLOTS * P.b_slot_bytes + 1024 + 256;
     AMB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wgrad_kernel<<<base_jobs * ksplit, 256, smem, (cudaStream_t)a->stream>>>(P);
     AMB_LAUNCH_CHECK();
