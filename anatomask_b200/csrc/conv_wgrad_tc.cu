@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     uint64_t* b_empty = b_full + WG_B_SLOTS;
     uint64_t* acc_full = b_empty + WG_B_SLOTS;
     uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+    // per-CTA table of the slab loads of each unit of this batch: {a-map index, shifts, first channel} (−1 = no load)
+    int4* s_slab = (int4*)(ctrl + 256);                 // [<=32 units][8 slabs]
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -135,48 +137,64 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     const long ktiles = wg_num_ktiles(P);
     const long k_begin = ktiles * ks / P.ksplit, k_end = ktiles * (ks + 1) / P.ksplit;
 
-    if (warp == 0) {
-        // producer: warp-uniform loops, one elected lane issues (keeps addresses/descriptors in uniform registers)
-        uint32_t a_slot = 0, a_phase = 0, bi = 0;
+    for (int i = threadIdx.x; i < B.unit_count * 8; i += blockDim.x) {
+        const int ul = i >> 3, j = i & 7, u = B.unit_begin + ul;
+        int4 e = make_int4(-1, 0, 0, 0);
+        if (j < P.a_slabs) {
+            int ti, c0;
+            if (P.stacked) { ti = P.unit_taps[u][j]; c0 = 0; }
+            else { ti = u / P.mslabs; c0 = (u % P.mslabs) * 128 + j * P.slabW; }
+            if (ti >= 0) {
+                const WTap T = P.taps[ti];
+                e = make_int4(T.aview, (T.sx & 0xFF) | ((T.sy & 0xFF) << 8) | ((T.sz & 0xFF) << 16), c0, 1);
+            }
+        }
+        s_slab[i] = e;
+    }
+    __syncthreads();
+
+    if (warp == 0 || warp == 2 || warp == 3) {
+        // three producer warps (the per-unit TMA issue path was the bottleneck): warp 0 also feeds the X ring; unit i of
+        // the CTA's stream goes to ring slot i % A_SLOTS, producer w takes units i ≡ w (mod 3)
+        const int pw = warp == 0 ? 0 : warp - 1;             // 0, 1, 2
+        uint32_t a_slot = (uint32_t)pw % (uint32_t)A_SLOTS, a_phase = 0, bi = 0;
+        int ucur = pw;                                        // unit index inside the current K tile (may run past it)
+        const uint32_t a_bytes1 = P.a_slab_bytes;
         for (long kt = k_begin; kt < k_end; ++kt, ++bi) {
             int n0, z0, y0, x0;
             wg_decode(P, kt, n0, z0, y0, x0);
-            const int bs = bi % WG_B_SLOTS;
-            mbar_wait(&b_empty[bs], ((bi / WG_B_SLOTS) & 1) ^ 1, 11);
-            if (elect_one()) {
-                mbar_expect_tx(&b_full[bs], P.b_slab_bytes * P.b_slabs);
-                for (int j = 0; j < P.b_slabs; ++j)
-                    tma_load_5d(b_ring + bs * P.b_slot_bytes + j * P.b_slab_bytes, &P.b_maps[B.bview], &b_full[bs],
-                                nchunk * P.NTw + j * P.nslabW, x0, y0, z0, n0);
-            }
-            __syncwarp();
-            for (int u = B.unit_begin; u < B.unit_begin + B.unit_count; ++u) {
-                mbar_wait(&a_empty[a_slot], a_phase ^ 1u, 12);
-                uint8_t* dst = a_ring + a_slot * ASB;
+            if (pw == 0) {
+                const int bs = bi % WG_B_SLOTS;
+                mbar_wait(&b_empty[bs], ((bi / WG_B_SLOTS) & 1) ^ 1, 11);
                 if (elect_one()) {
-                    if (P.stacked) {
-                        int real = 0;
-                        for (int j = 0; j < P.a_slabs; ++j) real += P.unit_taps[u][j] >= 0;
-                        mbar_expect_tx(&a_full[a_slot], P.a_slab_bytes * real);
-                        for (int j = 0; j < P.a_slabs; ++j) {
-                            const int ti = P.unit_taps[u][j];
-                            if (ti < 0) continue;
-                            const WTap T = P.taps[ti];
-                            tma_load_5d(dst + j * P.a_slab_bytes, &P.a_maps[T.aview], &a_full[a_slot], 0, x0 + T.sx,
-                                        y0 + T.sy, z0 + T.sz, n0);
-                        }
-                    } else {
-                        const WTap T = P.taps[u / P.mslabs];
-                        const int ms = u % P.mslabs;
-                        mbar_expect_tx(&a_full[a_slot], P.a_slab_bytes * P.a_slabs);
-                        for (int j = 0; j < P.a_slabs; ++j)
-                            tma_load_5d(dst + j * P.a_slab_bytes, &P.a_maps[T.aview], &a_full[a_slot],
-                                        ms * 128 + j * P.slabW, x0 + T.sx, y0 + T.sy, z0 + T.sz, n0);
+                    mbar_expect_tx(&b_full[bs], P.b_slab_bytes * P.b_slabs);
+                    for (int j = 0; j < P.b_slabs; ++j)
+                        tma_load_5d(b_ring + bs * P.b_slot_bytes + j * P.b_slab_bytes, &P.b_maps[B.bview], &b_full[bs],
+                                    nchunk * P.NTw + j * P.nslabW, x0, y0, z0, n0);
+                }
+                __syncwarp();
+            }
+            for (; ucur < B.unit_count; ucur += 3) {
+                mbar_wait(&a_empty[a_slot], a_phase ^ 1u, 12);
+                if (elect_one()) {
+                    const int4* tab = s_slab + ucur * 8;
+                    int real = 0;
+                    for (int j = 0; j < P.a_slabs; ++j) real += tab[j].x >= 0;
+                    mbar_expect_tx(&a_full[a_slot], a_bytes1 * (uint32_t)real);
+                    uint8_t* dst = a_ring + a_slot * ASB;
+                    for (int j = 0; j < P.a_slabs; ++j) {
+                        const int4 e = tab[j];
+                        if (e.x < 0) continue;
+                        const int sx = (int)(int8_t)(e.y & 0xFF), sy = (int)(int8_t)((e.y >> 8) & 0xFF),
+                                  sz = (int)(int8_t)((e.y >> 16) & 0xFF);
+                        tma_load_5d(dst + j * a_bytes1, &P.a_maps[e.x], &a_full[a_slot], e.z, x0 + sx, y0 + sy, z0 + sz, n0);
                     }
                 }
                 __syncwarp();
-                if (++a_slot == (uint32_t)A_SLOTS) { a_slot = 0; a_phase ^= 1u; }
+                a_slot += 3;
+                while (a_slot >= (uint32_t)A_SLOTS) { a_slot -= (uint32_t)A_SLOTS; a_phase ^= 1u; }
             }
+            ucur -= B.unit_count;
         }
     } else if (warp == 1) {
         uint32_t a_slot = 0, a_phase = 0, bi = 0;
@@ -297,7 +315,7 @@ int igemm_wgrad(const Plan& p, const amb_wgrad_args* a) {
     P.b_slabs = P.NTw / P.nslabW;
     P.n_nchunks = p.Cx / P.NTw;
     const char* kvenv = getenv("AMB_WG_KV");
-    P.KV = (kvenv && atoi(kvenv) == 128) ? 128 : 64;
+    P.KV = (kvenv && atoi(kvenv) == 64) ? 64 : 128;      // measured: 64-voxel tiles halve throughput (per-unit issue cost)
     P.a_slab_bytes = (uint32_t)P.KV * P.slabW * 2u;
     P.b_slab_bytes = (uint32_t)P.KV * P.nslabW * 2u;
     auto layout_of = [](int w) { return w == 64 ? 2u : (w == 32 ? 4u : 6u); };
@@ -377,9 +395,9 @@ int igemm_wgrad(const Plan& p, const amb_wgrad_args* a) {
     P.ksplit = ksplit;
     P.b_slot_bytes = (P.b_slab_bytes * P.b_slabs + 1023u) & ~1023u;
     P.a_slot_bytes = (uint32_t)P.KV * 256u;           // 128 M rows x KV voxels x 2 B
-    P.a_slots = (int)((227u * 1024u - 1280u - WG_B_SLOTS * P.b_slot_bytes) / P.a_slot_bytes);
+    P.a_slots = (int)((227u * 1024u - 1280u - 4096u - WG_B_SLOTS * P.b_slot_bytes) / P.a_slot_bytes);
     if (P.a_slots > WG_A_SLOTS_MAX) P.a_slots = WG_A_SLOTS_MAX;
-    size_t smem = (size_t)P.a_slots * P.a_slot_bytes + (size_t)WG_B_SLOTS * P.b_slot_bytes + 1024 + 256;
+    size_t smem = (size_t)P.a_slots * P.a_slot_bytes + (size_t)WG_B_SLOTS * P.b_slot_bytes + 1024 + 256 + 32 * 8 * 16;
     AMB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wgrad_kernel<<<base_jobs * ksplit, 256, smem, (cudaStream_t)a->stream>>>(P);
     AMB_LAUNCH_CHECK();
