@@ -389,13 +389,33 @@ stem_fwd_kernel(Geo g, const float* __restrict__ inp, const float* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = sw[27 * C + cg * 8 + j];
         float center = 0.f;
+        // visibility / bounds are resolved per input ROW (9 rows), not per tap: inside a patch row only the two x-edge
+        // voxels can see a different patch
+        const int px = x >> g.lgP, xin = x & (g.P - 1);
 #pragma unroll
-        for (int tap = 0; tap < 27; ++tap) {
-            const int dz = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dx = tap % 3 - 1;
-            const float xv = masked_input(g, inp, r.n, z + dz, y + dy, x + dx);
-            if (tap == 13) center = xv;
+        for (int r9 = 0; r9 < 9; ++r9) {
+            const int iz = z + r9 / 3 - 1, iy = y + r9 % 3 - 1;
+            float xv[3] = {0.f, 0.f, 0.f};
+            if ((unsigned)iz < (unsigned)g.D && (unsigned)iy < (unsigned)g.H) {
+                const uint8_t* arow = g.active + ((r.n * g.fd + (iz >> g.lgP)) * g.fh + (iy >> g.lgP)) * g.fw;
+                const float* row = inp + (((long)r.n * g.D + iz) * g.H + iy) * g.W + x;
+                const bool a_mid = arow[px] != 0;
+                const bool a_lo = xin == 0 ? (px > 0 && arow[px - 1] != 0) : a_mid;
+                const bool a_hi = xin == g.P - 1 ? (px + 1 < g.fw && arow[px + 1] != 0) : a_mid;
+                if (a_lo) xv[0] = row[-1];
+                if (a_mid) xv[1] = row[0];
+                if (a_hi) xv[2] = row[1];
+            }
+            if (r9 == 4) center = xv[1];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, sw[tap * C + cg * 8 + j], acc[j]);
+            for (int dx = 0; dx < 3; ++dx) {
+                const float4 w0 = *reinterpret_cast<const float4*>(&sw[(r9 * 3 + dx) * C + cg * 8]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&sw[(r9 * 3 + dx) * C + cg * 8 + 4]);
+                acc[0] = fmaf(xv[dx], w0.x, acc[0]); acc[1] = fmaf(xv[dx], w0.y, acc[1]);
+                acc[2] = fmaf(xv[dx], w0.z, acc[2]); acc[3] = fmaf(xv[dx], w0.w, acc[3]);
+                acc[4] = fmaf(xv[dx], w1.x, acc[4]); acc[5] = fmaf(xv[dx], w1.y, acc[5]);
+                acc[6] = fmaf(xv[dx], w1.z, acc[6]); acc[7] = fmaf(xv[dx], w1.w, acc[7]);
+            }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) o3[j] = fmaf(center, sw[28 * C + cg * 8 + j], sw[29 * C + cg * 8 + j]);

@@ -73,7 +73,7 @@ __device__ __forceinline__ float act_grad(float u, int act) {
 // Σx, Σx² (mode 0)   |   Σg, Σg·x̂ (+ Σ_inactive dout → dtoken) (mode 1)
 // ------------------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(512) reduce_kernel(Geo g, const bf16* __restrict__ x, const bf16* __restrict__ dout,
+__global__ void __launch_bounds__(512, 2) reduce_kernel(Geo g, const bf16* __restrict__ x, const bf16* __restrict__ dout,
                                                      const bf16* __restrict__ res, const float* __restrict__ scale,
                                                      const float* __restrict__ shift, const float* __restrict__ saved,
                                                      int act, int fill, double* __restrict__ sums,
@@ -189,7 +189,7 @@ __global__ void eval_kernel(const float* gamma, const float* beta, const float* 
     }
 }
 
-__global__ void __launch_bounds__(512) apply_kernel(Geo g, const bf16* __restrict__ x, const float* __restrict__ scale,
+__global__ void __launch_bounds__(512, 2) apply_kernel(Geo g, const bf16* __restrict__ x, const float* __restrict__ scale,
                                                     const float* __restrict__ shift, const bf16* __restrict__ res,
                                                     const float* __restrict__ token, int act, bf16* __restrict__ out) {
     const int CG = g.C / 8;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(512) apply_kernel(Geo g, const bf16* __restric
     }
 }
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 bwd_apply_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ x, const bf16* __restrict__ res,
                  const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ saved,
                  const double* __restrict__ sums, int act, int fill, bf16* __restrict__ dx, bf16* __restrict__ dres,
@@ -349,7 +349,7 @@ __global__ void active_list_kernel(const uint8_t* __restrict__ active, int n, in
 
 static int grid_for(long work_items, int block) {
     long b = (work_items + block - 1) / block;
-    long cap = (long)num_sms() * 8;
+    long cap = (long)num_sms() * 16;
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return (int)b;
