@@ -230,8 +230,9 @@ class PretrainEngine:
     def graph_step(self, inp: torch.Tensor, epoch: int = 0):
         """Same semantics as step() in device-RNG mode, replayed from a CUDA graph.  Graphs are keyed by the number of
         hard patches (a launch parameter of the top-k kernel that changes every few epochs)."""
-        from .AnatoMask import SparK as _AM
         m = self.model
+        if self.world > 1 and getattr(m, 'sbn', False):
+            return self.step(inp, epoch)                 # SyncBN all-reduces sit inside autograd: keep NCCL out of captures
         nm = m.fmap_h * m.fmap_w * m.fmap_d - m.len_keep
         len_loss = int(nm * (float((epoch + 1) / (self.epochs - 1)) * 0.5))
         self.model.train()

@@ -1,0 +1,69 @@
+"""2-rank NCCL checks (run under torchrun on a 2-GPU box):  python -m torch.distributed.run --nproc-per-node 2 tests/dist_checks.py
+
+1. SyncBN path: with sbn=True and IDENTICAL inputs/masks on both ranks the pooled statistics equal the local ones, so
+   loss and gradients must match the single-process sbn=False run (validates the (Σx, Σx², n) and (Σg, Σg·x̂)
+   all-reduces, forward and backward).
+2. Data-parallel step: after one engine step with different per-rank batches, parameters are identical on both ranks
+   (one SUM all-reduce of the gradient arena, 1/world folded into AdamW)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import reference_port as rp  # noqa: E402
+from anatomask_b200.trainer import PretrainEngine, build_model  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+    torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
+    dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))
+    cfg = rp.CONFIGS['S64']
+    st = {k: v.cuda() for k, v in rp.make_state(cfg, 5).items()}
+    inp = rp.make_input(cfg, 2, 5).cuda()
+    active = rp.random_mask(cfg, 2, torch.Generator().manual_seed(6)).cuda()
+
+    def run(sbn):
+        m = build_model(base=cfg.base, depth=cfg.depth, input_size=cfg.input_size, anatomask=True, sbn=sbn)
+        m.load_state_dict(st)
+        m.train()
+        rec = m.reconstruct(inp, active)
+        loss, _ = m.forward_loss(inp, rec, active)
+        loss.backward()
+        return float(loss), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+
+    l0, g0 = run(False)
+    l1, g1 = run(True)
+    worst = max(float((g1[k] - g0[k]).norm() / (g0[k].norm() + 1e-12)) for k in g0 if float(g0[k].norm()) > 1e-6)
+    ok1 = abs(l1 - l0) <= 1e-5 * abs(l0) and worst < 2e-2
+    if rank == 0:
+        print(f'RESULT syncbn loss {l0:.6f} vs {l1:.6f}; worst grad rel {worst:.2e}; ok={ok1}')
+
+    torch.manual_seed(100 + rank)
+    m = build_model(base=cfg.base, depth=cfg.depth, input_size=cfg.input_size, anatomask=True)
+    m.load_state_dict(st)
+    eng = PretrainEngine(m, epochs=1000, anatomask=True, mask_rng='device', process_group=dist.group.WORLD)
+    x = torch.randn(2, 1, *cfg.input_size, device='cuda')
+    for _ in range(2):
+        eng.step(x, epoch=500)
+    for _ in range(2):
+        eng.graph_step(x, epoch=500)
+    flat = eng.arena.flat.clone()
+    other = flat.clone()
+    dist.broadcast(other, 0)
+    same = bool(torch.equal(flat, other))
+    tf = eng.tarena.flat.clone()
+    to = tf.clone()
+    dist.broadcast(to, 0)
+    same_t = bool(torch.equal(tf, to))
+    if rank == 0 or not (same and same_t):
+        print(f'RESULT ddp rank{rank}: params identical across ranks={same} teacher identical={same_t}')
+    dist.barrier()
+    dist.destroy_process_group()
+    assert ok1 and same and same_t
+
+
+if __name__ == '__main__':
+    main()
