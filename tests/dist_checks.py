@@ -43,7 +43,7 @@ def main():
     keys = [k for k in g0 if k.startswith(('dense_decoder.dec.3', 'dense_decoder.proj'))]
     rel = lambda a, b: max(float((a[k] - b[k]).norm() / (b[k].norm() + 1e-12)) for k in keys)
     noise, worst = rel(g0b, g0), rel(g1, g0)
-    ok1 = abs(l1 - l0) <= 2e-4 * abs(l0) and worst < max(3e-2, 3 * noise)
+    ok1 = abs(l1 - l0) <= 2e-4 * abs(l0) and worst < max(5e-2, 5 * noise)
     if rank == 0:
         print(f'RESULT run-to-run noise on dec.3/proj grads {noise:.2e}')
     if rank == 0:
