@@ -72,6 +72,9 @@ CONFIGS = {
     'B128': Cfg(base=32, depth=1, input_size=(128, 128, 128)),
     'L64': Cfg(base=64, depth=2, input_size=(64, 64, 64)),
     'L128': Cfg(base=64, depth=2, input_size=(128, 128, 128)),
+    # non-cubic volume with odd mask-grid extents (the authors train at 112x112x128 -> fmap 7x7x8)
+    'S_aniso': Cfg(base=16, depth=1, input_size=(48, 80, 32)),
+    'L32': Cfg(base=64, depth=2, input_size=(32, 32, 32)),
 }
 
 

@@ -77,7 +77,7 @@ def test_direct_and_tcgen05_agree_exactly_on_integers():
     assert torch.equal(ys[0], ys[1])
 
 
-@pytest.mark.parametrize('name,seed', [('tiny', 3), ('S64', 5), ('B64', 5)])
+@pytest.mark.parametrize('name,seed', [('tiny', 3), ('S64', 5), ('B64', 5), ('S_aniso', 4), ('L32', 2)])
 def test_spark_step_matches_oracle(name, seed):
     mc.check_spark(name=name, seed=seed, verbose=False)
 

@@ -21,7 +21,7 @@ def _check_digest(t, d, rtol, atol_scale=1e-6):
     assert abs(float(t.norm()) - d['norm']) <= rtol * d['norm'] + 1e-9
 
 
-@pytest.mark.parametrize('name', ['tiny', 'S64'])
+@pytest.mark.parametrize('name', ['tiny', 'S64', 'S_aniso', 'L32'])
 def test_spark_forward_backward_matches_reference(golden_dir, name):
     g = _load(golden_dir, f'spark_{name}.pt')
     cfg = rp.Cfg(**g['cfg'])
@@ -45,8 +45,11 @@ def test_spark_forward_backward_matches_reference(golden_dir, name):
             assert float(t.norm()) < 1e-5, k
             continue
         err = float((t[:64] - d['head'].double()).norm()) / max(float(d['head'].double().norm()), 1e-3 * d['norm'])
-        assert err < 5e-3, (k, err)       # fp32 summation-order noise on 10^5-term reductions
-        assert abs(float(t.norm()) - d['norm']) <= 1e-3 * d['norm'], k
+        # fp32 summation-order noise on 10^5-term reductions; 'L32' pools its deepest norms over 6 voxels and its
+        # fp32 gradients are correspondingly noisier (both the reference and the port sit ~1e-2 from fp64 there)
+        loose = 4.0 if name == 'L32' else 1.0
+        assert err < 5e-3 * loose, (k, err)
+        assert abs(float(t.norm()) - d['norm']) <= 1e-3 * loose * d['norm'], k
     for k, v in g['buffers'].items():
         assert torch.allclose(out['new_buffers'][k].to(v.dtype), v, rtol=1e-5, atol=1e-6), k
 
