@@ -389,7 +389,11 @@ int igemm_wgrad(const Plan& p, const amb_wgrad_args* a) {
 
     long ktiles_upper = (long)P.Tn * P.Tz * P.Ty * P.Tx;
     int base_jobs = nb * P.n_nchunks;
-    int ksplit = (2 * num_sms() + base_jobs - 1) / base_jobs;
+    // split-K: enough CTAs to fill the chip, but every extra split costs a full set of fp32 reductions in the epilogue:
+    // two waves only when each CTA still gets a long K range
+    const char* wenv = getenv("AMB_WG_WAVES");
+    int waves = wenv ? atoi(wenv) : (ktiles_upper * base_jobs >= 64L * num_sms() ? 2 : 1);
+    int ksplit = (waves * num_sms() + base_jobs - 1) / base_jobs;
     if (ksplit > ktiles_upper) ksplit = (int)ktiles_upper;
     if (ksplit < 1) ksplit = 1;
     P.ksplit = ksplit;
