@@ -127,13 +127,12 @@ __device__ __forceinline__ long geo_num_runs(const Geo& g) {
 }
 
 __device__ __forceinline__ bool voxel_active(const Geo& g, long voxel) {
-    // voxel linear → patch flag
-    int x = (int)(voxel % g.W);
-    long t = voxel / g.W;
-    int y = (int)(t % g.H);
-    t /= g.H;
-    int z = (int)(t % g.D);
-    int n = (int)(t / g.D);
+    // voxel linear → patch flag (32-bit arithmetic: voxel counts on this path are far below 2^31)
+    uint32_t t = (uint32_t)voxel;
+    const uint32_t x = t % (uint32_t)g.W; t /= (uint32_t)g.W;
+    const uint32_t y = t % (uint32_t)g.H; t /= (uint32_t)g.H;
+    const uint32_t z = t % (uint32_t)g.D;
+    const uint32_t n = t / (uint32_t)g.D;
     return g.active[((n * g.fd + (z >> g.lgP)) * g.fh + (y >> g.lgP)) * g.fw + (x >> g.lgP)] != 0;
 }
 
