@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(512) reduce_kernel(Geo g, const bf16* __restri
         }
     }
     Walk w = make_walk(gd, CG);
+#pragma unroll 4
     for (; w.slot < w.nslots; w.slot += w.step) {
         Item it;
         it.voxel = slot_voxel(gd, w.slot);
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(512) apply_kernel(Geo g, const bf16* __restric
         tk[j] = token ? token[cg * 8 + j] : 0.f;
     }
     Walk w = make_walk(gd, CG);
+#pragma unroll 4
     for (; w.slot < w.nslots; w.slot += w.step) {
         Item it;
         it.voxel = slot_voxel(gd, w.slot);
@@ -273,6 +275,7 @@ bwd_apply_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ 
         }
     }
     Walk w = make_walk(g, CG);
+#pragma unroll 4
     for (; w.slot < w.nslots; w.slot += w.step) {
         Item it;
         it.voxel = slot_voxel(g, w.slot);
