@@ -84,9 +84,29 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
     return v;
 }
 
+// explicit 128-bit accesses: the struct-typed form above was split by nvcc into four 32-bit LDGs, which left every
+// elementwise kernel at a fraction of HBM speed
+__device__ __forceinline__ void unpack_u4(const uint4& v, float* f) {
+    float2 t;
+    t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x)); f[0] = t.x; f[1] = t.y;
+    t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y)); f[2] = t.x; f[3] = t.y;
+    t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.z)); f[4] = t.x; f[5] = t.y;
+    t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.w)); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ void load8(const bf16* p, float* f) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    unpack_u4(v, f);
+}
+
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ void store8(bf16* p, const float* f) {
+    uint4 v;
+    v.x = pack2(f[0], f[1]); v.y = pack2(f[2], f[3]); v.z = pack2(f[4], f[5]); v.w = pack2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = v;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(256) direct_conv_kernel(const __grid_constant_
                     const bf16* wr = P.w + ((long)T.w * p.Cy + r) * p.Cx;
                     for (int c = 0; c < p.Cx; c += 8) {
                         float a[8], b[8];
-                        unpack8(*reinterpret_cast<const bf16x8*>(xr + c), a);
-                        unpack8(*reinterpret_cast<const bf16x8*>(wr + c), b);
+                        load8(xr + c, a);
+                        load8(wr + c, b);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) acc = fmaf(a[j], b[j], acc);
                     }
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) direct_wgrad_kernel(const __grid_constant
         if ((unsigned)iz >= (unsigned)iv.D || (unsigned)iy >= (unsigned)iv.H || (unsigned)ix >= (unsigned)iv.W) continue;
         const float d = bf2f(P.dy[ov.base + n * ov.sN + z * ov.sD + y * ov.sH + x * ov.sW + r]);
         float a[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(P.x + iv.base + n * iv.sN + iz * iv.sD + iy * iv.sH + ix * iv.sW + cg * 8), a);
+        load8(P.x + iv.base + n * iv.sN + iz * iv.sD + iy * iv.sH + ix * iv.sW + cg * 8, a);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(d, a[j], acc[j]);
     }

@@ -419,8 +419,8 @@ stem_fwd_kernel(Geo g, const float* __restrict__ inp, const float* __restrict__ 
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) o3[j] = fmaf(center, sw[28 * C + cg * 8 + j], sw[29 * C + cg * 8 + j]);
-        *reinterpret_cast<bf16x8*>(out1 + voxel * C + cg * 8) = pack8(acc);
-        *reinterpret_cast<bf16x8*>(out3 + voxel * C + cg * 8) = pack8(o3);
+        store8(out1 + voxel * C + cg * 8, acc);
+        store8(out3 + voxel * C + cg * 8, o3);
     }
 }
 
@@ -473,7 +473,7 @@ stem_wgrad_kernel(Geo g, const float* __restrict__ inp, const bf16* __restrict__
                     xv = ok ? row[x] : 0.f;
                 }
                 float d[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(dptr + (long)v * C), d);
+                load8(dptr + (long)v * C, d);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[j] = fmaf(d[j], xv, acc[j]);
             }
@@ -505,7 +505,7 @@ __global__ void proj_fwd_kernel(const bf16* __restrict__ x, const float* __restr
         float acc = bias;
         for (int c = 0; c < C; c += 8) {
             float f[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(x + v * C + c), f);
+            load8(x + v * C + c, f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc = fmaf(f[j], sw[c + j], acc);
         }
@@ -529,10 +529,10 @@ proj_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const f
         const long v = item / CG;
         const float d = drec[v];
         float f[8], o[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(x + v * C + cg * 8), f);
+        load8(x + v * C + cg * 8, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { o[j] = d * wv[j]; acc[j] = fmaf(d, f[j], acc[j]); }
-        *reinterpret_cast<bf16x8*>(dx + v * C + cg * 8) = pack8(o);
+        store8(dx + v * C + cg * 8, o);
         if (cg == 0) accb += d;
     }
 #pragma unroll

@@ -114,13 +114,10 @@ __global__ void __launch_bounds__(512) reduce_kernel(Geo g, const bf16* __restri
     Geo gd = g;
     if (MODE == 1 && fill) gd.list = nullptr;            // densify backward visits every voxel
     const int cg = threadIdx.x % CG;
-    float sc[8], sh[8], mu[8], rs[8];
+    float sc[8], sh[8];
     if (MODE == 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j];
-            mu[j] = saved[cg * 8 + j]; rs[j] = saved[g.C + cg * 8 + j];
-        }
+        for (int j = 0; j < 8; ++j) { sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j]; }
     }
     Walk w = make_walk(gd, CG);
 #pragma unroll 4
@@ -131,28 +128,33 @@ __global__ void __launch_bounds__(512) reduce_kernel(Geo g, const bf16* __restri
         const long off = it.voxel * g.C + it.cg * 8;
         if (MODE == 0) {
             float f[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(x + off), f);
+            load8(x + off, f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { a0[j] += f[j]; a1[j] += f[j] * f[j]; }
         } else {
             float d[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(dout + off), d);
+            load8(dout + off, d);
             if (fill && !voxel_active(g, it.voxel)) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) a2[j] += d[j];
                 continue;
             }
             float f[8], r[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(x + off), f);
-            if (res) unpack8(*reinterpret_cast<const bf16x8*>(res + off), r);
+            load8(x + off, f);
+            if (res) load8(res + off, r);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float u = sc[j] * f[j] + sh[j] + (res ? r[j] : 0.f);
                 float gj = d[j] * act_grad(u, act);
                 a0[j] += gj;
-                a1[j] += gj * (f[j] - mu[j]) * rs[j];
+                a1[j] += gj * f[j];            // Σg·x; turned into Σg·x̂ = rstd·(Σg·x − μ·Σg) after the loop
             }
         }
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            a1[j] = saved[g.C + cg * 8 + j] * (a1[j] - saved[cg * 8 + j] * a0[j]);
     }
     // lanes of a warp that share a channel group (lane % CG equal) are combined with shuffles first
     const bool shfl = CG < 32 && (CG & (CG - 1)) == 0 && (blockDim.x & 31) == 0;
@@ -242,12 +244,12 @@ __global__ void __launch_bounds__(512) apply_kernel(Geo g, const bf16* __restric
             for (int j = 0; j < 8; ++j) o[j] = tk[j];
         } else {
             float f[8], r[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(x + off), f);
-            if (res) unpack8(*reinterpret_cast<const bf16x8*>(res + off), r);
+            load8(x + off, f);
+            if (res) load8(res + off, r);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = act_fwd(sc[j] * f[j] + sh[j] + (res ? r[j] : 0.f), act);
         }
-        *reinterpret_cast<bf16x8*>(out + off) = pack8(o);
+        store8(out + off, o);
     }
 }
 
@@ -260,13 +262,16 @@ bwd_apply_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ 
     const int cg = threadIdx.x % CG;
     const double n = n_total ? *n_total
                              : (g.list ? (double)((long)(*g.count) << (3 * g.lgP)) : (double)g.N * g.D * g.H * g.W);
-    float sc[8], sh[8], mu[8], rs[8], m1[8], m2[8];
+    // dx = scale·(g − Σg/n − x̂·Σ(g·x̂)/n) = scale·g + ca·x + cb with per-channel constants (fewer live registers)
+    float sc[8], sh[8], ca[8], cb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         int c = cg * 8 + j;
-        sc[j] = scale[c]; sh[j] = shift[c]; mu[j] = saved[c]; rs[j] = saved[g.C + c];
-        m1[j] = (float)(sums[c] / n);
-        m2[j] = (float)(sums[g.C + c] / n);
+        sc[j] = scale[c]; sh[j] = shift[c];
+        const float mu = saved[c], rs = saved[g.C + c];
+        const float m1 = (float)(sums[c] / n), m2 = (float)(sums[g.C + c] / n);
+        ca[j] = -sc[j] * m2 * rs;
+        cb[j] = -sc[j] * m1 - ca[j] * mu;
     }
     if (blockIdx.x == 0 && dgamma) {
         for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
@@ -282,31 +287,29 @@ bwd_apply_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ 
         it.cg = cg;
         const long off = it.voxel * g.C + it.cg * 8;
         float d[8], f[8], r[8], o[8], gg[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(dout + off), d);
-        unpack8(*reinterpret_cast<const bf16x8*>(x + off), f);
-        if (res) unpack8(*reinterpret_cast<const bf16x8*>(res + off), r);
+        load8(dout + off, d);
+        load8(x + off, f);
+        if (res) load8(res + off, r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float u = sc[j] * f[j] + sh[j] + (res ? r[j] : 0.f);
             gg[j] = d[j] * act_grad(u, act);
-            float xh = (f[j] - mu[j]) * rs[j];
-            o[j] = sc[j] * (gg[j] - m1[j] - xh * m2[j]);
+            o[j] = fmaf(sc[j], gg[j], fmaf(ca[j], f[j], cb[j]));
         }
-        *reinterpret_cast<bf16x8*>(dx + off) = pack8(o);
-        if (dres) *reinterpret_cast<bf16x8*>(dres + off) = pack8(gg);
+        store8(dx + off, o);
+        if (dres) store8(dres + off, gg);
     }
 }
 
-__global__ void add_kernel(const bf16x8* __restrict__ a, const bf16x8* __restrict__ b, bf16x8* __restrict__ out,
-                           long n8) {
+__global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, long n8) {
     const long stride = (long)gridDim.x * blockDim.x;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
         float fa[8], fb[8];
-        unpack8(a[i], fa);
-        unpack8(b[i], fb);
+        load8(a + i * 8, fa);
+        load8(b + i * 8, fb);
 #pragma unroll
         for (int j = 0; j < 8; ++j) fa[j] += fb[j];
-        out[i] = pack8(fa);
+        store8(out + i * 8, fa);
     }
 }
 
@@ -502,8 +505,7 @@ extern "C" int amb_count_voxels(const amb_geo* a, double* out, void* stream) {
 
 extern "C" int amb_add(const void* a, const void* b, void* out, long n, void* stream) {
     AMB_CHECK(n % 8 == 0, AMB_ERR_ARG, "amb_add: n must be a multiple of 8");
-    add_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16x8*)a, (const bf16x8*)b,
-                                                                       (bf16x8*)out, n / 8);
+    add_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n / 8);
     AMB_LAUNCH_CHECK();
     return 0;
 }
