@@ -98,12 +98,13 @@ __device__ __forceinline__ float act_grad(float u, int act) {
 // ------------------------------------------------------------------------------------------------------------
 // Σx, Σx² (mode 0)   |   Σg, Σg·x̂ (+ Σ_inactive dout → dtoken) (mode 1)
 // ------------------------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, int ACT>
 __global__ void __launch_bounds__(512) reduce_kernel(Geo g, const bf16* __restrict__ x, const bf16* __restrict__ dout,
                                                      const bf16* __restrict__ res, const float* __restrict__ scale,
                                                      const float* __restrict__ shift, const float* __restrict__ saved,
-                                                     int act, int fill, double* __restrict__ sums,
+                                                     int act_unused, int fill, double* __restrict__ sums,
                                                      double* __restrict__ dtoken) {
+    constexpr int act = ACT;
     extern __shared__ float sacc[];           // [3][C]: Σ, Σ·, Σ_inactive — per-CTA fp32 partials, fp64 across CTAs
     const int CG = g.C / 8;
     for (int i = threadIdx.x; i < g.C * 3; i += blockDim.x) sacc[i] = 0.f;
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(512) reduce_kernel(Geo g, const bf16* __restri
         for (int j = 0; j < 8; ++j) { sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j]; }
     }
     Walk w = make_walk(gd, CG);
-#pragma unroll 4
+#pragma unroll 2
     for (; w.slot < w.nslots; w.slot += w.step) {
         Item it;
         it.voxel = slot_voxel(gd, w.slot);
@@ -218,9 +219,11 @@ __global__ void eval_kernel(const float* gamma, const float* beta, const float* 
     }
 }
 
+template <int ACT>
 __global__ void __launch_bounds__(512) apply_kernel(Geo g, const bf16* __restrict__ x, const float* __restrict__ scale,
                                                     const float* __restrict__ shift, const bf16* __restrict__ res,
-                                                    const float* __restrict__ token, int act, bf16* __restrict__ out) {
+                                                    const float* __restrict__ token, int act_unused, bf16* __restrict__ out) {
+    constexpr int act = ACT;
     const int CG = g.C / 8;
     Geo gd = g;
     if (token) gd.list = nullptr;
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(512) apply_kernel(Geo g, const bf16* __restric
         tk[j] = token ? token[cg * 8 + j] : 0.f;
     }
     Walk w = make_walk(gd, CG);
-#pragma unroll 4
+#pragma unroll 2
     for (; w.slot < w.nslots; w.slot += w.step) {
         Item it;
         it.voxel = slot_voxel(gd, w.slot);
@@ -253,11 +256,13 @@ __global__ void __launch_bounds__(512) apply_kernel(Geo g, const bf16* __restric
     }
 }
 
+template <int ACT>
 __global__ void __launch_bounds__(512)
 bwd_apply_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ x, const bf16* __restrict__ res,
                  const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ saved,
-                 const double* __restrict__ sums, int act, int fill, bf16* __restrict__ dx, bf16* __restrict__ dres,
+                 const double* __restrict__ sums, int act_unused, int fill, bf16* __restrict__ dx, bf16* __restrict__ dres,
                  float* __restrict__ dgamma, float* __restrict__ dbeta, const double* n_total) {
+    constexpr int act = ACT;
     const int CG = g.C / 8;
     const int cg = threadIdx.x % CG;
     const double n = n_total ? *n_total
@@ -280,7 +285,7 @@ bwd_apply_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ 
         }
     }
     Walk w = make_walk(g, CG);
-#pragma unroll 4
+#pragma unroll 2
     for (; w.slot < w.nslots; w.slot += w.step) {
         Item it;
         it.voxel = slot_voxel(g, w.slot);
@@ -423,7 +428,7 @@ extern "C" int amb_norm_stats(const amb_geo* a, const void* x, double* sums, voi
     if (int e = make_geo(a, g)) return e;
     int CG = g.C / 8, block = pick_block(CG);
     if (block < 0) return block;
-    reduce_kernel<0><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>(
+    reduce_kernel<0, 0><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>(
         g, (const bf16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, sums, nullptr);
     AMB_LAUNCH_CHECK();
     return 0;
@@ -455,8 +460,13 @@ extern "C" int amb_norm_apply(const amb_geo* a, const void* x, const float* scal
     AMB_CHECK(!token || g.active, AMB_ERR_ARG, "densify fill needs the active mask");
     int CG = g.C / 8, block = pick_block(CG);
     if (block < 0) return block;
-    apply_kernel<<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(
-        g, (const bf16*)x, scale, shift, (const bf16*)residual, token, act, (bf16*)out);
+#define AMB_APPLY(A)                                                                                    \
+    apply_kernel<A><<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(          \
+        g, (const bf16*)x, scale, shift, (const bf16*)residual, token, act, (bf16*)out)
+    if (act == AMB_ACT_LRELU) AMB_APPLY(1);
+    else if (act == AMB_ACT_RELU6) AMB_APPLY(2);
+    else AMB_APPLY(0);
+#undef AMB_APPLY
     AMB_LAUNCH_CHECK();
     return 0;
 }
@@ -469,8 +479,13 @@ extern "C" int amb_norm_bwd_reduce(const amb_geo* a, const void* dout, const voi
     AMB_CHECK(!fill || g.active, AMB_ERR_ARG, "densify backward needs the active mask");
     int CG = g.C / 8, block = pick_block(CG);
     if (block < 0) return block;
-    reduce_kernel<1><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>(
-        g, (const bf16*)x, (const bf16*)dout, (const bf16*)residual, scale, shift, saved, act, fill, sums, dtoken);
+#define AMB_RED(A)                                                                                                       \
+    reduce_kernel<1, A><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>( \
+        g, (const bf16*)x, (const bf16*)dout, (const bf16*)residual, scale, shift, saved, act, fill, sums, dtoken)
+    if (act == AMB_ACT_LRELU) AMB_RED(1);
+    else if (act == AMB_ACT_RELU6) AMB_RED(2);
+    else AMB_RED(0);
+#undef AMB_RED
     AMB_LAUNCH_CHECK();
     return 0;
 }
@@ -484,9 +499,14 @@ extern "C" int amb_norm_bwd_apply(const amb_geo* a, const void* dout, const void
     (void)fill;   // dx is only defined on visited (active) voxels; the caller zero-fills dx when the list is sparse
     int CG = g.C / 8, block = pick_block(CG);
     if (block < 0) return block;
-    bwd_apply_kernel<<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(
-        g, (const bf16*)dout, (const bf16*)x, (const bf16*)residual, scale, shift, saved, sums, act, fill, (bf16*)dx,
-        (bf16*)dres, dgamma, dbeta, n_total);
+#define AMB_BWD(A)                                                                                              \
+    bwd_apply_kernel<A><<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(              \
+        g, (const bf16*)dout, (const bf16*)x, (const bf16*)residual, scale, shift, saved, sums, act, fill, (bf16*)dx, \
+        (bf16*)dres, dgamma, dbeta, n_total)
+    if (act == AMB_ACT_LRELU) AMB_BWD(1);
+    else if (act == AMB_ACT_RELU6) AMB_BWD(2);
+    else AMB_BWD(0);
+#undef AMB_BWD
     AMB_LAUNCH_CHECK();
     return 0;
 }

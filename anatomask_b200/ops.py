@@ -161,7 +161,7 @@ class ConvFn(torch.autograd.Function):
     2×8×8 tile fits a patch — masked tiles are never computed."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, k, stride, m, transposed, impl, stats=None):
+    def forward(ctx, x, weight, bias, k, stride, m, transposed, impl, stats=None, zero_inactive=True):
         require_cuda(x)
         x = x.contiguous()
         N, D, H, W, Cin = x.shape
@@ -177,7 +177,9 @@ class ConvFn(torch.autograd.Function):
             Cout = weight.shape[0]
             wp = _pack(weight, k3, Cout, Cin, 1, Cin * k3, k3)
             shape = (N, D // stride, H // stride, W // stride, Cout)
-            y = torch.zeros(shape, dtype=bf16, device=x.device) if m is not None else \
+            # masked voxels are never written where the work-list skips whole tiles: zero-fill unless the only consumer
+            # (a pooled masked norm) visits visible voxels exclusively
+            y = torch.zeros(shape, dtype=bf16, device=x.device) if (m is not None and zero_inactive) else \
                 torch.empty(shape, dtype=bf16, device=x.device)
             flops = 2.0 * N * (D // stride) * (H // stride) * (W // stride) * k3 * Cin * Cout * \
                 (m.frac_hint if m is not None else 1.0)
@@ -233,7 +235,7 @@ class ConvFn(torch.autograd.Function):
                 L.call('amb_unpack_wgrad', _p(dwp), _p(dw), k3, Cout, Cin, 1, Cin * k3, k3, _stream())
         if has_bias and ctx.needs_input_grad[2]:
             db = column_sums(dy, m if not transposed else None)
-        return dx, dw, db, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None
 
 
 def fused_stats_ok(cin: int, cout: int) -> bool:
@@ -246,8 +248,9 @@ def new_stats(channels: int, device) -> torch.Tensor:
     return torch.zeros(2 * channels + 1, dtype=torch.float64, device=device)
 
 
-def conv3d(x, weight, bias=None, k=3, stride=1, m: Optional[MaskCtx] = None, impl=L.IMPL_AUTO, stats=None):
-    return ConvFn.apply(x, weight, bias, k, stride, m, False, impl, stats)
+def conv3d(x, weight, bias=None, k=3, stride=1, m: Optional[MaskCtx] = None, impl=L.IMPL_AUTO, stats=None,
+           zero_inactive=True):
+    return ConvFn.apply(x, weight, bias, k, stride, m, False, impl, stats, zero_inactive)
 
 
 def conv_transpose3d(x, weight, bias=None, impl=L.IMPL_AUTO):
@@ -259,13 +262,14 @@ class StemFn(torch.autograd.Function):
     (P/STUNet_head.py:96-101 with P/spark3D.py:104-107 folded in)."""
 
     @staticmethod
-    def forward(ctx, inp, w1, b1, w3, b3, m: MaskCtx):
+    def forward(ctx, inp, w1, b1, w3, b3, m: MaskCtx, zero_inactive=True):
         require_cuda(inp)
         inp = inp.float().contiguous()
         N, _, D, H, W = inp.shape
         Cc = w1.shape[0]
-        out1 = torch.zeros((N, D, H, W, Cc), dtype=bf16, device=inp.device)
-        out3 = torch.zeros((N, D, H, W, Cc), dtype=bf16, device=inp.device)
+        alloc = torch.zeros if zero_inactive else torch.empty
+        out1 = alloc((N, D, H, W, Cc), dtype=bf16, device=inp.device)
+        out3 = alloc((N, D, H, W, Cc), dtype=bf16, device=inp.device)
         L.call('amb_stem_fwd', _p(inp), _p(m.active), _p(m.list), _p(m.count), N, D, H, W, m.fd, m.fh, m.fw, Cc,
                _p(w1), _p(b1), _p(w3), _p(b3), _p(out1), _p(out3), _stream())
         ctx.save_for_backward(inp)
@@ -282,7 +286,7 @@ class StemFn(torch.autograd.Function):
         dw1, db1, dw3, db3 = g[:Cc * 27], g[Cc * 27:Cc * 28], g[Cc * 28:Cc * 29], g[Cc * 29:]
         L.call('amb_stem_wgrad', _p(inp), _p(m.active), _p(m.list), _p(m.count), N, D, H, W, m.fd, m.fh, m.fw, Cc,
                _p(d1), _p(d3), _p(dw1), _p(db1), _p(dw3), _p(db3), _stream())
-        return None, dw1.view(Cc, 1, 3, 3, 3), db1, dw3.view(Cc, 1, 1, 1, 1), db3, None
+        return None, dw1.view(Cc, 1, 3, 3, 3), db1, dw3.view(Cc, 1, 1, 1, 1), db3, None, None
 
 
 class ProjFn(torch.autograd.Function):
