@@ -19,9 +19,9 @@ y = torch.empty(N, S, S, S, co, dtype=torch.bfloat16, device=dev)
 dx = torch.empty_like(x)
 dw = torch.zeros(27, co, ci, device=dev)
 for _ in range(3):
-    ops._conv_call(L.OP_CONV, L.IMPL_TCGEN05_V1, (N, S, S, S), ci, co, 3, 1, x, y, wf)
+    ops._conv_call(L.OP_CONV, L.IMPL_TCGEN05, (N, S, S, S), ci, co, 3, 1, x, y, wf)
 for _ in range(3):
-    ops._conv_call(L.OP_CONV_DGRAD, L.IMPL_TCGEN05_V1, (N, S, S, S), ci, co, 3, 1, dy, dx, wd)
+    ops._conv_call(L.OP_CONV_DGRAD, L.IMPL_TCGEN05, (N, S, S, S), ci, co, 3, 1, dy, dx, wd)
 a = L.WgradArgs(L.OP_CONV, L.IMPL_TCGEN05, N, S, S, S, ci, co, 3, 1, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), 1, 1, 1, 0, 0,
                 torch.cuda.current_stream().cuda_stream)
 for _ in range(3):
