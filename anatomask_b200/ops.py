@@ -23,6 +23,22 @@ def _p(t: Optional[torch.Tensor]):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+# ConvFn.backward runs the weight-gradient branch (wgrad → unpack → bias column sums) on a side stream: dgrad and wgrad
+# only share the read-only dy, so inside the captured step graph they become parallel branches — the deep, small layers
+# launch too few CTAs to fill 148 SMs on their own.  AMB_NO_SIDE_STREAM=1 disables it.
+_SIDE = {}
+
+
+def _side_stream(dev):
+    import os
+    if os.environ.get('AMB_NO_SIDE_STREAM') == '1':
+        return None
+    s = _SIDE.get(dev)
+    if s is None:
+        s = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    return s
+
+
 # bench.py sets PROFILE to a list: every conv-family launch is then bracketed by CUDA events on the launching stream
 # and recorded as (kind, algorithmic FLOPs, start, end) — the live roofline measurement (no effect when None).
 PROFILE = None
@@ -199,42 +215,65 @@ class ConvFn(torch.autograd.Function):
         N, D, H, W, Cin = x.shape
         k3 = k * k * k
         dx = dw = db = None
-        if transposed:
-            Cout = weight.shape[1]
-            if ctx.needs_input_grad[0]:
+        need_w = ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])
+        main = torch.cuda.current_stream()
+        side = _side_stream(x.device) if (need_w and ctx.needs_input_grad[0]) else None
+        if side is not None:
+            side.wait_stream(main)
+
+        def weight_branch():
+            dw_ = db_ = None
+            if transposed:
+                Cout = weight.shape[1]
+                if ctx.needs_input_grad[1]:
+                    dwp = torch.zeros((64, Cout, Cin), dtype=torch.float32, device=x.device)
+                    a = L.WgradArgs(L.OP_CONVT, impl, N, D, H, W, Cin, Cout, 4, 2, x.data_ptr(), dy.data_ptr(),
+                                    dwp.data_ptr(), 1, 1, 1, 0, 0, torch.cuda.current_stream().cuda_stream)
+                    with _Timed('convT_wgrad', ctx.flops):
+                        L.call('amb_conv_wgrad', C.byref(a))
+                    dw_ = torch.empty_like(weight)
+                    L.call('amb_unpack_wgrad', _p(dwp), _p(dw_), 64, Cout, Cin, 1, 64, Cout * 64, _stream())
+            else:
+                Cout = weight.shape[0]
+                if ctx.needs_input_grad[1]:
+                    dwp = torch.zeros((k3, Cout, Cin), dtype=torch.float32, device=x.device)
+                    a = L.WgradArgs(L.OP_CONV, impl, N, D, H, W, Cin, Cout, k, stride, x.data_ptr(), dy.data_ptr(),
+                                    dwp.data_ptr(), 1 if m is None else m.fd, 1 if m is None else m.fh,
+                                    1 if m is None else m.fw, 0 if m is None else m.list.data_ptr(),
+                                    0 if m is None else m.count.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                    with _Timed('conv_wgrad', ctx.flops):
+                        L.call('amb_conv_wgrad', C.byref(a))
+                    dw_ = torch.empty_like(weight)
+                    L.call('amb_unpack_wgrad', _p(dwp), _p(dw_), k3, Cout, Cin, 1, Cin * k3, k3, _stream())
+            if has_bias and ctx.needs_input_grad[2]:
+                db_ = column_sums(dy, m if not transposed else None)
+            return dw_, db_
+
+        if side is not None:
+            with torch.cuda.stream(side):
+                dw, db = weight_branch()
+            for t in (dw, db, dy, x):
+                if t is not None:
+                    t.record_stream(side)
+        if ctx.needs_input_grad[0]:
+            if transposed:
+                Cout = weight.shape[1]
                 wp = _pack(weight, 64, Cin, Cout, 1, Cout * 64, 64)
                 dx = torch.empty_like(x)
                 with _Timed('convT_dgrad', ctx.flops):
                     _conv_call(L.OP_CONVT_DGRAD, impl, (N, D, H, W), Cin, Cout, 4, 2, dy, dx, wp)
-            if ctx.needs_input_grad[1]:
-                dwp = torch.zeros((64, Cout, Cin), dtype=torch.float32, device=x.device)
-                a = L.WgradArgs(L.OP_CONVT, impl, N, D, H, W, Cin, Cout, 4, 2, x.data_ptr(), dy.data_ptr(),
-                                dwp.data_ptr(), 1, 1, 1, 0, 0, torch.cuda.current_stream().cuda_stream)
-                with _Timed('convT_wgrad', ctx.flops):
-                    L.call('amb_conv_wgrad', C.byref(a))
-                dw = torch.empty_like(weight)
-                L.call('amb_unpack_wgrad', _p(dwp), _p(dw), 64, Cout, Cin, 1, 64, Cout * 64, _stream())
-        else:
-            Cout = weight.shape[0]
-            if ctx.needs_input_grad[0]:
+            else:
+                Cout = weight.shape[0]
                 wp = _pack(weight, k3, Cin, Cout, 1, k3, Cin * k3)
                 need_zero = m is not None or (k == 1 and stride == 2)
                 dx = torch.zeros_like(x) if need_zero else torch.empty_like(x)
                 with _Timed('conv_dgrad', ctx.flops):
                     _conv_call(L.OP_CONV_DGRAD, impl, (N, D, H, W), Cin, Cout, k, stride, dy, dx, wp, None, m,
                                sparse=m is not None)
-            if ctx.needs_input_grad[1]:
-                dwp = torch.zeros((k3, Cout, Cin), dtype=torch.float32, device=x.device)
-                a = L.WgradArgs(L.OP_CONV, impl, N, D, H, W, Cin, Cout, k, stride, x.data_ptr(), dy.data_ptr(),
-                                dwp.data_ptr(), 1 if m is None else m.fd, 1 if m is None else m.fh,
-                                1 if m is None else m.fw, 0 if m is None else m.list.data_ptr(),
-                                0 if m is None else m.count.data_ptr(), torch.cuda.current_stream().cuda_stream)
-                with _Timed('conv_wgrad', ctx.flops):
-                    L.call('amb_conv_wgrad', C.byref(a))
-                dw = torch.empty_like(weight)
-                L.call('amb_unpack_wgrad', _p(dwp), _p(dw), k3, Cout, Cin, 1, Cin * k3, k3, _stream())
-        if has_bias and ctx.needs_input_grad[2]:
-            db = column_sums(dy, m if not transposed else None)
+        if side is not None:
+            main.wait_stream(side)
+        elif need_w:
+            dw, db = weight_branch()
         return dx, dw, db, None, None, None, None, None, None, None
 
 
