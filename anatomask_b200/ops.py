@@ -27,6 +27,18 @@ def _p(t: Optional[torch.Tensor]):
 # only share the read-only dy, so inside the captured step graph they become parallel branches — the deep, small layers
 # launch too few CTAs to fill 148 SMs on their own.  AMB_NO_SIDE_STREAM=1 disables it.
 _SIDE = {}
+# Engine mode: weight / bias gradients are written straight into the (pre-allocated) .grad views of the parameter arena
+# on the side stream and ConvFn.backward returns None for them, so the whole weight-gradient chain of the backward pass
+# runs as one long parallel branch next to the dgrad / norm-backward chain; the engine joins it before the optimiser.
+DEFER_WGRAD = False
+
+
+def join_side_stream(dev=None):
+    dev = torch.device('cuda', torch.cuda.current_device()) if dev is None else dev
+    s = _SIDE.get(dev)
+    if s is not None:
+        torch.cuda.current_stream().wait_stream(s)
+
 
 
 def _side_stream(dev):
@@ -203,6 +215,8 @@ class ConvFn(torch.autograd.Function):
                 _conv_call(L.OP_CONV, impl, (N, D, H, W), Cin, Cout, k, stride, x, y, wp, bias, m, sparse=m is not None,
                            stats=stats)
         ctx.save_for_backward(x, weight)
+        ctx.bias_ref = bias
+        ctx.weight_ref = weight
         ctx.flops = flops
         ctx.cfg = (k, stride, m, transposed, impl, bias is not None)
         return y
@@ -211,6 +225,7 @@ class ConvFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
         k, stride, m, transposed, impl, has_bias = ctx.cfg
+        bias_ref = ctx.bias_ref
         dy = dy.contiguous()
         N, D, H, W, Cin = x.shape
         k3 = k * k * k
@@ -221,7 +236,7 @@ class ConvFn(torch.autograd.Function):
         if side is not None:
             side.wait_stream(main)
 
-        def weight_branch():
+        def weight_branch(dst_w=None):
             dw_ = db_ = None
             if transposed:
                 Cout = weight.shape[1]
@@ -231,7 +246,7 @@ class ConvFn(torch.autograd.Function):
                                     dwp.data_ptr(), 1, 1, 1, 0, 0, torch.cuda.current_stream().cuda_stream)
                     with _Timed('convT_wgrad', ctx.flops):
                         L.call('amb_conv_wgrad', C.byref(a))
-                    dw_ = torch.empty_like(weight)
+                    dw_ = torch.empty_like(weight) if dst_w is None else dst_w
                     L.call('amb_unpack_wgrad', _p(dwp), _p(dw_), 64, Cout, Cin, 1, 64, Cout * 64, _stream())
             else:
                 Cout = weight.shape[0]
@@ -243,18 +258,28 @@ class ConvFn(torch.autograd.Function):
                                     0 if m is None else m.count.data_ptr(), torch.cuda.current_stream().cuda_stream)
                     with _Timed('conv_wgrad', ctx.flops):
                         L.call('amb_conv_wgrad', C.byref(a))
-                    dw_ = torch.empty_like(weight)
+                    dw_ = torch.empty_like(weight) if dst_w is None else dst_w
                     L.call('amb_unpack_wgrad', _p(dwp), _p(dw_), k3, Cout, Cin, 1, Cin * k3, k3, _stream())
             if has_bias and ctx.needs_input_grad[2]:
                 db_ = column_sums(dy, m if not transposed else None)
             return dw_, db_
 
+        deferred = False
         if side is not None:
+            wref = ctx.weight_ref
+            can_defer = DEFER_WGRAD and wref.grad is not None and wref.grad.is_contiguous() and \
+                (bias_ref is None or not has_bias or bias_ref.grad is not None)
             with torch.cuda.stream(side):
-                dw, db = weight_branch()
+                dw, db = weight_branch(wref.grad if can_defer else None)
+                if can_defer:
+                    if db is not None:
+                        bias_ref.grad.copy_(db)
+                    deferred = True
             for t in (dw, db, dy, x):
                 if t is not None:
                     t.record_stream(side)
+            if deferred:
+                dw = db = None
         if ctx.needs_input_grad[0]:
             if transposed:
                 Cout = weight.shape[1]
@@ -270,9 +295,9 @@ class ConvFn(torch.autograd.Function):
                 with _Timed('conv_dgrad', ctx.flops):
                     _conv_call(L.OP_CONV_DGRAD, impl, (N, D, H, W), Cin, Cout, k, stride, dy, dx, wp, None, m,
                                sparse=m is not None)
-        if side is not None:
+        if side is not None and not deferred:
             main.wait_stream(side)
-        elif need_w:
+        elif side is None and need_w:
             dw, db = weight_branch()
         return dx, dw, db, None, None, None, None, None, None, None
 

@@ -196,7 +196,12 @@ class PretrainEngine:
         rec = m.reconstruct(inp, mask)
         loss, _ = m.forward_loss(inp, rec, mask)
         self.arena.zero_grad()
-        loss.backward()
+        ops.DEFER_WGRAD = True                     # wgrad chain → side stream, written straight into the arena views
+        try:
+            loss.backward()
+        finally:
+            ops.DEFER_WGRAD = False
+        ops.join_side_stream(inp.device)
         return loss.detach(), mask, recon
 
     def _device_tail(self):
