@@ -157,6 +157,38 @@ def check_device_step(name='S64', batch=2, seed=1, steps=4):
     return {'losses': losses}
 
 
+def check_graph_matches_eager(name='S64', batch=2, seed=1, steps=3):
+    """The CUDA-graph replay (side-stream weight-gradient chain written straight into the arena, device-side scalars)
+    against the same device-RNG step launched eagerly: identical masks, losses and parameters up to atomics noise."""
+    from anatomask_b200.trainer import PretrainEngine
+    cfg = rp.CONFIGS[name]
+    inp = rp.make_input(cfg, batch, seed).cuda()
+    runs = []
+    for mode in ('eager', 'graph'):
+        eng = PretrainEngine(build(cfg, seed, anatomask=True), lr=1e-4, epochs=1000, anatomask=True, mask_rng='device')
+        eng.teacher.rng_counter = eng.step_counter
+        losses, masks = [], []
+        for i in range(steps):
+            if mode == 'eager':
+                eng._set_hyper(500)
+                loss, mask, _ = eng._device_step(inp, 500)
+                eng.t += 1
+            else:
+                loss, mask, _ = eng.graph_step(inp, 500)
+            losses.append(float(loss))
+            masks.append(mask.clone())
+        torch.cuda.synchronize()
+        runs.append((losses, masks, eng.arena.flat[:eng.arena.n_live].clone(), eng.tarena.flat.clone(), eng.t))
+    (l0, m0, p0, t0, n0), (l1, m1, p1, t1, n1) = runs
+    res = {'loss_eager': l0, 'loss_graph': l1, 'masks_equal': all(torch.equal(a, b) for a, b in zip(m0, m1)),
+           'param_maxdiff': float((p0 - p1).abs().max()), 'teacher_maxdiff': float((t0 - t1).abs().max()), 'steps': (n0, n1)}
+    print('RESULT graph_matches_eager', name, json.dumps(res))
+    assert n0 == n1 == steps and res['masks_equal']
+    assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(l0, l1)), res
+    assert res['param_maxdiff'] <= 2.5 * steps * 1e-4 and res['teacher_maxdiff'] <= 1e-4, res      # Adam steps are <= lr each
+    return res
+
+
 CHECKS = {n[6:]: f for n, f in list(globals().items()) if n.startswith('check_')}
 
 if __name__ == '__main__':

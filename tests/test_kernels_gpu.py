@@ -112,6 +112,10 @@ def test_device_rng_step_runs_without_host_sync():
     mc.check_device_step()
 
 
+def test_graph_replay_matches_eager_launches():
+    mc.check_graph_matches_eager()
+
+
 def test_full_size_properties_B128():
     """BASELINE size (STUNet-B, 128^3, batch 2): size-independent properties of one AnatoMask step."""
     from oracle import reference_port as rp
