@@ -69,29 +69,25 @@ class STUNet(nn.Module):
     def __init__(self, input_channels, num_classes, depth=[1, 1, 1, 1, 1, 1], dims=[32, 64, 128, 256, 512, 512],
                  pool_op_kernel_sizes=None, conv_kernel_sizes=None, enable_deep_supervision=True):
         super().__init__()
-        self.conv_op = nn.Conv3d
-        self.input_channels = input_channels
-        self.num_classes = num_classes
-        self.final_nonlin = lambda x: x
+        n_stages = len(pool_op_kernel_sizes)
+        assert n_stages == len(dims) - 1
+        self.conv_op, self.input_channels, self.num_classes = nn.Conv3d, input_channels, num_classes
+        self.final_nonlin, self.upscale_logits = (lambda x: x), False
         self.decoder = Decoder()
         self.decoder.deep_supervision = enable_deep_supervision
-        self.upscale_logits = False
-        self.dims = dims
-        self.pool_op_kernel_sizes = pool_op_kernel_sizes
-        self.conv_kernel_sizes = conv_kernel_sizes
-        self.conv_pad_sizes = [[i // 2 for i in krnl] for krnl in self.conv_kernel_sizes]
-        num_pool = len(pool_op_kernel_sizes)
-        assert num_pool == len(dims) - 1
-        self.conv_blocks_context = nn.ModuleList()
-        k, p = self.conv_kernel_sizes, self.conv_pad_sizes
-        self.conv_blocks_context.append(nn.Sequential(
-            BasicResBlock(input_channels, dims[0], k[0], p[0], use_1x1conv=True),
-            *[BasicResBlock(dims[0], dims[0], k[0], p[0]) for _ in range(depth[0] - 1)]))
-        for d in range(1, num_pool):
-            self.conv_blocks_context.append(nn.Sequential(
-                BasicResBlock(dims[d - 1], dims[d], k[d], p[d], stride=self.pool_op_kernel_sizes[d - 1],
-                              use_1x1conv=True),
-                *[BasicResBlock(dims[d], dims[d], k[d], p[d]) for _ in range(depth[d] - 1)]))
+        self.dims, self.pool_op_kernel_sizes, self.conv_kernel_sizes = dims, pool_op_kernel_sizes, conv_kernel_sizes
+        self.conv_pad_sizes = [[k // 2 for k in ks] for ks in conv_kernel_sizes]
+
+        def stage(s: int) -> nn.Sequential:
+            cin = input_channels if s == 0 else dims[s - 1]
+            extra = {} if s == 0 else {'stride': pool_op_kernel_sizes[s - 1]}
+            k, p = conv_kernel_sizes[s], self.conv_pad_sizes[s]
+            blocks = [BasicResBlock(cin, dims[s], k, p, use_1x1conv=True, **extra)]
+            blocks += [BasicResBlock(dims[s], dims[s], k, p) for _ in range(depth[s] - 1)]
+            return nn.Sequential(*blocks)
+
+        # five encoder stages (the sixth width/depth entry belongs to the full U-Net bottleneck and is unused here)
+        self.conv_blocks_context = nn.ModuleList(stage(s) for s in range(n_stages))
 
     def get_downsample_ratio(self) -> int:
         return 16
@@ -100,8 +96,8 @@ class STUNet(nn.Module):
         return self.dims[:5]
 
     def forward(self, x, hierarchical=False):
-        skips = []
-        for d in range(len(self.conv_blocks_context)):
-            x = self.conv_blocks_context[d](x)
-            skips.append(x)
-        return skips if hierarchical else x
+        feats = []
+        for blocks in self.conv_blocks_context:
+            x = blocks(x)
+            feats.append(x)
+        return feats if hierarchical else x

@@ -18,48 +18,48 @@ from . import encoder3D, ops
 from .decoder3D import LightDecoder
 
 
+def _densify_norm(kind: str, width: int, sbn: bool) -> nn.Module:
+    """densify_norm option → sparse norm layer (P/spark3D.py:61-72)."""
+    if kind == 'bn':
+        return (encoder3D.SparseSyncBatchNorm3d if sbn else encoder3D.SparseBatchNorm3d)(width)
+    if kind == 'ln':
+        return encoder3D.SparseConvNeXtLayerNorm(width, data_format='channels_first', sparse=True)
+    if kind == 'gn':
+        return encoder3D.SparseGroupNorm(width, width, sparse=True)
+    if kind == 'in':
+        return encoder3D.SparseInstanceNorm(width, sparse=True)
+    return nn.Identity()
+
+
 class SparK(nn.Module):
     def __init__(self, sparse_encoder: encoder3D.SparseEncoder, dense_decoder: LightDecoder, mask_ratio=0.6,
                  densify_norm='in', sbn=False):
         super().__init__()
-        input_size, downsample_ratio = sparse_encoder.input_size, sparse_encoder.downsample_ratio
-        self.downsample_ratio = downsample_ratio
-        self.fmap_h, self.fmap_w, self.fmap_d = (input_size[0] // downsample_ratio, input_size[1] // downsample_ratio,
-                                                 input_size[2] // downsample_ratio)
+        r = sparse_encoder.downsample_ratio
+        self.downsample_ratio = r
+        self.fmap_h, self.fmap_w, self.fmap_d = (s // r for s in sparse_encoder.input_size)
         self.mask_ratio = mask_ratio
         self.len_keep = round(self.fmap_h * self.fmap_w * self.fmap_d * (1 - mask_ratio))
-        self.sparse_encoder = sparse_encoder
-        self.dense_decoder = dense_decoder
+        self.sparse_encoder, self.dense_decoder = sparse_encoder, dense_decoder
         self.sbn = sbn
-        self.hierarchy = len(sparse_encoder.enc_feat_map_chs)
         self.densify_norm_str = densify_norm.lower()
-        self.densify_norms = nn.ModuleList()
-        self.densify_projs = nn.ModuleList()
-        self.mask_tokens = nn.ParameterList()
-        e_widths, d_width = list(self.sparse_encoder.enc_feat_map_chs), self.dense_decoder.width
-        for i in range(self.hierarchy):          # from the smallest feature map to the largest
-            e_width = e_widths.pop()
-            p = nn.Parameter(torch.zeros(1, e_width, 1, 1, 1))
-            nn.init.trunc_normal_(p, mean=0, std=.02, a=-.02, b=.02)
-            self.mask_tokens.append(p)
-            if self.densify_norm_str == 'bn':
-                norm = (encoder3D.SparseSyncBatchNorm3d if self.sbn else encoder3D.SparseBatchNorm3d)(e_width)
-            elif self.densify_norm_str == 'ln':
-                norm = encoder3D.SparseConvNeXtLayerNorm(e_width, data_format='channels_first', sparse=True)
-            elif self.densify_norm_str == 'gn':
-                norm = encoder3D.SparseGroupNorm(e_width, e_width, sparse=True)
-            elif self.densify_norm_str == 'in':
-                norm = encoder3D.SparseInstanceNorm(e_width, sparse=True)
+        enc_widths = list(sparse_encoder.enc_feat_map_chs)[::-1]           # deepest feature map first
+        self.hierarchy = len(enc_widths)
+        dec_widths = [dense_decoder.width >> i for i in range(self.hierarchy)]
+        tokens, norms, projs = [], [], []
+        for level, (e_w, d_w) in enumerate(zip(enc_widths, dec_widths)):
+            tok = nn.Parameter(torch.zeros(1, e_w, 1, 1, 1))
+            nn.init.trunc_normal_(tok, mean=0, std=.02, a=-.02, b=.02)
+            tokens.append(tok)
+            norms.append(_densify_norm(self.densify_norm_str, e_w, sbn))
+            if level == 0 and e_w == d_w:
+                projs.append(nn.Identity())                                 # STUNet: decoder width == deepest encoder width
             else:
-                norm = nn.Identity()
-            self.densify_norms.append(norm)
-            if i == 0 and e_width == d_width:
-                proj = nn.Identity()
-            else:
-                ks = 1 if i <= 0 else 3
-                proj = nn.Conv3d(e_width, d_width, kernel_size=ks, stride=1, padding=ks // 2, bias=True)
-            self.densify_projs.append(proj)
-            d_width //= 2
+                ks = 3 if level > 0 else 1
+                projs.append(nn.Conv3d(e_w, d_w, kernel_size=ks, stride=1, padding=ks // 2, bias=True))
+        self.densify_norms = nn.ModuleList(norms)
+        self.densify_projs = nn.ModuleList(projs)
+        self.mask_tokens = nn.ParameterList(tokens)
 
     # ---- masking -------------------------------------------------------------------------------------------
     def mask(self, B: int, device, generator=None):
@@ -129,24 +129,23 @@ class SparK(nn.Module):
         return inp_bchwd, inp_bchwd * active, torch.where(active, inp_bchwd, rec_bchwd)
 
     def patchify(self, bchwd):
-        p = self.downsample_ratio
-        h, w, d = self.fmap_h, self.fmap_w, self.fmap_d
+        """(B,C,H,W,D) → (B, L, p³·C): patch index l = (h·fw + w)·fd + d, element index ((p·r + q)·r + g)·C + c."""
+        r = self.downsample_ratio
+        fh, fw, fd = self.fmap_h, self.fmap_w, self.fmap_d
         B, C = bchwd.shape[:2]
-        bchwd = bchwd.reshape(shape=(B, C, h, p, w, p, d, p))
-        bchwd = torch.einsum('bchpwqdg->bhwdpqgc', bchwd)
-        return bchwd.reshape(shape=(B, h * w * d, C * p ** 3))
+        x = bchwd.reshape(B, C, fh, r, fw, r, fd, r).permute(0, 2, 4, 6, 3, 5, 7, 1)
+        return x.reshape(B, fh * fw * fd, r ** 3 * C)
 
     def unpatchify(self, bln):
-        p = self.downsample_ratio
-        h, w, d = self.fmap_h, self.fmap_w, self.fmap_d
-        B, C = bln.shape[0], bln.shape[-1] // p ** 3
-        bln = bln.reshape(shape=(B, h, w, d, p, p, p, C))
-        bln = torch.einsum('bhwdpqgc->bchpwqdg', bln)
-        return bln.reshape(shape=(B, C, h * p, w * p, d * p))
+        r = self.downsample_ratio
+        fh, fw, fd = self.fmap_h, self.fmap_w, self.fmap_d
+        B, C = bln.shape[0], bln.shape[-1] // r ** 3
+        x = bln.reshape(B, fh, fw, fd, r, r, r, C).permute(0, 7, 1, 4, 2, 5, 3, 6)
+        return x.reshape(B, C, fh * r, fw * r, fd * r)
 
     def __repr__(self):
-        return (f'\n[SparK.config]: {pformat(self.get_config(), indent=2, width=250)}\n'
-                f'[SparK.structure]: {super(SparK, self).__repr__().replace(SparK.__name__, "")}')
+        body = super().__repr__().replace(type(self).__name__, '', 1)
+        return f'\n[SparK.config]: {pformat(self.get_config(), indent=2, width=250)}\n[SparK.structure]: {body}'
 
     def get_config(self):
         return {'mask_ratio': self.mask_ratio, 'densify_norm_str': self.densify_norm_str, 'sbn': self.sbn,
@@ -154,20 +153,19 @@ class SparK(nn.Module):
                 'dense_decoder.width': self.dense_decoder.width}
 
     def state_dict(self, destination=None, prefix='', keep_vars=False, with_config=False):
-        state = super(SparK, self).state_dict(destination=destination, prefix=prefix, keep_vars=keep_vars)
+        sd = super().state_dict(destination=destination, prefix=prefix, keep_vars=keep_vars)
         if with_config:
-            state['config'] = self.get_config()
-        return state
+            sd['config'] = self.get_config()
+        return sd
 
     def load_state_dict(self, state_dict, strict=True):
-        config: dict = state_dict.pop('config', None)
-        incompatible_keys = super(SparK, self).load_state_dict(state_dict, strict=strict)
-        if config is not None:
-            for k, v in self.get_config().items():
-                ckpt_v = config.get(k, None)
-                if ckpt_v != v:
-                    err = f'[SparseMIM.load_state_dict] config mismatch:  this.{k}={v} (ckpt.{k}={ckpt_v})'
-                    if strict:
-                        raise AttributeError(err)
-                    print(err, file=sys.stderr)
-        return incompatible_keys
+        saved_cfg = state_dict.pop('config', None)
+        result = super().load_state_dict(state_dict, strict=strict)
+        mismatches = [] if saved_cfg is None else \
+            [(k, v, saved_cfg.get(k)) for k, v in self.get_config().items() if saved_cfg.get(k) != v]
+        for k, mine, theirs in mismatches:                     # same message / exception type as P/spark3D.py:199-201
+            msg = f'[SparseMIM.load_state_dict] config mismatch:  this.{k}={mine} (ckpt.{k}={theirs})'
+            if strict:
+                raise AttributeError(msg)
+            print(msg, file=sys.stderr)
+        return result
