@@ -1,0 +1,51 @@
+"""Checkpoint compatibility with the reference scripts.
+
+Writer: the `<model>_head_{latest,best}.pt` dictionary of P/pretrain.py:450-463 / P/pretrain_AntoMask.py:472-479 — keys
+prefixed `module.` because the scripts save the LocalDDP/DDP wrapper's state_dict.  The EMA teacher and the arena
+optimiser state are saved too (the reference drops the teacher; resuming needs it).
+Reader-side contract: `load_stunet_ssl_weights` (nnunetv2/run/load_pretrained_weights.py:66-105) keeps entries whose key
+contains 'encoder' and strips everything up to 'sp_cnn.'; `encoder_state_for_finetune` applies the same mapping so a
+fine-tuning STUNet can `load_state_dict(..., strict=False)` the result."""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import torch
+
+
+def head_checkpoint(model: torch.nn.Module, engine=None, train_loss=None, val_loss=None, epoch: int = 0) -> Dict:
+    sd = OrderedDict(('module.' + k, v.detach().clone()) for k, v in model.state_dict().items())
+    ckpt = {'network_weights': sd, 'optimizer_state': None, 'grad_scaler_state': None, 'train_loss': train_loss,
+            'val_loss': val_loss, 'current_epoch': epoch}
+    if engine is not None:
+        ckpt['optimizer_state'] = {'exp_avg': engine.m.clone(), 'exp_avg_sq': engine.v.clone(), 'step': engine.t,
+                                   'layout': dict(engine.arena.offsets), 'n_live': engine.arena.n_live}
+        if engine.teacher is not None:
+            ckpt['ema_weights'] = OrderedDict((k, v.detach().clone()) for k, v in engine.teacher.state_dict().items())
+    return ckpt
+
+
+def save_head_checkpoint(path: str, model, engine=None, **kw) -> None:
+    torch.save(head_checkpoint(model, engine, **kw), path)
+
+
+def encoder_state_for_finetune(network_weights: Dict[str, torch.Tensor]) -> 'OrderedDict[str, torch.Tensor]':
+    out = OrderedDict()
+    for k, v in network_weights.items():
+        if 'encoder' in k:
+            out[k.split('sp_cnn.')[-1]] = v
+    return out
+
+
+def resume(engine, ckpt: Dict) -> None:
+    """Restores student, teacher and optimiser state written by head_checkpoint (the reference has no resume path)."""
+    sd = OrderedDict((k[len('module.'):] if k.startswith('module.') else k, v) for k, v in ckpt['network_weights'].items())
+    engine.model.load_state_dict(sd)
+    if engine.teacher is not None and 'ema_weights' in ckpt:
+        engine.teacher.load_state_dict(ckpt['ema_weights'])
+    opt: Optional[Dict] = ckpt.get('optimizer_state')
+    if opt:
+        engine.m.copy_(opt['exp_avg'])
+        engine.v.copy_(opt['exp_avg_sq'])
+        engine.t = int(opt['step'])

@@ -79,3 +79,26 @@ def test_unsupported_layers_raise_like_the_reference():
     from anatomask_b200 import encoder3D
     with pytest.raises(NotImplementedError):
         encoder3D.SparseEncoder.dense_model_to_sparse(torch.nn.Conv1d(1, 1, 1))
+
+
+def test_checkpoint_keys_feed_the_reference_finetune_loader(tmp_path):
+    """`_head_latest.pt` layout (P/pretrain.py:450-463) and the key mapping of load_stunet_ssl_weights
+    (nnunetv2/run/load_pretrained_weights.py:76-79): encoder keys come out as conv_blocks_context.{s}.{b}.*"""
+    from anatomask_b200.trainer import build_model
+    from anatomask_b200 import checkpoint
+    cfg = rp.CONFIGS['tiny']
+    model = build_model(base=cfg.base, input_size=cfg.input_size, device='cpu')
+    path = str(tmp_path / 'STUNet_B_head_latest.pt')
+    checkpoint.save_head_checkpoint(path, model, epoch=3)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) >= {'network_weights', 'optimizer_state', 'grad_scaler_state', 'train_loss', 'val_loss', 'current_epoch'}
+    assert all(k.startswith('module.') for k in ck['network_weights'])
+    enc = checkpoint.encoder_state_for_finetune(ck['network_weights'])
+    assert 'conv_blocks_context.0.0.conv1.weight' in enc and 'conv_blocks_context.4.0.norm2.bias' in enc
+    assert all(k.startswith('conv_blocks_context.') for k in enc) and len(enc) == 50
+    # a fine-tuning STUNet (same block naming) accepts them
+    from anatomask_b200.STUNet_head import STUNet
+    ft = STUNet(1, 1, depth=[1] * 6, dims=[cfg.base * x for x in (1, 2, 4, 8, 16, 16)],
+                pool_op_kernel_sizes=[[2, 2, 2]] * 4 + [[1, 1, 1]], conv_kernel_sizes=[[3, 3, 3]] * 6)
+    missing, unexpected = ft.load_state_dict(enc, strict=False)
+    assert not unexpected and not missing
