@@ -50,8 +50,9 @@ __device__ __forceinline__ Walk make_walk(const Geo& g, int CG) {
     w.nslots = g.list ? ((long)(*g.count) << (3 * g.lgP)) : (long)g.N * g.D * g.H * g.W;
     return w;
 }
+template <bool LIST>
 __device__ __forceinline__ long slot_voxel(const Geo& g, long slot) {
-    if (g.list == nullptr) return slot;
+    if (!LIST) return slot;
     const uint32_t P1 = (uint32_t)g.P - 1u;
     const uint32_t s = (uint32_t)slot;                    // < 2^31 for every tensor on this path
     const uint32_t v = s & P1, ry = (s >> g.lgP) & P1, rz = (s >> (2 * g.lgP)) & P1;
@@ -98,13 +99,16 @@ __device__ __forceinline__ float act_grad(float u, int act) {
 // ------------------------------------------------------------------------------------------------------------
 // Σx, Σx² (mode 0)   |   Σg, Σg·x̂ (+ Σ_inactive dout → dtoken) (mode 1)
 // ------------------------------------------------------------------------------------------------------------
-template <int MODE, int ACT>
+// LIST: walk the active-patch work-list (else the dense tensor); FILL: densify backward (visits every voxel, routes
+// masked voxels to the mask-token gradient).  Compile-time so the dense BatchNorm instantiation carries no decode code.
+template <int MODE, int ACT, bool LIST, bool FILL>
 __global__ void __launch_bounds__(512) reduce_kernel(Geo g, const bf16* __restrict__ x, const bf16* __restrict__ dout,
                                                      const bf16* __restrict__ res, const float* __restrict__ scale,
                                                      const float* __restrict__ shift, const float* __restrict__ saved,
-                                                     int act_unused, int fill, double* __restrict__ sums,
+                                                     int act_unused, int fill_unused, double* __restrict__ sums,
                                                      double* __restrict__ dtoken) {
     constexpr int act = ACT;
+    constexpr bool fill = FILL;
     extern __shared__ float sacc[];           // [3][C]: Σ, Σ·, Σ_inactive — per-CTA fp32 partials, fp64 across CTAs
     const int CG = g.C / 8;
     for (int i = threadIdx.x; i < g.C * 3; i += blockDim.x) sacc[i] = 0.f;
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(512) reduce_kernel(Geo g, const bf16* __restri
 #pragma unroll 2
     for (; w.slot < w.nslots; w.slot += w.step) {
         Item it;
-        it.voxel = slot_voxel(gd, w.slot);
+        it.voxel = slot_voxel<LIST && !FILL>(gd, w.slot);
         it.cg = cg;
         const long off = it.voxel * g.C + it.cg * 8;
         if (MODE == 0) {
@@ -219,14 +223,14 @@ __global__ void eval_kernel(const float* gamma, const float* beta, const float* 
     }
 }
 
-template <int ACT>
+template <int ACT, bool LIST, bool FILL>
 __global__ void __launch_bounds__(512) apply_kernel(Geo g, const bf16* __restrict__ x, const float* __restrict__ scale,
                                                     const float* __restrict__ shift, const bf16* __restrict__ res,
                                                     const float* __restrict__ token, int act_unused, bf16* __restrict__ out) {
     constexpr int act = ACT;
     const int CG = g.C / 8;
     Geo gd = g;
-    if (token) gd.list = nullptr;
+    if (FILL) gd.list = nullptr;
     const int cg = threadIdx.x % CG;
     float sc[8], sh[8], tk[8];
 #pragma unroll
@@ -238,11 +242,11 @@ __global__ void __launch_bounds__(512) apply_kernel(Geo g, const bf16* __restric
 #pragma unroll 2
     for (; w.slot < w.nslots; w.slot += w.step) {
         Item it;
-        it.voxel = slot_voxel(gd, w.slot);
+        it.voxel = slot_voxel<LIST && !FILL>(gd, w.slot);
         it.cg = cg;
         const long off = it.voxel * g.C + it.cg * 8;
         float o[8];
-        if (token && !voxel_active(g, it.voxel)) {
+        if (FILL && !voxel_active(g, it.voxel)) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = tk[j];
         } else {
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(512) apply_kernel(Geo g, const bf16* __restric
     }
 }
 
-template <int ACT>
+template <int ACT, bool LIST>
 __global__ void __launch_bounds__(512)
 bwd_apply_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ x, const bf16* __restrict__ res,
                  const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ saved,
@@ -288,7 +292,7 @@ bwd_apply_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ 
 #pragma unroll 2
     for (; w.slot < w.nslots; w.slot += w.step) {
         Item it;
-        it.voxel = slot_voxel(g, w.slot);
+        it.voxel = slot_voxel<LIST>(g, w.slot);
         it.cg = cg;
         const long off = it.voxel * g.C + it.cg * 8;
         float d[8], f[8], r[8], o[8], gg[8];
@@ -428,8 +432,12 @@ extern "C" int amb_norm_stats(const amb_geo* a, const void* x, double* sums, voi
     if (int e = make_geo(a, g)) return e;
     int CG = g.C / 8, block = pick_block(CG);
     if (block < 0) return block;
-    reduce_kernel<0, 0><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>(
-        g, (const bf16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, sums, nullptr);
+    if (g.list)
+        reduce_kernel<0, 0, true, false><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>(
+            g, (const bf16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, sums, nullptr);
+    else
+        reduce_kernel<0, 0, false, false><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>(
+            g, (const bf16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, sums, nullptr);
     AMB_LAUNCH_CHECK();
     return 0;
 }
@@ -460,12 +468,19 @@ extern "C" int amb_norm_apply(const amb_geo* a, const void* x, const float* scal
     AMB_CHECK(!token || g.active, AMB_ERR_ARG, "densify fill needs the active mask");
     int CG = g.C / 8, block = pick_block(CG);
     if (block < 0) return block;
-#define AMB_APPLY(A)                                                                                    \
-    apply_kernel<A><<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(          \
+#define AMB_APPLY(A, LI, FI)                                                                                \
+    apply_kernel<A, LI, FI><<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(        \
         g, (const bf16*)x, scale, shift, (const bf16*)residual, token, act, (bf16*)out)
-    if (act == AMB_ACT_LRELU) AMB_APPLY(1);
-    else if (act == AMB_ACT_RELU6) AMB_APPLY(2);
-    else AMB_APPLY(0);
+    if (token) { AMB_APPLY(0, false, true); }                       // densify fill: every voxel, no activation
+    else if (g.list) {
+        if (act == AMB_ACT_LRELU) AMB_APPLY(1, true, false);
+        else if (act == AMB_ACT_RELU6) AMB_APPLY(2, true, false);
+        else AMB_APPLY(0, true, false);
+    } else {
+        if (act == AMB_ACT_LRELU) AMB_APPLY(1, false, false);
+        else if (act == AMB_ACT_RELU6) AMB_APPLY(2, false, false);
+        else AMB_APPLY(0, false, false);
+    }
 #undef AMB_APPLY
     AMB_LAUNCH_CHECK();
     return 0;
@@ -479,12 +494,19 @@ extern "C" int amb_norm_bwd_reduce(const amb_geo* a, const void* dout, const voi
     AMB_CHECK(!fill || g.active, AMB_ERR_ARG, "densify backward needs the active mask");
     int CG = g.C / 8, block = pick_block(CG);
     if (block < 0) return block;
-#define AMB_RED(A)                                                                                                       \
-    reduce_kernel<1, A><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>( \
+#define AMB_RED(A, LI, FI)                                                                                                       \
+    reduce_kernel<1, A, LI, FI><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>( \
         g, (const bf16*)x, (const bf16*)dout, (const bf16*)residual, scale, shift, saved, act, fill, sums, dtoken)
-    if (act == AMB_ACT_LRELU) AMB_RED(1);
-    else if (act == AMB_ACT_RELU6) AMB_RED(2);
-    else AMB_RED(0);
+    if (fill) { AMB_RED(0, false, true); }
+    else if (g.list) {
+        if (act == AMB_ACT_LRELU) AMB_RED(1, true, false);
+        else if (act == AMB_ACT_RELU6) AMB_RED(2, true, false);
+        else AMB_RED(0, true, false);
+    } else {
+        if (act == AMB_ACT_LRELU) AMB_RED(1, false, false);
+        else if (act == AMB_ACT_RELU6) AMB_RED(2, false, false);
+        else AMB_RED(0, false, false);
+    }
 #undef AMB_RED
     AMB_LAUNCH_CHECK();
     return 0;
@@ -499,13 +521,19 @@ extern "C" int amb_norm_bwd_apply(const amb_geo* a, const void* dout, const void
     (void)fill;   // dx is only defined on visited (active) voxels; the caller zero-fills dx when the list is sparse
     int CG = g.C / 8, block = pick_block(CG);
     if (block < 0) return block;
-#define AMB_BWD(A)                                                                                              \
-    bwd_apply_kernel<A><<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(              \
+#define AMB_BWD(A, LI)                                                                                          \
+    bwd_apply_kernel<A, LI><<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(          \
         g, (const bf16*)dout, (const bf16*)x, (const bf16*)residual, scale, shift, saved, sums, act, fill, (bf16*)dx, \
         (bf16*)dres, dgamma, dbeta, n_total)
-    if (act == AMB_ACT_LRELU) AMB_BWD(1);
-    else if (act == AMB_ACT_RELU6) AMB_BWD(2);
-    else AMB_BWD(0);
+    if (g.list) {
+        if (act == AMB_ACT_LRELU) AMB_BWD(1, true);
+        else if (act == AMB_ACT_RELU6) AMB_BWD(2, true);
+        else AMB_BWD(0, true);
+    } else {
+        if (act == AMB_ACT_LRELU) AMB_BWD(1, false);
+        else if (act == AMB_ACT_RELU6) AMB_BWD(2, false);
+        else AMB_BWD(0, false);
+    }
 #undef AMB_BWD
     AMB_LAUNCH_CHECK();
     return 0;
