@@ -102,7 +102,7 @@ __device__ __forceinline__ float act_grad(float u, int act) {
 // LIST: walk the active-patch work-list (else the dense tensor); FILL: densify backward (visits every voxel, routes
 // masked voxels to the mask-token gradient).  Compile-time so the dense BatchNorm instantiation carries no decode code.
 template <int MODE, int ACT, bool LIST, bool FILL>
-__global__ void __launch_bounds__(512) reduce_kernel(Geo g, const bf16* __restrict__ x, const bf16* __restrict__ dout,
+__global__ void __launch_bounds__(512, 2) reduce_kernel(Geo g, const bf16* __restrict__ x, const bf16* __restrict__ dout,
                                                      const bf16* __restrict__ res, const float* __restrict__ scale,
                                                      const float* __restrict__ shift, const float* __restrict__ saved,
                                                      int act_unused, int fill_unused, double* __restrict__ sums,
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(512) apply_kernel(Geo g, const bf16* __restric
 }
 
 template <int ACT, bool LIST>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 bwd_apply_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ x, const bf16* __restrict__ res,
                  const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ saved,
                  const double* __restrict__ sums, int act_unused, int fill, bf16* __restrict__ dx, bf16* __restrict__ dres,
