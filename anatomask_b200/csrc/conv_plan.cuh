@@ -187,5 +187,6 @@ int igemm_conv(const Plan& p, const amb_conv_args* a);
 int igemm2_conv(const Plan& p, const amb_conv_args* a);
 int igemm3_conv(const Plan& p, const amb_conv_args* a);
 int igemm_wgrad(const Plan& p, const amb_wgrad_args* a);
+int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a);
 
 }  // namespace amb

@@ -1,0 +1,354 @@
+// tcgen05 weight-gradient kernel, halo-plane variant: dense 3×3×3 stride-1 convolutions whose dY is narrow (Cy = 32/64)
+// — LightDecoder's last two blocks at 64³/128³, where the per-tap kernel (conv_wgrad_tc.cu) re-reads dY 27× through TMA
+// and is bound by the per-unit TMA issue path (measured: tensor pipe 26 %, 2.9 GB DRAM reads for 1.07 GB of operands).
+//
+//     dW[tap][r][c] = Σ_o dY[o − off(tap), r] · X[o, c]          M = r (dY channels), N = c (X channels), K = voxels
+//
+// A CTA walks z along a column of 8×8-voxel tiles.  Per z step it needs one X box [8 y][8 x][Cx] (B operand, MN-major)
+// and the three dY halo planes z−1, z, z+1, each ONE TMA box [10 y][16 x][Cy] that stays in a ring while z advances:
+// every plane is loaded once per column instead of 27 times per tile.  All 9 in-plane taps read the plane in place —
+// the A descriptor starts ((sy+1)·16 + (sx+1)) voxel rows into it (SBO = one y row of the plane; the swizzle phase
+// follows the absolute smem address, as in conv_igemm3.cu).  Taps are stacked along M through the descriptor's LBO:
+//   Cy = 64 : two taps per unit (LBO = byte distance between the two tap origins inside the plane)
+//   Cy = 32 : the three sx taps of one (sz, sy) per unit (LBO = one voxel row = 64 B; the 4th atom is discarded)
+//
+//   warp 0  dY plane producer        warp 1  MMA issuer        warp 2  TMEM allocator       warp 3  X box producer
+//   warps 4-7 epilogue: accumulators (TMEM) → fp32 red.v4 into dW (split-K reduction across CTAs)
+#include "conv_plan.cuh"
+#include "ptx.cuh"
+
+namespace amb {
+
+using namespace ptx;
+
+int encode_view_map(CUtensorMap* m, const void* tensor_base, const View& v, int C, int kc, const int box[4]);
+
+#define WH_MAX_UNITS 28
+#define WH_UNITS_CTA 8               // accumulator units per CTA (unrolled issue loop)
+#define WH_A_SLOTS_MAX 8
+#define WH_B_SLOTS 4
+
+struct WhUnit {
+    int16_t tap[4];                  // weight slab index per M atom (−1 = atom discarded)
+    int32_t off;                     // byte offset of atom 0 inside its plane
+    int32_t lbo;                     // bytes between consecutive atoms
+    int32_t dzslot;                  // 0, 1, 2 : plane z−1, z, z+1 of the step
+};
+
+struct WgradHaloParams {
+    CUtensorMap a_map;               // dY, box (slabW channels, 16 x, 10 y, 1, 1)
+    CUtensorMap b_map;               // X,  box (nslabW channels, 8 x, 8 y, 1, 1)
+    WhUnit units[WH_MAX_UNITS];
+    int n_units, n_batches, units_per_batch;
+    int Cx, Cy, slabW, NTw, nslabW, b_slabs, n_nchunks;
+    uint32_t plane_bytes, b_slab_bytes, b_slot_bytes;
+    uint32_t a_layout, b_layout, a_sbo, b_sbo, a_kstep, b_kstep, idesc;
+    int a_slots;
+    int oN, oD, oH, oW, Ty, Tx;
+    uint32_t n_steps;                // columns × oD
+    int ksplit;
+    float* dw;
+};
+
+struct WhCol {
+    int n0, y0, x0;
+};
+__device__ __forceinline__ WhCol wh_column(const WgradHaloParams& P, uint32_t col) {
+    WhCol c;
+    c.x0 = (int)(col % (uint32_t)P.Tx) * 8; col /= (uint32_t)P.Tx;
+    c.y0 = (int)(col % (uint32_t)P.Ty) * 8;
+    c.n0 = (int)(col / (uint32_t)P.Ty);
+    return c;
+}
+
+__global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constant__ WgradHaloParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t A_SLOTS = (uint32_t)P.a_slots;
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + A_SLOTS * P.plane_bytes;
+    uint8_t* ctrl = b_ring + WH_B_SLOTS * P.b_slot_bytes;
+    uint64_t* a_full = (uint64_t*)ctrl;
+    uint64_t* a_empty = a_full + WH_A_SLOTS_MAX;
+    uint64_t* b_full = a_empty + WH_A_SLOTS_MAX;
+    uint64_t* b_empty = b_full + WH_B_SLOTS;
+    uint64_t* acc_full = b_empty + WH_B_SLOTS;
+    uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < WH_B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // job decode: blockIdx.x = (batch, nchunk, ksplit)
+    uint32_t job = blockIdx.x;
+    const uint32_t ks = job % (uint32_t)P.ksplit; job /= (uint32_t)P.ksplit;
+    const int nchunk = (int)(job % (uint32_t)P.n_nchunks); job /= (uint32_t)P.n_nchunks;
+    const int unit_begin = (int)job * P.units_per_batch;
+    const int unit_count = (P.n_units - unit_begin) < P.units_per_batch ? (P.n_units - unit_begin) : P.units_per_batch;
+    const uint32_t s_begin = (uint32_t)((unsigned long long)P.n_steps * ks / (uint32_t)P.ksplit);
+    const uint32_t s_end = (uint32_t)((unsigned long long)P.n_steps * (ks + 1) / (uint32_t)P.ksplit);
+    const uint32_t oD = (uint32_t)P.oD;
+
+    if (warp == 0) {
+        // dY planes: a segment [z, zend) of one column needs planes z−1 … zend (rows / planes outside the tensor are
+        // zero-filled by TMA = the convolution's zero padding)
+        uint32_t slot = 0, phase = 0, s = s_begin;
+        while (s < s_end) {
+            const uint32_t col = s / oD;
+            const int z = (int)(s - col * oD);
+            const uint32_t rem = s_end - s;
+            const int zend = (oD - (uint32_t)z) < rem ? (int)oD : z + (int)rem;
+            const WhCol c = wh_column(P, col);
+            for (int zp = z - 1; zp <= zend; ++zp) {
+                mbar_wait(&a_empty[slot], phase ^ 1u, 21);
+                if (elect_one()) {
+                    mbar_expect_tx(&a_full[slot], P.plane_bytes);
+                    tma_load_5d(a_ring + slot * P.plane_bytes, &P.a_map, &a_full[slot], 0, c.x0 - 1, c.y0 - 1, zp, c.n0);
+                }
+                __syncwarp();
+                if (++slot == A_SLOTS) { slot = 0; phase ^= 1u; }
+            }
+            s += (uint32_t)(zend - z);
+        }
+    } else if (warp == 3) {
+        uint32_t slot = 0, phase = 0, s = s_begin;
+        while (s < s_end) {
+            const uint32_t col = s / oD;
+            const int z = (int)(s - col * oD);
+            const uint32_t rem = s_end - s;
+            const int zend = (oD - (uint32_t)z) < rem ? (int)oD : z + (int)rem;
+            const WhCol c = wh_column(P, col);
+            for (int zp = z; zp < zend; ++zp) {
+                mbar_wait(&b_empty[slot], phase ^ 1u, 22);
+                if (elect_one()) {
+                    mbar_expect_tx(&b_full[slot], P.b_slab_bytes * (uint32_t)P.b_slabs);
+                    for (int j = 0; j < P.b_slabs; ++j)
+                        tma_load_5d(b_ring + slot * P.b_slot_bytes + j * P.b_slab_bytes, &P.b_map, &b_full[slot],
+                                    nchunk * P.NTw + j * P.nslabW, c.x0, c.y0, zp, c.n0);
+                }
+                __syncwarp();
+                if (++slot == WH_B_SLOTS) { slot = 0; phase ^= 1u; }
+            }
+            s += (uint32_t)(zend - z);
+        }
+    } else if (warp == 1) {
+        // per-unit descriptor constants (registers: the issue loop below is fully unrolled over the CTA's units).  Only
+        // the low descriptor word differs between units: start address (per step) | LBO << 16
+        uint32_t a_lbo[WH_UNITS_CTA], a_off[WH_UNITS_CTA], a_dz[WH_UNITS_CTA];
+#pragma unroll
+        for (int u = 0; u < WH_UNITS_CTA; ++u) {
+            const WhUnit& U = P.units[unit_begin + (u < unit_count ? u : 0)];
+            a_lbo[u] = (((uint32_t)U.lbo >> 4) & 0x3FFFu) << 16;
+            a_off[u] = (uint32_t)U.off >> 4;
+            a_dz[u] = (uint32_t)U.dzslot;
+        }
+        const uint32_t a_desc_hi = (uint32_t)(umma_desc(0, 0, P.a_sbo, P.a_layout) >> 32);
+        const uint32_t a_kstep16 = P.a_kstep >> 4, b_kstep16 = P.b_kstep >> 4, NTw = (uint32_t)P.NTw, idesc = P.idesc;
+        const uint32_t a_ring_u32 = smem_u32(a_ring), b_ring_u32 = smem_u32(b_ring), PB = P.plane_bytes;
+        const uint64_t b_hi = umma_desc(0, P.b_slab_bytes, P.b_sbo, P.b_layout);
+        uint32_t ws = 0, wph = 0;          // next plane to wait for
+        uint32_t s0 = 0;                   // ring slot of plane z−1 of the current step
+        uint32_t bs = 0, bph = 0;
+        bool accum = false;
+        uint32_t s = s_begin;
+        while (s < s_end) {
+            const uint32_t col = s / oD;
+            const uint32_t z = s - col * oD;
+            const uint32_t rem = s_end - s;
+            const uint32_t len = (oD - z) < rem ? (oD - z) : rem;
+            for (int i = 0; i < 2; ++i) {
+                mbar_wait(&a_full[ws], wph, 23);
+                if (++ws == A_SLOTS) { ws = 0; wph ^= 1u; }
+            }
+            for (uint32_t j = 0; j < len; ++j) {
+                mbar_wait(&a_full[ws], wph, 24);
+                if (++ws == A_SLOTS) { ws = 0; wph ^= 1u; }
+                mbar_wait(&b_full[bs], bph, 25);
+                tc_fence_after();
+                const uint32_t s1 = (s0 + 1 == A_SLOTS) ? 0u : s0 + 1;
+                const uint32_t s2 = (s1 + 1 == A_SLOTS) ? 0u : s1 + 1;
+                if (elect_one()) {
+                    const uint32_t p0 = ((a_ring_u32 + s0 * PB) & 0x3FFFFu) >> 4, p1 = ((a_ring_u32 + s1 * PB) & 0x3FFFFu) >> 4,
+                                   p2 = ((a_ring_u32 + s2 * PB) & 0x3FFFFu) >> 4;
+                    const uint64_t bdesc = b_hi | (uint64_t)(((b_ring_u32 + bs * P.b_slot_bytes) & 0x3FFFFu) >> 4);
+                    uint32_t a_lo[WH_UNITS_CTA];
+#pragma unroll
+                    for (int u = 0; u < WH_UNITS_CTA; ++u)
+                        a_lo[u] = a_lbo[u] | ((a_dz[u] == 0 ? p0 : (a_dz[u] == 1 ? p1 : p2)) + a_off[u]);
+                    // 64 voxels = 4 × K16, k outermost: all units of the CTA interleave, so the dependent MMAs on one
+                    // accumulator are unit_count issue slots apart (measured: a lone trailing unit serialises)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                        for (int u = 0; u < WH_UNITS_CTA; ++u) {
+                            if (u < unit_count) {
+                                const uint64_t ad = ((uint64_t)a_desc_hi << 32) | (uint64_t)(a_lo[u] + a_kstep16 * (uint32_t)k);
+                                mma_bf16(tmem_base + (uint32_t)u * NTw, ad, bdesc + (uint64_t)(b_kstep16 * (uint32_t)k), idesc,
+                                         accum || (k != 0));
+                            }
+                        }
+                    }
+                    mma_commit(&a_empty[s0]);
+                    mma_commit(&b_empty[bs]);
+                }
+                __syncwarp();
+                accum = true;
+                s0 = s1;
+                if (++bs == WH_B_SLOTS) { bs = 0; bph ^= 1u; }
+            }
+            // the two trailing planes of the segment
+            const uint32_t t1 = (s0 + 1 == A_SLOTS) ? 0u : s0 + 1;
+            if (elect_one()) {
+                mma_commit(&a_empty[s0]);
+                mma_commit(&a_empty[t1]);
+            }
+            __syncwarp();
+            s0 = (t1 + 1 == A_SLOTS) ? 0u : t1 + 1;
+            s += len;
+        }
+        if (elect_one()) mma_commit(acc_full);
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        const int m = q * 32 + lane;
+        mbar_wait(acc_full, 0, 26);
+        tc_fence_after();
+        if (s_end > s_begin) {
+            const int atom = m / P.slabW, r = m % P.slabW;
+            for (int u = 0; u < unit_count; ++u) {
+                const int w = P.units[unit_begin + u].tap[atom];
+                float* dst = nullptr;
+                if (w >= 0) dst = P.dw + ((long)w * P.Cy + r) * P.Cx + nchunk * P.NTw;
+                const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * P.NTw);
+                for (int col = 0; col < P.NTw; col += 16) {
+                    uint32_t rr[16];
+                    tmem_ld_x16(t_addr + col, rr);
+                    tmem_ld_wait();
+                    if (dst) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + col + j),
+                                         "f"(__uint_as_float(rr[j])), "f"(__uint_as_float(rr[j + 1])),
+                                         "f"(__uint_as_float(rr[j + 2])), "f"(__uint_as_float(rr[j + 3]))
+                                         : "memory");
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// returns 1 when handled, 0 when the shape is outside this kernel's scope, <0 on error
+int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a) {
+    if (getenv("AMB_DISABLE_WH")) return 0;
+    if (a->active_list != nullptr) return 0;                       // sparse layers: the work-list kernel skips tiles
+    if (p.n_in_views != 1 || p.n_out_views != 1 || p.n_taps != 27) return 0;
+    for (int i = 0; i < 27; ++i) {
+        const Tap& T = p.taps[i];
+        if (T.dz < -1 || T.dz > 1 || T.dy < -1 || T.dy > 1 || T.dx < -1 || T.dx > 1) return 0;
+    }
+    if (p.Cy != 32 && p.Cy != 64) return 0;
+    if (!(p.Cx == 32 || p.Cx == 64 || p.Cx % 128 == 0)) return 0;
+    if (p.oH % 8 != 0 || p.oW % 8 != 0 || p.oH < 16 || p.oW < 16) return 0;
+    const View& vi = p.in_views[0];
+    if (vi.D != p.oD || vi.H != p.oH || vi.W != p.oW) return 0;   // stride 1 only
+
+    static WgradHaloParams P;
+    memset(&P, 0, sizeof(P));
+    P.Cx = p.Cx; P.Cy = p.Cy;
+    P.slabW = p.Cy;                                                // one atom = all dY channels of one tap
+    P.NTw = p.Cx < 128 ? p.Cx : 128;
+    P.nslabW = P.NTw < 64 ? P.NTw : 64;
+    P.b_slabs = P.NTw / P.nslabW;
+    P.n_nchunks = p.Cx / P.NTw;
+    const uint32_t a_row = (uint32_t)P.slabW * 2u, b_row = (uint32_t)P.nslabW * 2u;
+    P.plane_bytes = 10u * 16u * a_row;                             // 20 KB (Cy 64) / 10 KB (Cy 32), 1024-aligned
+    P.b_slab_bytes = 64u * b_row;
+    P.b_slot_bytes = P.b_slab_bytes * (uint32_t)P.b_slabs;
+    auto layout_of = [](int w) { return w == 64 ? 2u : (w == 32 ? 4u : 6u); };
+    P.a_layout = layout_of(P.slabW); P.b_layout = layout_of(P.nslabW);
+    P.a_sbo = 16u * a_row;                                         // next 8-voxel group = next y row of the plane
+    P.a_kstep = 2u * P.a_sbo;                                      // K16 = two y rows
+    P.b_sbo = 8u * b_row;
+    P.b_kstep = 16u * b_row;
+    P.idesc = umma_idesc_bf16(128, P.NTw, 1, 1);
+    P.oN = p.oN; P.oD = p.oD; P.oH = p.oH; P.oW = p.oW;
+    P.Ty = p.oH / 8; P.Tx = p.oW / 8;
+    P.dw = a->dw;
+
+    // units: taps of one dY plane (same sz) stacked along M
+    const bool single = getenv("AMB_WH_SINGLE") != nullptr;       // debugging aid: one tap per unit
+    int nu = 0;
+    for (int sz = -1; sz <= 1; ++sz) {
+        // taps of this plane sorted by their byte offset in the plane
+        int idx[9], offs[9], n = 0;
+        for (int sy = -1; sy <= 1; ++sy)
+            for (int sx = -1; sx <= 1; ++sx)
+                for (int t = 0; t < 27; ++t)
+                    if (-p.taps[t].dz == sz && -p.taps[t].dy == sy && -p.taps[t].dx == sx) {
+                        idx[n] = t;
+                        offs[n] = ((sy + 1) * 16 + (sx + 1)) * (int)a_row;
+                        n++;
+                    }
+        if (n != 9) return 0;
+        const int per_unit = single ? 1 : (p.Cy == 64 ? 2 : 3);
+        for (int i = 0; i < 9; i += per_unit) {
+            if (nu >= WH_MAX_UNITS) { set_error("wgrad halo: too many units"); return 0; }
+            WhUnit& U = P.units[nu++];
+            for (int j = 0; j < 4; ++j) U.tap[j] = -1;
+            U.off = offs[i];
+            U.dzslot = sz + 1;
+            U.lbo = (int)a_row;                                    // default: next voxel row (discarded atoms)
+            if (per_unit >= 2 && i + 1 < 9) U.lbo = offs[i + 1] - offs[i];
+            for (int j = 0; j < per_unit && i + j < 9; ++j) {
+                if (j >= 2 && offs[i + j] - offs[i + j - 1] != U.lbo) { set_error("wgrad halo: taps not equidistant"); return -1; }
+                U.tap[j] = p.taps[idx[i + j]].w;
+            }
+        }
+    }
+    P.n_units = nu;
+    int per_batch = 512 / P.NTw;
+    if (per_batch > WH_UNITS_CTA) per_batch = WH_UNITS_CTA;
+    P.n_batches = (nu + per_batch - 1) / per_batch;
+    P.units_per_batch = (nu + P.n_batches - 1) / P.n_batches;
+    P.n_batches = (nu + P.units_per_batch - 1) / P.units_per_batch;
+
+    const int abox[4] = {1, 1, 10, 16}, bbox[4] = {1, 1, 8, 8};
+    if (int e = encode_view_map(&P.a_map, a->dy, p.out_views[0], p.Cy, P.slabW, abox)) return e;
+    if (int e = encode_view_map(&P.b_map, a->x, p.in_views[0], p.Cx, P.nslabW, bbox)) return e;
+
+    const long steps = (long)p.oN * P.Ty * P.Tx * p.oD;
+    if (steps >= (1L << 31)) return 0;
+    P.n_steps = (uint32_t)steps;
+    const int base_jobs = P.n_batches * P.n_nchunks;
+    int ksplit = num_sms() / base_jobs;
+    if (ksplit < 1) ksplit = 1;
+    if ((long)ksplit > steps) ksplit = (int)steps;
+    P.ksplit = ksplit;
+    const uint32_t budget = 227u * 1024u - 1024u - 512u - WH_B_SLOTS * P.b_slot_bytes;
+    P.a_slots = (int)(budget / P.plane_bytes);
+    if (P.a_slots > WH_A_SLOTS_MAX) P.a_slots = WH_A_SLOTS_MAX;
+    if (P.a_slots < 4) return 0;
+    const size_t smem = (size_t)P.a_slots * P.plane_bytes + (size_t)WH_B_SLOTS * P.b_slot_bytes + 1024 + 512;
+    AMB_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad_halo_kernel<<<base_jobs * ksplit, 256, smem, (cudaStream_t)a->stream>>>(P);
+    AMB_LAUNCH_CHECK();
+    return 1;
+}
+
+}  // namespace amb

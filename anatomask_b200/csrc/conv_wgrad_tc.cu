@@ -298,6 +298,8 @@ static int pow2_ceilw(int v) { return 1 << ilog2w(v); }
 static bool chan_ok(int c) { return c == 16 || c == 32 || c == 64 || c % 128 == 0; }
 
 int igemm_wgrad(const Plan& p, const amb_wgrad_args* a) {
+    // dense 3x3x3 s1 with narrow dY: halo-plane kernel (conv_wgrad_halo.cu)
+    if (int r = igemm_wgrad_halo(p, a)) return r;
     // roles here: dY has p.Cy channels (M), X has p.Cx channels (N)
     if (!chan_ok(p.Cx) || !chan_ok(p.Cy)) {
         set_error("wgrad: channels (%d,%d) must be 16, 32, 64 or a multiple of 128", p.Cx, p.Cy);

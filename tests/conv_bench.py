@@ -37,7 +37,9 @@ def main(which):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     # T1 = one accumulator per CTA iteration (dependent-MMA chain), T = interleaved accumulators (default)
     impls = {'v1': (L.IMPL_TCGEN05_V1, None), 'v3': (L.IMPL_TCGEN05, None)}
-    if which != 'all':
+    if which == 'wgrad':
+        impls = {}
+    elif which != 'all':
         impls = {which: impls[which]}
     out = []
     for name, ci, co, S, N in LAYERS:
