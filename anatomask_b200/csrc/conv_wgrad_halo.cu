@@ -12,7 +12,7 @@
 //   Cy = 64 : two taps per unit (LBO = byte distance between the two tap origins inside the plane)
 //   Cy = 32 : the three sx taps of one (sz, sy) per unit (LBO = one voxel row = 64 B; the 4th atom is discarded)
 //
-//   warp 0  dY plane producer        warp 1  MMA issuer        warp 2  TMEM allocator       warp 3  X box producer
+//   warp 0  dY plane producer     warps 1, 2  MMA issuers (warp 2 also owns the TMEM allocation)     warp 3  X box producer
 //   warps 4-7 epilogue: accumulators (TMEM) → fp32 red.v4 into dW (split-K reduction across CTAs)
 #include "conv_plan.cuh"
 #include "ptx.cuh"
@@ -43,7 +43,7 @@ struct WgradHaloParams {
     int Cx, Cy, slabW, NTw, nslabW, b_slabs, n_nchunks;
     uint32_t plane_bytes, b_slab_bytes, b_slot_bytes;
     uint32_t a_layout, b_layout, a_sbo, b_sbo, a_kstep, b_kstep, idesc;
-    int a_slots;
+    int a_slots, issuers;
     int oN, oD, oH, oW, Ty, Tx;
     uint32_t n_steps;                // columns × oD
     int ksplit;
@@ -77,9 +77,10 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
     uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
 
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < WH_B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        mbar_init(acc_full, 1);
+        const uint32_t nI = (uint32_t)P.issuers;                 // every issuing warp commits to the "empty" barriers
+        for (uint32_t s = 0; s < A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], nI); }
+        for (int s = 0; s < WH_B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], nI); }
+        mbar_init(acc_full, nI);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -140,19 +141,24 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
             }
             s += (uint32_t)(zend - z);
         }
-    } else if (warp == 1) {
-        // per-unit descriptor constants (registers: the issue loop below is fully unrolled over the CTA's units).  Only
-        // the low descriptor word differs between units: start address (per step) | LBO << 16
+    } else if (warp == 1 || (warp == 2 && P.issuers == 2)) {
+        // MMA issuers.  One elected thread sustains roughly one tcgen05.mma per ~45 ns (descriptor arithmetic + R2UR moves on
+        // a single warp without ILP), which is slower than the tensor pipe at N <= 64 — so the CTA's units are split across
+        // TWO issuing warps (independent accumulators; every ring barrier then counts both warps' commits).
+        const int iw = warp == 1 ? 0 : 1, nI = P.issuers;
         uint32_t a_lbo[WH_UNITS_CTA], a_off[WH_UNITS_CTA], a_dz[WH_UNITS_CTA];
 #pragma unroll
-        for (int u = 0; u < WH_UNITS_CTA; ++u) {
+        for (int j = 0; j < WH_UNITS_CTA; ++j) {
+            const int u = j * nI + iw;
             const WhUnit& U = P.units[unit_begin + (u < unit_count ? u : 0)];
-            a_lbo[u] = (((uint32_t)U.lbo >> 4) & 0x3FFFu) << 16;
-            a_off[u] = (uint32_t)U.off >> 4;
-            a_dz[u] = (uint32_t)U.dzslot;
+            a_lbo[j] = (((uint32_t)U.lbo >> 4) & 0x3FFFu) << 16;
+            a_off[j] = (uint32_t)U.off >> 4;
+            a_dz[j] = (uint32_t)U.dzslot;
         }
+        const int my_units = (unit_count - iw + nI - 1) / nI;      // units iw, iw + nI, ...
         const uint32_t a_desc_hi = (uint32_t)(umma_desc(0, 0, P.a_sbo, P.a_layout) >> 32);
-        const uint32_t a_kstep16 = P.a_kstep >> 4, b_kstep16 = P.b_kstep >> 4, NTw = (uint32_t)P.NTw, idesc = P.idesc;
+        const uint32_t a_kstep16 = P.a_kstep >> 4, b_kstep16 = P.b_kstep >> 4, idesc = P.idesc;
+        const uint32_t d_stride = (uint32_t)(P.NTw * nI), d_base = tmem_base + (uint32_t)(iw * P.NTw);
         const uint32_t a_ring_u32 = smem_u32(a_ring), b_ring_u32 = smem_u32(b_ring), PB = P.plane_bytes;
         const uint64_t b_hi = umma_desc(0, P.b_slab_bytes, P.b_sbo, P.b_layout);
         uint32_t ws = 0, wph = 0;          // next plane to wait for
@@ -184,15 +190,15 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
 #pragma unroll
                     for (int u = 0; u < WH_UNITS_CTA; ++u)
                         a_lo[u] = a_lbo[u] | ((a_dz[u] == 0 ? p0 : (a_dz[u] == 1 ? p1 : p2)) + a_off[u]);
-                    // 64 voxels = 4 × K16, k outermost: all units of the CTA interleave, so the dependent MMAs on one
-                    // accumulator are unit_count issue slots apart (measured: a lone trailing unit serialises)
+                    // 64 voxels = 4 × K16, k outermost: all units of this issuer interleave, so the dependent MMAs on one
+                    // accumulator are my_units issue slots apart (measured: a lone trailing unit serialises)
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
 #pragma unroll
                         for (int u = 0; u < WH_UNITS_CTA; ++u) {
-                            if (u < unit_count) {
+                            if (u < my_units) {
                                 const uint64_t ad = ((uint64_t)a_desc_hi << 32) | (uint64_t)(a_lo[u] + a_kstep16 * (uint32_t)k);
-                                mma_bf16(tmem_base + (uint32_t)u * NTw, ad, bdesc + (uint64_t)(b_kstep16 * (uint32_t)k), idesc,
+                                mma_bf16(d_base + (uint32_t)u * d_stride, ad, bdesc + (uint64_t)(b_kstep16 * (uint32_t)k), idesc,
                                          accum || (k != 0));
                             }
                         }
@@ -290,6 +296,8 @@ int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a) {
     P.oN = p.oN; P.oD = p.oD; P.oH = p.oH; P.oW = p.oW;
     P.Ty = p.oH / 8; P.Tx = p.oW / 8;
     P.dw = a->dw;
+    const char* ienv = getenv("AMB_WH_ISSUERS");
+    P.issuers = (ienv && atoi(ienv) == 1) ? 1 : 2;
 
     // units: taps of one dY plane (same sz) stacked along M
     const bool single = getenv("AMB_WH_SINGLE") != nullptr;       // debugging aid: one tap per unit
