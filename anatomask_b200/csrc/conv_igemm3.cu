@@ -22,7 +22,7 @@ namespace amb {
 using namespace ptx;
 
 #define V3_PLANE_BYTES (18 * 16 * 64)      // 18 KB
-#define V3_A_SLOTS 8
+#define V3_A_SLOTS_MAX 12              // plane ring depth is a launch parameter (6 planes in use + prefetch)
 #define V3_B_SLOTS 8
 #define V3_T 4
 
@@ -36,7 +36,7 @@ struct Igemm3Params {
     double* stats;
     int oN, oD, oH, oW, Cy;
     int lgPv, fd, fh, fw;
-    int Ty, Tx, Tzg, n_ntiles, NT, kchunks;
+    int Ty, Tx, Tzg, n_ntiles, NT, kchunks, issuers, a_slots;
     uint32_t b_bytes, b_tx, tmem_cols, idesc;
     int8_t tap_dy[27], tap_dx[27];       // taps sorted by dz (9 per plane offset), values 0..2
     int16_t tap_w[27];
@@ -74,11 +74,12 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* a_ring = smem;
+    const uint32_t V3_A_SLOTS = (uint32_t)P.a_slots;
     uint8_t* b_ring = smem + V3_A_SLOTS * V3_PLANE_BYTES;
     uint8_t* ctrl = b_ring + (size_t)V3_B_SLOTS * P.b_bytes;
-    uint64_t* a_full = (uint64_t*)ctrl;            // [8]
-    uint64_t* a_empty = a_full + 8;                // [8]
-    uint64_t* b_full = a_empty + 8;                // [8]
+    uint64_t* a_full = (uint64_t*)ctrl;            // [12]
+    uint64_t* a_empty = a_full + V3_A_SLOTS_MAX;   // [12]
+    uint64_t* b_full = a_empty + V3_A_SLOTS_MAX;   // [8]
     uint64_t* b_empty = b_full + 8;                // [8]
     uint64_t* tfull = b_empty + 8;                 // [2]
     uint64_t* tempty = tfull + 2;                  // [2]
@@ -86,11 +87,10 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
     float* s_stats = (float*)(ctrl + 512);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 8; ++s) {
-            mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1);
-            mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1);
-        }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        const uint32_t nI = (uint32_t)P.issuers;          // every issuing warp commits to the consumer-side barriers
+        for (int s = 0; s < V3_A_SLOTS_MAX; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], nI); }
+        for (int s = 0; s < V3_B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], nI); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], nI); mbar_init(&tempty[a], 4); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) { prefetch_tmap(&P.a_map); prefetch_tmap(&P.w_map); }
@@ -145,8 +145,12 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == 1) {
-        // =============================== MMA issuer ===============================
+    } else if (warp == 1 || (warp == 2 && P.issuers == 2)) {
+        // =============================== MMA issuers ===============================
+        // One elected thread sustains about one tcgen05.mma per 45 ns, slower than the tensor pipe at N <= 64; with two
+        // issuing warps each owns half of the V3_T tiles (independent accumulators).
+        const int t_begin = P.issuers == 2 ? (warp == 1 ? 0 : V3_T / 2) : 0;
+        const int t_end = P.issuers == 2 ? t_begin + V3_T / 2 : V3_T;
         // K-major, 64-byte swizzle: layout 4.  A: 8-row groups (x) 1024 B apart (one y step of the plane).  B: 512 B.
         const uint32_t a_hi = (uint32_t)(umma_desc(0, 16, 1024, 4) >> 32), b_hi = (uint32_t)(umma_desc(0, 16, 512, 4) >> 32);
         const uint32_t lo_const = (uint32_t)(umma_desc(0, 16, 0, 4) & 0xFFFFFFFFu);
@@ -179,6 +183,7 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
                             for (int k = 0; k < 2; ++k) {
 #pragma unroll
                                 for (int t = 0; t < V3_T; ++t) {
+                                    if (t < t_begin || t >= t_end) continue;
                                     uint32_t s = a_slot0 + (uint32_t)(t + dz);
                                     if (s >= V3_A_SLOTS) s -= V3_A_SLOTS;
                                     const uint32_t a_addr = a_ring_u32 + s * V3_PLANE_BYTES + row_off;
@@ -318,6 +323,8 @@ int igemm3_conv(const Plan& p, const amb_conv_args* a) {
     P.lgPv = p.lgPv; P.fd = p.fd; P.fh = p.fh; P.fw = p.fw;
     P.Ty = ceil_div(p.oH, 16); P.Tx = ceil_div(p.oW, 8); P.Tzg = ceil_div(p.oD, V3_T);
     P.NT = NT; P.n_ntiles = p.Cy / NT; P.kchunks = p.Cx / 32;
+    const char* ienv = getenv("AMB_V3_ISSUERS");
+    P.issuers = (ienv && atoi(ienv) == 1) ? 1 : 2;
     P.b_tx = (uint32_t)NT * 64u;
     P.b_bytes = (P.b_tx + 1023u) & ~1023u;
     P.tmem_cols = 32;
@@ -360,7 +367,15 @@ int igemm3_conv(const Plan& p, const amb_conv_args* a) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         AMB_CHECK(r == CUDA_SUCCESS, AMB_ERR_CUDA, "cuTensorMapEncodeTiled(weight slab) failed: %d", (int)r);
     }
-    size_t smem = (size_t)V3_A_SLOTS * V3_PLANE_BYTES + (size_t)V3_B_SLOTS * P.b_bytes + 1024 + 512 +
+    // plane ring: 6 planes are in use per (unit, channel chunk) and four of them are released together at its end, so
+    // with 8 slots the next chunk's planes 2..5 only start loading then (a ~1 us bubble per chunk); 10 slots hide it
+    const char* senv = getenv("AMB_V3_A_SLOTS");
+    P.a_slots = senv ? atoi(senv) : 10;
+    if (P.a_slots < 7 || P.a_slots > V3_A_SLOTS_MAX) P.a_slots = 10;
+    while (P.a_slots > 7 && (size_t)P.a_slots * V3_PLANE_BYTES + (size_t)V3_B_SLOTS * P.b_bytes + 1024 + 512 +
+                                    (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0) > 227 * 1024)
+        P.a_slots--;
+    size_t smem = (size_t)P.a_slots * V3_PLANE_BYTES + (size_t)V3_B_SLOTS * P.b_bytes + 1024 + 512 +
                   (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0);
     if (smem > 227 * 1024) return 0;
     long units = (long)p.oN * P.Ty * P.Tx * P.Tzg * P.n_ntiles;

@@ -42,7 +42,7 @@ def main(which):
     elif which != 'all':
         impls = {which: impls[which]}
     out = []
-    for name, ci, co, S, N in LAYERS:
+    for name, ci, co, S, N in LAYERS[:int(os.environ.get('AMB_CB_LAYERS', len(LAYERS)))]:
         x = torch.randn(N, S, S, S, ci, device=dev).to(bf16)
         dy = torch.randn(N, S, S, S, co, device=dev).to(bf16)
         w = torch.randn(co, ci, 3, 3, 3, device=dev) / (27 * ci) ** 0.5
