@@ -654,18 +654,107 @@ extern "C" int amb_adamw_step(float* p, const float* g, float* m, float* v, long
     return 0;
 }
 
+// Tiled variant for the layouts the path actually uses: the parameter tensor has the taps innermost (stride 1) and one of
+// the two channel axes next (stride T), i.e. param[(slow·F + fast)·T + t] ↔ packed[(t·A + a)·B + b].  A block moves a tile
+// of 256 (a, b) positions × ≤32 taps through shared memory so that both sides are accessed in runs of ≥ 32 B — the
+// element-wise kernels above read with a stride of T floats and ran at ~1/4 of HBM speed.
+//   PACK  : fp32 parameters → bf16 packed          !PACK : fp32 packed gradient → fp32 parameter layout
+template <bool PACK>
+__global__ void __launch_bounds__(256) repack_tiled_kernel(const float* __restrict__ src, void* __restrict__ dst_, int T,
+                                                           int A, int B, int b_fast, int tiles_b, int tchunks) {
+    __shared__ float tile[256][33];
+    const int TA = b_fast ? 4 : 16, TB = b_fast ? 64 : 16;
+    uint32_t blk = blockIdx.x;
+    const int tcx = (int)(blk % (uint32_t)tchunks); blk /= (uint32_t)tchunks;
+    const int a0 = (int)(blk / (uint32_t)tiles_b) * TA, b0 = (int)(blk % (uint32_t)tiles_b) * TB;
+    const int t0 = tcx * 32;
+    const int tc = (T - t0) < 32 ? (T - t0) : 32;
+    const uint32_t n = 256u * (uint32_t)tc;
+    // parameter-layout index of tile position (la, lb), tap 0
+    auto param_index = [&](int la, int lb) -> long {
+        const int a = a0 + la, b = b0 + lb;
+        return (b_fast ? ((long)a * B + b) : ((long)b * A + a)) * T + t0;
+    };
+    if (PACK) {
+        for (uint32_t e = threadIdx.x; e < n; e += 256u) {          // parameter order: taps, then the fast channel axis
+            const int t = (int)(e % (uint32_t)tc);
+            const uint32_t q = e / (uint32_t)tc;
+            int la, lb;
+            if (b_fast) { lb = (int)(q % (uint32_t)TB); la = (int)(q / (uint32_t)TB); }
+            else { la = (int)(q % (uint32_t)TA); lb = (int)(q / (uint32_t)TA); }
+            float v = 0.f;
+            if (a0 + la < A && b0 + lb < B) v = src[param_index(la, lb) + t];
+            tile[la * TB + lb][t] = v;
+        }
+        __syncthreads();
+        bf16* dst = (bf16*)dst_;
+        const uint32_t hb = (uint32_t)TB / 2u;
+        for (uint32_t e = threadIdx.x; e < n / 2u; e += 256u) {     // packed order: b pairs, a, tap
+            const int lb = (int)(e % hb) * 2;
+            const uint32_t q = e / hb;
+            const int la = (int)(q % (uint32_t)TA), t = (int)(q / (uint32_t)TA);
+            if (a0 + la < A && b0 + lb < B) {
+                const int p = la * TB + lb;
+                *reinterpret_cast<uint32_t*>(dst + ((long)(t0 + t) * A + a0 + la) * B + b0 + lb) = pack2(tile[p][t], tile[p + 1][t]);
+            }
+        }
+    } else {
+        for (uint32_t e = threadIdx.x; e < n; e += 256u) {          // packed order
+            const int lb = (int)(e % (uint32_t)TB);
+            const uint32_t q = e / (uint32_t)TB;
+            const int la = (int)(q % (uint32_t)TA), t = (int)(q / (uint32_t)TA);
+            float v = 0.f;
+            if (a0 + la < A && b0 + lb < B) v = src[((long)(t0 + t) * A + a0 + la) * B + b0 + lb];
+            tile[la * TB + lb][t] = v;
+        }
+        __syncthreads();
+        float* dst = (float*)dst_;
+        for (uint32_t e = threadIdx.x; e < n; e += 256u) {          // parameter order
+            const int t = (int)(e % (uint32_t)tc);
+            const uint32_t q = e / (uint32_t)tc;
+            int la, lb;
+            if (b_fast) { lb = (int)(q % (uint32_t)TB); la = (int)(q / (uint32_t)TB); }
+            else { la = (int)(q % (uint32_t)TA); lb = (int)(q / (uint32_t)TA); }
+            if (a0 + la < A && b0 + lb < B) dst[param_index(la, lb) + t] = tile[la * TB + lb][t];
+        }
+    }
+}
+
+// 1: b is the fast parameter axis, 0: a is, −1: layout not covered by the tiled kernel
+static int repack_case(int T, int A, int B, long st, long sa, long sb) {
+    if (st != 1 || (B & 1)) return -1;
+    if (sb == T && sa == (long)B * T) return 1;
+    if (sa == T && sb == (long)A * T) return 0;
+    return -1;
+}
+
+template <bool PACK>
+static void launch_repack(const float* src, void* dst, int T, int A, int B, int b_fast, cudaStream_t st) {
+    const int TA = b_fast ? 4 : 16, TB = b_fast ? 64 : 16;
+    const int tiles_a = (A + TA - 1) / TA, tiles_b = (B + TB - 1) / TB, tchunks = (T + 31) / 32;
+    repack_tiled_kernel<PACK><<<tiles_a * tiles_b * tchunks, 256, 0, st>>>(src, dst, T, A, B, b_fast, tiles_b, tchunks);
+}
+
 extern "C" int amb_pack_weight(const float* src, void* dst, int T, int A, int B, long st, long sa, long sb,
                                void* stream) {
-    pack_weight_kernel<<<grid_cap((long)T * A * B, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, T, A, B,
-                                                                                           st, sa, sb);
+    const int c = repack_case(T, A, B, st, sa, sb);
+    if (c >= 0)
+        launch_repack<true>(src, dst, T, A, B, c, (cudaStream_t)stream);
+    else
+        pack_weight_kernel<<<grid_cap((long)T * A * B, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, T, A, B,
+                                                                                               st, sa, sb);
     AMB_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int amb_unpack_wgrad(const float* src, float* dst, int T, int A, int B, long st, long sa, long sb,
                                 void* stream) {
-    unpack_wgrad_kernel<<<grid_cap((long)T * A * B, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, dst, T, A, B, st, sa,
-                                                                                            sb);
+    const int c = repack_case(T, A, B, st, sa, sb);
+    if (c >= 0)
+        launch_repack<false>(src, dst, T, A, B, c, (cudaStream_t)stream);
+    else
+        unpack_wgrad_kernel<<<grid_cap((long)T * A * B, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, dst, T, A, B, st,
+                                                                                                sa, sb);
     AMB_LAUNCH_CHECK();
     return 0;
 }

@@ -41,9 +41,12 @@ def join_side_stream(dev=None):
 
 
 
+NO_SIDE = False      # bench.py's per-launch timing pass: one stream, so a launch's CUDA-event pair times that launch alone
+
+
 def _side_stream(dev):
     import os
-    if os.environ.get('AMB_NO_SIDE_STREAM') == '1':
+    if NO_SIDE or os.environ.get('AMB_NO_SIDE_STREAM') == '1':
         return None
     s = _SIDE.get(dev)
     if s is None:

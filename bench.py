@@ -209,7 +209,10 @@ def run_ours(args):
     value = B * world / (ms_step / 1e3)
     # ---- the same K steps launched eagerly with a CUDA-event pair around every conv launch: per-kernel durations for
     #      the roofline and the launch count (a graph replay issues exactly these launches) ---------------------------
+    #      (single stream for this pass: with the weight-gradient branch on its side stream two kernels share the SMs and
+    #      an event pair would time both)
     ops.PROFILE = []
+    ops.NO_SIDE = True
     lib.amb_reset_launch_count()
     barrier()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -221,6 +224,7 @@ def run_ours(args):
     ms_eager_total = p0.elapsed_time(p1)
     launches = int(lib.amb_launch_count())
     prof, ops.PROFILE = ops.PROFILE, None
+    ops.NO_SIDE = False
     # ---- roofline of the dominant kernel family (live CUDA-event timing of every launch in the timed region) ----
     fam = {}
     for kind, flops, a, b in prof:
@@ -243,7 +247,7 @@ def run_ours(args):
                 'peak_source': f'{peak_src} bf16_tflops_sustained (kernel timed inside a long step)', 'traffic': None,
                 'launches_timed': n_k, 'avg_launch_ms': ms_k / max(1, n_k),
                 'all_conv_kernels': {'achieved': conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0,
-                                     'share_of_step': conv_ms / ms_total, 'eager_pass_ms_per_step': ms_eager_total / args.steps,
+                                     'share_of_step': conv_ms / ms_eager_total, 'eager_pass_ms_per_step': ms_eager_total / args.steps,
                                      'per_family_tflops': {k: v[0] / (v[1] * 1e-3) / 1e12 for k, v in fam.items() if v[1] > 0}},
                 'algorithmic_flops_per_step': conv_fl / args.steps}
     # ---- timed region 2: end to end through the public API, host buffers -----------------------------------
