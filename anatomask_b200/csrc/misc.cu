@@ -492,6 +492,113 @@ stem_wgrad_kernel(Geo g, const float* __restrict__ inp, const bf16* __restrict__
     }
 }
 
+// Tiled variant (the default): a block stages SW_VOX visible voxels (SW_VOX / P runs) of dy1 / dy3 as fp32 and the masked
+// 3 × 3 × (P + 2) input neighbourhood of every run in shared memory; thread = (run group, channel group, slot) then runs a
+// pure LDS + FMA loop (the kernel above issues a dependent global load per voxel and slot and reached 270 GB/s).
+#define SW_VOX 128
+__global__ void __launch_bounds__(256)
+stem_wgrad_tiled_kernel(Geo g, const float* __restrict__ inp, const bf16* __restrict__ dy1, const bf16* __restrict__ dy3,
+                        float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw3,
+                        float* __restrict__ db3) {
+    extern __shared__ float sm[];
+    const int C = g.C, CG = C / 8, P = g.P, R = SW_VOX >> g.lgP, PX = P + 2;
+    float* sd1 = sm;                         // [SW_VOX][C]
+    float* sd3 = sd1 + SW_VOX * C;           // [SW_VOX][C]
+    float* sx = sd3 + SW_VOX * C;            // [R][9][PX]  masked input rows (dz, dy), x0 − 1 … x0 + P
+    float* sacc = sx + R * 9 * PX;           // [32][C]
+    int* meta = (int*)(sacc + 32 * C);       // [R][5] first voxel (−1 = no run), n, z, y, x0
+    for (int i = threadIdx.x; i < 32 * C; i += blockDim.x) sacc[i] = 0.f;
+    const int slot = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int cg = wq % CG, grp = wq / CG, G = 8 / CG;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const long nruns = geo_num_runs(g);
+    for (long base = (long)blockIdx.x * R; base < nruns; base += (long)gridDim.x * R) {
+        __syncthreads();                     // previous tile fully consumed (and sacc zeroed on the first pass)
+        if ((int)threadIdx.x < R) {
+            const long run = base + threadIdx.x;
+            int* m = meta + threadIdx.x * 5;
+            if (run < nruns) {
+                const RunPos r = decode_run(g, run);
+                uint32_t t = (uint32_t)r.voxel;
+                m[0] = (int)t;
+                m[4] = (int)(t % (uint32_t)g.W); t /= (uint32_t)g.W;
+                m[3] = (int)(t % (uint32_t)g.H); t /= (uint32_t)g.H;
+                m[2] = (int)(t % (uint32_t)g.D);
+                m[1] = r.n;
+            } else {
+                m[0] = -1;
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < SW_VOX * CG; i += blockDim.x) {
+            const int c8 = i % CG, vox = i / CG;
+            const int vfirst = meta[(vox >> g.lgP) * 5];
+            float a[8], b[8];
+            if (vfirst >= 0) {
+                const long off = ((long)vfirst + (vox & (P - 1))) * C + c8 * 8;
+                load8(dy1 + off, a);
+                load8(dy3 + off, b);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+            }
+            float4* o1 = reinterpret_cast<float4*>(sd1 + vox * C + c8 * 8);
+            float4* o3 = reinterpret_cast<float4*>(sd3 + vox * C + c8 * 8);
+            o1[0] = make_float4(a[0], a[1], a[2], a[3]); o1[1] = make_float4(a[4], a[5], a[6], a[7]);
+            o3[0] = make_float4(b[0], b[1], b[2], b[3]); o3[1] = make_float4(b[4], b[5], b[6], b[7]);
+        }
+        for (int i = threadIdx.x; i < R * 9 * PX; i += blockDim.x) {
+            const int xi = i % PX, q = i / PX;
+            const int r9 = q % 9, r = q / 9;
+            const int* m = meta + r * 5;
+            float v = 0.f;
+            if (m[0] >= 0) {
+                const int iz = m[2] + r9 / 3 - 1, iy = m[3] + r9 % 3 - 1, x = m[4] - 1 + xi;
+                if ((unsigned)iz < (unsigned)g.D && (unsigned)iy < (unsigned)g.H && (unsigned)x < (unsigned)g.W &&
+                    g.active[((m[1] * g.fd + (iz >> g.lgP)) * g.fh + (iy >> g.lgP)) * g.fw + (x >> g.lgP)])
+                    v = inp[(((long)m[1] * g.D + iz) * g.H + iy) * g.W + x];
+            }
+            sx[i] = v;
+        }
+        __syncthreads();
+        if (slot < 30) {
+            const float* dbase = slot >= 28 ? sd3 : sd1;
+            for (int r = grp; r < R; r += G) {
+                const float* xrow = slot < 27 ? sx + (r * 9 + slot / 3) * PX + slot % 3
+                                              : (slot == 28 ? sx + (r * 9 + 4) * PX + 1 : nullptr);
+                const float* d = dbase + (r << g.lgP) * C + cg * 8;
+#pragma unroll 4
+                for (int v = 0; v < P; ++v) {
+                    const float xv = xrow ? xrow[v] : 1.f;
+                    const float4 a = *reinterpret_cast<const float4*>(d + v * C);
+                    const float4 b = *reinterpret_cast<const float4*>(d + v * C + 4);
+                    acc[0] = fmaf(a.x, xv, acc[0]); acc[1] = fmaf(a.y, xv, acc[1]);
+                    acc[2] = fmaf(a.z, xv, acc[2]); acc[3] = fmaf(a.w, xv, acc[3]);
+                    acc[4] = fmaf(b.x, xv, acc[4]); acc[5] = fmaf(b.y, xv, acc[5]);
+                    acc[6] = fmaf(b.z, xv, acc[6]); acc[7] = fmaf(b.w, xv, acc[7]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (slot < 30) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&sacc[slot * C + cg * 8 + j], acc[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 30 * C; i += blockDim.x) {
+        const int s = i / C, c = i % C;
+        const float v = sacc[i];
+        if (v == 0.f) continue;
+        if (s < 27) atomicAdd(&dw1[c * 27 + s], v);
+        else if (s == 27) atomicAdd(&db1[c], v);
+        else if (s == 28) atomicAdd(&dw3[c], v);
+        else atomicAdd(&db3[c], v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // reconstruction head (C → 1)
 // ------------------------------------------------------------------------------------------------------------
@@ -659,63 +766,64 @@ extern "C" int amb_adamw_step(float* p, const float* g, float* m, float* v, long
 // of 256 (a, b) positions × ≤32 taps through shared memory so that both sides are accessed in runs of ≥ 32 B — the
 // element-wise kernels above read with a stride of T floats and ran at ~1/4 of HBM speed.
 //   PACK  : fp32 parameters → bf16 packed          !PACK : fp32 packed gradient → fp32 parameter layout
-template <bool PACK>
+template <bool PACK, bool BFAST>
 __global__ void __launch_bounds__(256) repack_tiled_kernel(const float* __restrict__ src, void* __restrict__ dst_, int T,
-                                                           int A, int B, int b_fast, int tiles_b, int tchunks) {
+                                                           int A, int B, int tiles_b, int tchunks) {
     __shared__ float tile[256][33];
-    const int TA = b_fast ? 4 : 16, TB = b_fast ? 64 : 16;
+    constexpr uint32_t TA = BFAST ? 4 : 16, TB = BFAST ? 64 : 16;     // powers of two: index splits are shifts
     uint32_t blk = blockIdx.x;
     const int tcx = (int)(blk % (uint32_t)tchunks); blk /= (uint32_t)tchunks;
-    const int a0 = (int)(blk / (uint32_t)tiles_b) * TA, b0 = (int)(blk % (uint32_t)tiles_b) * TB;
+    const int a0 = (int)(blk / (uint32_t)tiles_b) * (int)TA, b0 = (int)(blk % (uint32_t)tiles_b) * (int)TB;
     const int t0 = tcx * 32;
-    const int tc = (T - t0) < 32 ? (T - t0) : 32;
-    const uint32_t n = 256u * (uint32_t)tc;
-    // parameter-layout index of tile position (la, lb), tap 0
-    auto param_index = [&](int la, int lb) -> long {
-        const int a = a0 + la, b = b0 + lb;
-        return (b_fast ? ((long)a * B + b) : ((long)b * A + a)) * T + t0;
+    const uint32_t tc = (uint32_t)((T - t0) < 32 ? (T - t0) : 32);
+    const float inv_tc = 1.0f / (float)tc;                              // e / tc below is exact for e < 8192, tc <= 32
+    const uint32_t n = 256u * tc;
+    // parameter-layout index of tile position (la, lb), tap t0
+    auto param_index = [&](uint32_t la, uint32_t lb) -> long {
+        const long a = a0 + (int)la, b = b0 + (int)lb;
+        return (BFAST ? (a * B + b) : (b * A + a)) * T + t0;
+    };
+    // parameter order: taps fastest, then the fast channel axis
+    auto split_param = [&](uint32_t e, uint32_t& la, uint32_t& lb, uint32_t& t) {
+        const uint32_t q = (uint32_t)(((float)e + 0.5f) * inv_tc);
+        t = e - q * tc;
+        if (BFAST) { lb = q % TB; la = q / TB; }
+        else { la = q % TA; lb = q / TA; }
     };
     if (PACK) {
-        for (uint32_t e = threadIdx.x; e < n; e += 256u) {          // parameter order: taps, then the fast channel axis
-            const int t = (int)(e % (uint32_t)tc);
-            const uint32_t q = e / (uint32_t)tc;
-            int la, lb;
-            if (b_fast) { lb = (int)(q % (uint32_t)TB); la = (int)(q / (uint32_t)TB); }
-            else { la = (int)(q % (uint32_t)TA); lb = (int)(q / (uint32_t)TA); }
+        for (uint32_t e = threadIdx.x; e < n; e += 256u) {
+            uint32_t la, lb, t;
+            split_param(e, la, lb, t);
             float v = 0.f;
-            if (a0 + la < A && b0 + lb < B) v = src[param_index(la, lb) + t];
+            if (a0 + (int)la < A && b0 + (int)lb < B) v = __ldg(src + param_index(la, lb) + t);
             tile[la * TB + lb][t] = v;
         }
         __syncthreads();
         bf16* dst = (bf16*)dst_;
-        const uint32_t hb = (uint32_t)TB / 2u;
+        constexpr uint32_t hb = TB / 2u;
         for (uint32_t e = threadIdx.x; e < n / 2u; e += 256u) {     // packed order: b pairs, a, tap
-            const int lb = (int)(e % hb) * 2;
-            const uint32_t q = e / hb;
-            const int la = (int)(q % (uint32_t)TA), t = (int)(q / (uint32_t)TA);
-            if (a0 + la < A && b0 + lb < B) {
-                const int p = la * TB + lb;
-                *reinterpret_cast<uint32_t*>(dst + ((long)(t0 + t) * A + a0 + la) * B + b0 + lb) = pack2(tile[p][t], tile[p + 1][t]);
+            const uint32_t lb = (e % hb) * 2u, q = e / hb;
+            const uint32_t la = q % TA, t = q / TA;
+            if (a0 + (int)la < A && b0 + (int)lb < B) {
+                const uint32_t p = la * TB + lb;
+                *reinterpret_cast<uint32_t*>(dst + ((long)(t0 + (int)t) * A + a0 + (int)la) * B + b0 + (int)lb) =
+                    pack2(tile[p][t], tile[p + 1][t]);
             }
         }
     } else {
         for (uint32_t e = threadIdx.x; e < n; e += 256u) {          // packed order
-            const int lb = (int)(e % (uint32_t)TB);
-            const uint32_t q = e / (uint32_t)TB;
-            const int la = (int)(q % (uint32_t)TA), t = (int)(q / (uint32_t)TA);
+            const uint32_t lb = e % TB, q = e / TB;
+            const uint32_t la = q % TA, t = q / TA;
             float v = 0.f;
-            if (a0 + la < A && b0 + lb < B) v = src[((long)(t0 + t) * A + a0 + la) * B + b0 + lb];
+            if (a0 + (int)la < A && b0 + (int)lb < B) v = __ldg(src + ((long)(t0 + (int)t) * A + a0 + (int)la) * B + b0 + (int)lb);
             tile[la * TB + lb][t] = v;
         }
         __syncthreads();
         float* dst = (float*)dst_;
-        for (uint32_t e = threadIdx.x; e < n; e += 256u) {          // parameter order
-            const int t = (int)(e % (uint32_t)tc);
-            const uint32_t q = e / (uint32_t)tc;
-            int la, lb;
-            if (b_fast) { lb = (int)(q % (uint32_t)TB); la = (int)(q / (uint32_t)TB); }
-            else { la = (int)(q % (uint32_t)TA); lb = (int)(q / (uint32_t)TA); }
-            if (a0 + la < A && b0 + lb < B) dst[param_index(la, lb) + t] = tile[la * TB + lb][t];
+        for (uint32_t e = threadIdx.x; e < n; e += 256u) {
+            uint32_t la, lb, t;
+            split_param(e, la, lb, t);
+            if (a0 + (int)la < A && b0 + (int)lb < B) dst[param_index(la, lb) + t] = tile[la * TB + lb][t];
         }
     }
 }
@@ -732,7 +840,10 @@ template <bool PACK>
 static void launch_repack(const float* src, void* dst, int T, int A, int B, int b_fast, cudaStream_t st) {
     const int TA = b_fast ? 4 : 16, TB = b_fast ? 64 : 16;
     const int tiles_a = (A + TA - 1) / TA, tiles_b = (B + TB - 1) / TB, tchunks = (T + 31) / 32;
-    repack_tiled_kernel<PACK><<<tiles_a * tiles_b * tchunks, 256, 0, st>>>(src, dst, T, A, B, b_fast, tiles_b, tchunks);
+    if (b_fast)
+        repack_tiled_kernel<PACK, true><<<tiles_a * tiles_b * tchunks, 256, 0, st>>>(src, dst, T, A, B, tiles_b, tchunks);
+    else
+        repack_tiled_kernel<PACK, false><<<tiles_a * tiles_b * tchunks, 256, 0, st>>>(src, dst, T, A, B, tiles_b, tchunks);
 }
 
 extern "C" int amb_pack_weight(const float* src, void* dst, int T, int A, int B, long st, long sa, long sb,
@@ -778,6 +889,16 @@ extern "C" int amb_stem_wgrad(const float* inp, const uint8_t* active, const int
     Geo g;
     if (int e = stem_geo(g, active, active_list, active_count, N, D, H, W, fd, fh, fw, C)) return e;
     int CG = C / 8;
+    if ((CG == 1 || CG == 2 || CG == 4 || CG == 8) && g.P <= SW_VOX && (SW_VOX / g.P) % (8 / CG) == 0 &&
+        !getenv("AMB_STEM_WGRAD_V1")) {
+        const int R = SW_VOX / g.P;
+        const size_t smem = ((size_t)2 * SW_VOX * C + (size_t)R * 9 * (g.P + 2) + 32 * C) * sizeof(float) + (size_t)R * 5 * sizeof(int);
+        AMB_CUDA(cudaFuncSetAttribute(stem_wgrad_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stem_wgrad_tiled_kernel<<<num_sms() * 4, 256, smem, (cudaStream_t)stream>>>(g, inp, (const bf16*)dy1, (const bf16*)dy3,
+                                                                                  dw1, db1, dw3, db3);
+        AMB_LAUNCH_CHECK();
+        return 0;
+    }
     int lanes = 1024 / (32 * CG);
     AMB_CHECK(lanes >= 1, AMB_ERR_ARG, "stem wgrad: C=%d too large", C);
     int block = lanes * 32 * CG;

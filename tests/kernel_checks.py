@@ -230,6 +230,33 @@ def check_stem(Cc=32, S=32, N=2, f=2, seed=0, tol=1.2e-2):
     return res
 
 
+def check_repack(seed=0):
+    """amb_pack_weight / amb_unpack_wgrad in the four layouts ops.py uses, bit-exact against torch."""
+    from anatomask_b200 import ops, _lib as L
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for (co, ci, T) in [(64, 64, 27), (24, 16, 27), (136, 72, 27), (32, 64, 1), (64, 32, 64), (8, 8, 27), (512, 256, 27)]:
+        w = torch.randn(co, ci, T, generator=g).to(dev)             # conv layout (Cout, Cin, taps)
+        fwd = ops._pack(w, T, co, ci, 1, ci * T, T)                 # [t][co][ci]
+        dgr = ops._pack(w, T, ci, co, 1, T, ci * T)                 # [t][ci][co]
+        assert torch.equal(fwd, w.permute(2, 0, 1).to(bf16)), ('fwd', co, ci, T)
+        assert torch.equal(dgr, w.permute(2, 1, 0).to(bf16)), ('dgrad', co, ci, T)
+        wt = torch.randn(ci, co, T, generator=g).to(dev)            # ConvTranspose layout (Cin, Cout, taps)
+        tf = ops._pack(wt, T, co, ci, 1, T, co * T)                 # [t][co][ci]
+        assert torch.equal(tf, wt.permute(2, 1, 0).to(bf16)), ('convT', co, ci, T)
+        dwp = torch.randn(T, co, ci, generator=g).to(dev)           # packed gradient → parameter layout
+        dw = torch.full((co, ci, T), float('nan'), device=dev)
+        L.call('amb_unpack_wgrad', ops._p(dwp), ops._p(dw), T, co, ci, 1, ci * T, T, ops._stream())
+        assert torch.equal(dw, dwp.permute(1, 2, 0)), ('unpack', co, ci, T)
+        dwt = torch.full((ci, co, T), float('nan'), device=dev)
+        L.call('amb_unpack_wgrad', ops._p(dwp), ops._p(dwt), T, co, ci, 1, T, co * T, ops._stream())
+        assert torch.equal(dwt, dwp.permute(2, 1, 0)), ('unpack convT', co, ci, T)
+        out[f'{co}x{ci}x{T}'] = 'exact'
+    torch.cuda.synchronize()
+    return out
+
+
 def check_proj(Cc=32, S=16, N=2, seed=0, tol=1e-2):
     from anatomask_b200 import ops
     dev = _dev()

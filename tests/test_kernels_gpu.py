@@ -21,6 +21,17 @@ def test_hbm_bound_kernels(name):
     kc.CHECKS[name]()
 
 
+@pytest.mark.parametrize('kw', [dict(Cc=64, S=32), dict(Cc=16, S=64, f=4), dict(Cc=8, S=32, N=1), dict(Cc=24, S=32)])
+def test_stem_channel_widths(kw):
+    """tiled stem wgrad: 8 / 4 / 2 / 1 channel groups per warp row; C = 24 takes the per-run kernel"""
+    kc.check_stem(**kw)
+
+
+def test_weight_repack_layouts():
+    """tiled pack / unpack (taps innermost) against torch permutes, incl. ragged tiles, k = 1 and the 64-tap ConvT"""
+    kc.check_repack()
+
+
 @pytest.mark.parametrize('kw', [
     dict(mode='sparse', act=1, residual=True), dict(mode='sparse', act=0, residual=False, Cc=32, S=32),
     dict(mode='dense', act=2, residual=False), dict(mode='dense', act=0, residual=False, Cc=512, S=8),
