@@ -376,15 +376,18 @@ stem_fwd_kernel(Geo g, const float* __restrict__ inp, const float* __restrict__ 
     __syncthreads();
     const long runs = geo_num_runs(g);
     const long total = (runs << g.lgP) * CG;
-    for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(item % CG);
-        const long t = item / CG;
-        const int v = (int)(t & (g.P - 1));
-        RunPos r = decode_run(g, t >> g.lgP);
+    // 32-bit index arithmetic throughout (host checks total < 2^31): five 64-bit divisions per thread cost more than the
+    // 27-tap stencil itself
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < (uint32_t)total; item += gridDim.x * blockDim.x) {
+        const int cg = (int)(item % (uint32_t)CG);
+        const uint32_t t = item / (uint32_t)CG;
+        const int v = (int)(t & (uint32_t)(g.P - 1));
+        RunPos r = decode_run(g, (long)(t >> g.lgP));
         const long voxel = r.voxel + v;
-        const int x = (int)(voxel % g.W);
-        const int y = (int)((voxel / g.W) % g.H);
-        const int z = (int)((voxel / ((long)g.W * g.H)) % g.D);
+        uint32_t vq = (uint32_t)voxel;
+        const int x = (int)(vq % (uint32_t)g.W); vq /= (uint32_t)g.W;
+        const int y = (int)(vq % (uint32_t)g.H); vq /= (uint32_t)g.H;
+        const int z = (int)(vq % (uint32_t)g.D);
         float acc[8], o3[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = sw[27 * C + cg * 8 + j];
@@ -631,9 +634,9 @@ proj_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const f
     float wv[8], acc[8], accb = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { wv[j] = w[cg * 8 + j]; acc[j] = 0.f; }
-    const long total = voxels * CG;
-    for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += (long)gridDim.x * blockDim.x) {
-        const long v = item / CG;
+    // blockDim is a multiple of CG: a thread keeps its channel group and walks voxels with a constant stride
+    const long vstride = (long)gridDim.x * (blockDim.x / CG);
+    for (long v = (long)blockIdx.x * (blockDim.x / CG) + threadIdx.x / CG; v < voxels; v += vstride) {
         const float d = drec[v];
         float f[8], o[8];
         load8(x + v * C + cg * 8, f);
@@ -876,6 +879,7 @@ extern "C" int amb_stem_fwd(const float* inp, const uint8_t* active, const int* 
     Geo g;
     if (int e = stem_geo(g, active, active_list, active_count, N, D, H, W, fd, fh, fw, C)) return e;
     int block = (256 / (C / 8)) * (C / 8);
+    AMB_CHECK((long)N * D * H * W * (C / 8) < (1L << 31), AMB_ERR_ARG, "stem: tensor too large for 32-bit indexing");
     stem_fwd_kernel<<<grid_cap((long)N * D * H * W * (C / 8), block, 8), block, 30 * C * sizeof(float),
                       (cudaStream_t)stream>>>(g, inp, w1, b1, w3, b3, (bf16*)out1, (bf16*)out3);
     AMB_LAUNCH_CHECK();

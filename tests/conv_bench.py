@@ -68,6 +68,17 @@ def main(which):
         row['wgrad'] = round(flops / t / 1e9, 1)
         print(json.dumps(row), flush=True)
         out.append(row)
+    # ConvTranspose k4 s2 (decoder upsampling): 64 -> 64, 64^3 -> 128^3 and 128 -> 128, 32^3 -> 64^3
+    for name, c, S, N in [('dec3.up 64->64 @64->128', 64, 64, 2), ('dec2.up 128->128 @32->64', 128, 32, 2)]:
+        x = torch.randn(N, S, S, S, c, device=dev).to(bf16)
+        w = torch.randn(c, c, 4, 4, 4, device=dev) / (8 * c) ** 0.5
+        wp = ops._pack(w, 64, c, c, 1, 64, c * 64)
+        y = torch.empty(N, 2 * S, 2 * S, 2 * S, c, dtype=bf16, device=dev)
+        flops = 2.0 * N * S ** 3 * 64 * c * c
+        t = time_it(lambda: ops._conv_call(L.OP_CONVT, L.IMPL_TCGEN05, (N, S, S, S), c, c, 4, 2, x, y, wp), flush)
+        row = {'layer': name, 'convT_fwd': round(flops / t / 1e9, 1)}
+        print(json.dumps(row), flush=True)
+        out.append(row)
     return out
 
 

@@ -61,7 +61,10 @@ def test_conv_fwd_dgrad_wgrad(kw):
 
 
 @pytest.mark.parametrize('kw', [dict(Cin=16, Cout=8, S=4, impl=D), dict(Cin=64, Cout=64, S=8, impl=T),
-                                dict(Cin=512, Cout=512, S=4, impl=T), dict(Cin=32, Cout=32, S=8, impl=T)])
+                                dict(Cin=512, Cout=512, S=4, impl=T), dict(Cin=32, Cout=32, S=8, impl=T),
+                                # halo-plane kernel, 8 parity classes as output groups (input edge >= 16, Cout <= 64)
+                                dict(Cin=64, Cout=64, S=16, impl=T), dict(Cin=64, Cout=32, S=16, N=1, impl=T),
+                                dict(Cin=128, Cout=64, S=16, N=1, impl=T), dict(Cin=32, Cout=16, S=20, N=1, impl=T)])
 def test_conv_transpose(kw):
     kc.check_convT(**kw)
 
