@@ -44,6 +44,8 @@ struct WgradHaloParams {
     uint32_t plane_bytes, b_slab_bytes, b_slot_bytes;
     uint32_t a_layout, b_layout, a_sbo, b_sbo, a_kstep, b_kstep, idesc;
     int a_slots, issuers;
+    int wide, mslabs, a_slabs, b_slots;   // wide: Cy >= 128, a unit is one tap x one 128-channel slab of dY (two 64-channel atoms)
+    uint32_t plane_slab_bytes;
     int oN, oD, oH, oW, Ty, Tx;
     uint32_t n_steps;                // columns × oD
     int ksplit;
@@ -68,7 +70,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
     const uint32_t A_SLOTS = (uint32_t)P.a_slots;
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + A_SLOTS * P.plane_bytes;
-    uint8_t* ctrl = b_ring + WH_B_SLOTS * P.b_slot_bytes;
+    const uint32_t B_SLOTS = (uint32_t)P.b_slots;
+    uint8_t* ctrl = b_ring + B_SLOTS * P.b_slot_bytes;
     uint64_t* a_full = (uint64_t*)ctrl;
     uint64_t* a_empty = a_full + WH_A_SLOTS_MAX;
     uint64_t* b_full = a_empty + WH_A_SLOTS_MAX;
@@ -93,6 +96,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
     uint32_t job = blockIdx.x;
     const uint32_t ks = job % (uint32_t)P.ksplit; job /= (uint32_t)P.ksplit;
     const int nchunk = (int)(job % (uint32_t)P.n_nchunks); job /= (uint32_t)P.n_nchunks;
+    const int mslab = (int)(job / (uint32_t)P.n_batches);
+    job %= (uint32_t)P.n_batches;
     const int unit_begin = (int)job * P.units_per_batch;
     const int unit_count = (P.n_units - unit_begin) < P.units_per_batch ? (P.n_units - unit_begin) : P.units_per_batch;
     const uint32_t s_begin = (uint32_t)((unsigned long long)P.n_steps * ks / (uint32_t)P.ksplit);
@@ -113,7 +118,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
                 mbar_wait(&a_empty[slot], phase ^ 1u, 21);
                 if (elect_one()) {
                     mbar_expect_tx(&a_full[slot], P.plane_bytes);
-                    tma_load_5d(a_ring + slot * P.plane_bytes, &P.a_map, &a_full[slot], 0, c.x0 - 1, c.y0 - 1, zp, c.n0);
+                    for (int j = 0; j < P.a_slabs; ++j)
+                        tma_load_5d(a_ring + slot * P.plane_bytes + j * P.plane_slab_bytes, &P.a_map, &a_full[slot],
+                                    mslab * 128 + j * 64, c.x0 - 1, c.y0 - 1, zp, c.n0);
                 }
                 __syncwarp();
                 if (++slot == A_SLOTS) { slot = 0; phase ^= 1u; }
@@ -137,7 +144,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
                                     nchunk * P.NTw + j * P.nslabW, c.x0, c.y0, zp, c.n0);
                 }
                 __syncwarp();
-                if (++slot == WH_B_SLOTS) { slot = 0; phase ^= 1u; }
+                if (++slot == B_SLOTS) { slot = 0; phase ^= 1u; }
             }
             s += (uint32_t)(zend - z);
         }
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
                 __syncwarp();
                 accum = true;
                 s0 = s1;
-                if (++bs == WH_B_SLOTS) { bs = 0; bph ^= 1u; }
+                if (++bs == B_SLOTS) { bs = 0; bph ^= 1u; }
             }
             // the two trailing planes of the segment
             const uint32_t t1 = (s0 + 1 == A_SLOTS) ? 0u : s0 + 1;
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
         mbar_wait(acc_full, 0, 26);
         tc_fence_after();
         if (s_end > s_begin) {
-            const int atom = m / P.slabW, r = m % P.slabW;
+            const int atom = P.wide ? 0 : m / P.slabW, r = P.wide ? mslab * 128 + m : m % P.slabW;
             for (int u = 0; u < unit_count; ++u) {
                 const int w = P.units[unit_begin + u].tap[atom];
                 float* dst = nullptr;
@@ -268,7 +275,8 @@ int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a) {
         const Tap& T = p.taps[i];
         if (T.dz < -1 || T.dz > 1 || T.dy < -1 || T.dy > 1 || T.dx < -1 || T.dx > 1) return 0;
     }
-    if (p.Cy != 32 && p.Cy != 64) return 0;
+    const bool wide = p.Cy >= 128 && !getenv("AMB_WH_NO_WIDE");
+    if (p.Cy != 32 && p.Cy != 64 && !(wide && p.Cy % 128 == 0)) return 0;
     if (!(p.Cx == 32 || p.Cx == 64 || p.Cx % 128 == 0)) return 0;
     if (p.oH % 8 != 0 || p.oW % 8 != 0 || p.oH < 16 || p.oW < 16) return 0;
     const View& vi = p.in_views[0];
@@ -277,13 +285,22 @@ int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a) {
     static WgradHaloParams P;
     memset(&P, 0, sizeof(P));
     P.Cx = p.Cx; P.Cy = p.Cy;
-    P.slabW = p.Cy;                                                // one atom = all dY channels of one tap
-    P.NTw = p.Cx < 128 ? p.Cx : 128;
+    P.slabW = wide ? 64 : p.Cy;                                    // one atom = all dY channels of one tap (64 when wide)
+    P.wide = wide ? 1 : 0;
+    P.mslabs = wide ? p.Cy / 128 : 1;
+    P.a_slabs = wide ? 2 : 1;
+    P.b_slots = wide ? 2 : WH_B_SLOTS;                             // wide planes are 40 KB: trade X ring depth for a 5th plane
+    // wide layers: 128-column accumulators (4 units per CTA).  Measured against 64 columns / 8 units per CTA: 1141 vs 908
+    // TFLOP/s on 128->128 @64^3 — the N = 128 MMA halves the operand reads per FLOP, which matters more than plane traffic
+    const char* ntenv = getenv("AMB_WH_WIDE_NT");
+    const int nt_cap = (wide && ntenv && atoi(ntenv) == 64) ? 64 : 128;
+    P.NTw = p.Cx < nt_cap ? p.Cx : nt_cap;
     P.nslabW = P.NTw < 64 ? P.NTw : 64;
     P.b_slabs = P.NTw / P.nslabW;
     P.n_nchunks = p.Cx / P.NTw;
     const uint32_t a_row = (uint32_t)P.slabW * 2u, b_row = (uint32_t)P.nslabW * 2u;
-    P.plane_bytes = 10u * 16u * a_row;                             // 20 KB (Cy 64) / 10 KB (Cy 32), 1024-aligned
+    P.plane_slab_bytes = 10u * 16u * a_row;                        // 20 KB (64 channels) / 10 KB (32), 1024-aligned
+    P.plane_bytes = P.plane_slab_bytes * (uint32_t)P.a_slabs;
     P.b_slab_bytes = 64u * b_row;
     P.b_slot_bytes = P.b_slab_bytes * (uint32_t)P.b_slabs;
     auto layout_of = [](int w) { return w == 64 ? 2u : (w == 32 ? 4u : 6u); };
@@ -314,7 +331,7 @@ int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a) {
                         n++;
                     }
         if (n != 9) return 0;
-        const int per_unit = single ? 1 : (p.Cy == 64 ? 2 : 3);
+        const int per_unit = (single || wide) ? 1 : (p.Cy == 64 ? 2 : 3);
         for (int i = 0; i < 9; i += per_unit) {
             if (nu >= WH_MAX_UNITS) { set_error("wgrad halo: too many units"); return 0; }
             WhUnit& U = P.units[nu++];
@@ -322,6 +339,7 @@ int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a) {
             U.off = offs[i];
             U.dzslot = sz + 1;
             U.lbo = (int)a_row;                                    // default: next voxel row (discarded atoms)
+            if (wide) U.lbo = (int)P.plane_slab_bytes;             // second atom = channels 64..127 of the same tap
             if (per_unit >= 2 && i + 1 < 9) U.lbo = offs[i + 1] - offs[i];
             for (int j = 0; j < per_unit && i + j < 9; ++j) {
                 if (j >= 2 && offs[i + j] - offs[i + j - 1] != U.lbo) { set_error("wgrad halo: taps not equidistant"); return -1; }
@@ -343,16 +361,16 @@ int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a) {
     const long steps = (long)p.oN * P.Ty * P.Tx * p.oD;
     if (steps >= (1L << 31)) return 0;
     P.n_steps = (uint32_t)steps;
-    const int base_jobs = P.n_batches * P.n_nchunks;
+    const int base_jobs = P.mslabs * P.n_batches * P.n_nchunks;
     int ksplit = num_sms() / base_jobs;
     if (ksplit < 1) ksplit = 1;
     if ((long)ksplit > steps) ksplit = (int)steps;
     P.ksplit = ksplit;
-    const uint32_t budget = 227u * 1024u - 1024u - 512u - WH_B_SLOTS * P.b_slot_bytes;
+    const uint32_t budget = 227u * 1024u - 1024u - 512u - (uint32_t)P.b_slots * P.b_slot_bytes;
     P.a_slots = (int)(budget / P.plane_bytes);
     if (P.a_slots > WH_A_SLOTS_MAX) P.a_slots = WH_A_SLOTS_MAX;
     if (P.a_slots < 4) return 0;
-    const size_t smem = (size_t)P.a_slots * P.plane_bytes + (size_t)WH_B_SLOTS * P.b_slot_bytes + 1024 + 512;
+    const size_t smem = (size_t)P.a_slots * P.plane_bytes + (size_t)P.b_slots * P.b_slot_bytes + 1024 + 512;
     AMB_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wgrad_halo_kernel<<<base_jobs * ksplit, 256, smem, (cudaStream_t)a->stream>>>(P);
     AMB_LAUNCH_CHECK();
