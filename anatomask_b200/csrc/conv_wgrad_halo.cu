@@ -23,7 +23,8 @@ using namespace ptx;
 
 int encode_view_map(CUtensorMap* m, const void* tensor_base, const View& v, int C, int kc, const int box[4]);
 
-#define WH_MAX_UNITS 28
+#define WH_MAX_UNITS 64
+#define WH_MAX_BATCHES 32
 #define WH_UNITS_CTA 8               // accumulator units per CTA (unrolled issue loop)
 #define WH_A_SLOTS_MAX 8
 #define WH_B_SLOTS 4
@@ -36,10 +37,13 @@ struct WhUnit {
 };
 
 struct WgradHaloParams {
-    CUtensorMap a_map;               // dY, box (slabW channels, 16 x, 10 y, 1, 1)
+    CUtensorMap a_maps[8];           // dY views (1 for a convolution, the 8 parity classes of a ConvTranspose), box
+                                     // (slabW channels, 16 x, 10 y, 1, 1)
     CUtensorMap b_map;               // X,  box (nslabW channels, 8 x, 8 y, 1, 1)
     WhUnit units[WH_MAX_UNITS];
-    int n_units, n_batches, units_per_batch;
+    int n_units, n_batches;
+    int16_t batch_unit_begin[WH_MAX_BATCHES], batch_unit_count[WH_MAX_BATCHES];   // a batch = the units of one CTA
+    int8_t batch_class[WH_MAX_BATCHES];                                          // dY view of the batch's units
     int Cx, Cy, slabW, NTw, nslabW, b_slabs, n_nchunks;
     uint32_t plane_bytes, b_slab_bytes, b_slot_bytes;
     uint32_t a_layout, b_layout, a_sbo, b_sbo, a_kstep, b_kstep, idesc;
@@ -98,8 +102,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
     const int nchunk = (int)(job % (uint32_t)P.n_nchunks); job /= (uint32_t)P.n_nchunks;
     const int mslab = (int)(job / (uint32_t)P.n_batches);
     job %= (uint32_t)P.n_batches;
-    const int unit_begin = (int)job * P.units_per_batch;
-    const int unit_count = (P.n_units - unit_begin) < P.units_per_batch ? (P.n_units - unit_begin) : P.units_per_batch;
+    const int unit_begin = P.batch_unit_begin[job], unit_count = P.batch_unit_count[job];
+    const CUtensorMap* a_map = &P.a_maps[P.batch_class[job]];
     const uint32_t s_begin = (uint32_t)((unsigned long long)P.n_steps * ks / (uint32_t)P.ksplit);
     const uint32_t s_end = (uint32_t)((unsigned long long)P.n_steps * (ks + 1) / (uint32_t)P.ksplit);
     const uint32_t oD = (uint32_t)P.oD;
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
                 if (elect_one()) {
                     mbar_expect_tx(&a_full[slot], P.plane_bytes);
                     for (int j = 0; j < P.a_slabs; ++j)
-                        tma_load_5d(a_ring + slot * P.plane_bytes + j * P.plane_slab_bytes, &P.a_map, &a_full[slot],
+                        tma_load_5d(a_ring + slot * P.plane_bytes + j * P.plane_slab_bytes, a_map, &a_full[slot],
                                     mslab * 128 + j * 64, c.x0 - 1, c.y0 - 1, zp, c.n0);
                 }
                 __syncwarp();
@@ -270,11 +274,15 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
 int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a) {
     if (getenv("AMB_DISABLE_WH")) return 0;
     if (a->active_list != nullptr) return 0;                       // sparse layers: the work-list kernel skips tiles
-    if (p.n_in_views != 1 || p.n_out_views != 1 || p.n_taps != 27) return 0;
-    for (int i = 0; i < 27; ++i) {
+    // a convolution (27 taps, one dY view) or a ConvTranspose k4 s2 (8 parity-class views of dY with 8 taps each)
+    const bool is_conv = p.n_out_views == 1 && p.n_taps == 27;
+    const bool is_convT = a->op == AMB_OP_CONVT && p.n_out_views == 8 && p.n_taps == 64 && !getenv("AMB_WH_NO_CONVT");
+    if (p.n_in_views != 1 || !(is_conv || is_convT)) return 0;
+    for (int i = 0; i < p.n_taps; ++i) {
         const Tap& T = p.taps[i];
         if (T.dz < -1 || T.dz > 1 || T.dy < -1 || T.dy > 1 || T.dx < -1 || T.dx > 1) return 0;
     }
+    if (is_convT && p.Cy < 64) return 0;
     const bool wide = p.Cy >= 128 && !getenv("AMB_WH_NO_WIDE");
     if (p.Cy != 32 && p.Cy != 64 && !(wide && p.Cy % 128 == 0)) return 0;
     if (!(p.Cx == 32 || p.Cx == 64 || p.Cx % 128 == 0)) return 0;
@@ -316,46 +324,60 @@ int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a) {
     const char* ienv = getenv("AMB_WH_ISSUERS");
     P.issuers = (ienv && atoi(ienv) == 1) ? 1 : 2;
 
-    // units: taps of one dY plane (same sz) stacked along M
+    // units: taps of one dY view and plane (same sz) stacked along M; batches = the units of one CTA, never mixing views
     const bool single = getenv("AMB_WH_SINGLE") != nullptr;       // debugging aid: one tap per unit
-    int nu = 0;
-    for (int sz = -1; sz <= 1; ++sz) {
-        // taps of this plane sorted by their byte offset in the plane
-        int idx[9], offs[9], n = 0;
-        for (int sy = -1; sy <= 1; ++sy)
-            for (int sx = -1; sx <= 1; ++sx)
-                for (int t = 0; t < 27; ++t)
-                    if (-p.taps[t].dz == sz && -p.taps[t].dy == sy && -p.taps[t].dx == sx) {
-                        idx[n] = t;
-                        offs[n] = ((sy + 1) * 16 + (sx + 1)) * (int)a_row;
-                        n++;
-                    }
-        if (n != 9) return 0;
-        const int per_unit = (single || wide) ? 1 : (p.Cy == 64 ? 2 : 3);
-        for (int i = 0; i < 9; i += per_unit) {
-            if (nu >= WH_MAX_UNITS) { set_error("wgrad halo: too many units"); return 0; }
-            WhUnit& U = P.units[nu++];
-            for (int j = 0; j < 4; ++j) U.tap[j] = -1;
-            U.off = offs[i];
-            U.dzslot = sz + 1;
-            U.lbo = (int)a_row;                                    // default: next voxel row (discarded atoms)
-            if (wide) U.lbo = (int)P.plane_slab_bytes;             // second atom = channels 64..127 of the same tap
-            if (per_unit >= 2 && i + 1 < 9) U.lbo = offs[i + 1] - offs[i];
-            for (int j = 0; j < per_unit && i + j < 9; ++j) {
-                if (j >= 2 && offs[i + j] - offs[i + j - 1] != U.lbo) { set_error("wgrad halo: taps not equidistant"); return -1; }
-                U.tap[j] = p.taps[idx[i + j]].w;
+    int per_batch = 512 / P.NTw;
+    if (per_batch > WH_UNITS_CTA) per_batch = WH_UNITS_CTA;
+    int nu = 0, nb = 0;
+    for (int g = 0; g < p.n_groups; ++g) {
+        const Group& G = p.groups[g];
+        const int cls_unit_begin = nu;
+        for (int sz = -1; sz <= 1; ++sz) {
+            // taps of this view and plane sorted by their byte offset in the plane
+            int idx[9], offs[9], n = 0;
+            for (int sy = -1; sy <= 1; ++sy)
+                for (int sx = -1; sx <= 1; ++sx)
+                    for (int t = G.tap_begin; t < G.tap_begin + G.tap_count; ++t)
+                        if (-p.taps[t].dz == sz && -p.taps[t].dy == sy && -p.taps[t].dx == sx) {
+                            idx[n] = t;
+                            offs[n] = ((sy + 1) * 16 + (sx + 1)) * (int)a_row;
+                            n++;
+                        }
+            const int per_unit = (single || wide) ? 1 : (p.Cy == 64 ? 2 : 3);
+            if (per_unit == 3 && n != 9) return 0;
+            for (int i = 0; i < n; i += per_unit) {
+                if (nu >= WH_MAX_UNITS) { set_error("wgrad halo: too many units"); return 0; }
+                WhUnit& U = P.units[nu++];
+                for (int j = 0; j < 4; ++j) U.tap[j] = -1;
+                U.off = offs[i];
+                U.dzslot = sz + 1;
+                U.lbo = (int)a_row;                                    // default: next voxel row (discarded atoms)
+                if (wide) U.lbo = (int)P.plane_slab_bytes;             // second atom = channels 64..127 of the same tap
+                if (per_unit >= 2 && i + 1 < n) U.lbo = offs[i + 1] - offs[i];
+                for (int j = 0; j < per_unit && i + j < n; ++j) {
+                    if (j >= 2 && offs[i + j] - offs[i + j - 1] != U.lbo) { set_error("wgrad halo: taps not equidistant"); return -1; }
+                    U.tap[j] = p.taps[idx[i + j]].w;
+                }
             }
+        }
+        // balanced batches over this view's units
+        const int cu = nu - cls_unit_begin;
+        if (cu == 0) continue;
+        const int cb = (cu + per_batch - 1) / per_batch, upb = (cu + cb - 1) / cb;
+        for (int u0 = 0; u0 < cu; u0 += upb) {
+            if (nb >= WH_MAX_BATCHES) { set_error("wgrad halo: too many batches"); return 0; }
+            P.batch_unit_begin[nb] = (int16_t)(cls_unit_begin + u0);
+            P.batch_unit_count[nb] = (int16_t)((cu - u0) < upb ? (cu - u0) : upb);
+            P.batch_class[nb] = (int8_t)G.out_view;
+            nb++;
         }
     }
     P.n_units = nu;
-    int per_batch = 512 / P.NTw;
-    if (per_batch > WH_UNITS_CTA) per_batch = WH_UNITS_CTA;
-    P.n_batches = (nu + per_batch - 1) / per_batch;
-    P.units_per_batch = (nu + P.n_batches - 1) / P.n_batches;
-    P.n_batches = (nu + P.units_per_batch - 1) / P.units_per_batch;
+    P.n_batches = nb;
 
     const int abox[4] = {1, 1, 10, 16}, bbox[4] = {1, 1, 8, 8};
-    if (int e = encode_view_map(&P.a_map, a->dy, p.out_views[0], p.Cy, P.slabW, abox)) return e;
+    for (int v = 0; v < p.n_out_views; ++v)
+        if (int e = encode_view_map(&P.a_maps[v], a->dy, p.out_views[v], p.Cy, P.slabW, abox)) return e;
     if (int e = encode_view_map(&P.b_map, a->x, p.in_views[0], p.Cx, P.nslabW, bbox)) return e;
 
     const long steps = (long)p.oN * P.Ty * P.Tx * p.oD;

@@ -77,6 +77,12 @@ def main(which):
         flops = 2.0 * N * S ** 3 * 64 * c * c
         t = time_it(lambda: ops._conv_call(L.OP_CONVT, L.IMPL_TCGEN05, (N, S, S, S), c, c, 4, 2, x, y, wp), flush)
         row = {'layer': name, 'convT_fwd': round(flops / t / 1e9, 1)}
+        dy = torch.randn(N, 2 * S, 2 * S, 2 * S, c, device=dev).to(bf16)
+        dw = torch.zeros(64, c, c, device=dev)
+        a = L.WgradArgs(L.OP_CONVT, L.IMPL_TCGEN05, N, S, S, S, c, c, 4, 2, x.data_ptr(), dy.data_ptr(), dw.data_ptr(),
+                        1, 1, 1, 0, 0, torch.cuda.current_stream().cuda_stream)
+        t = time_it(lambda: L.call('amb_conv_wgrad', C.byref(a)), flush)
+        row['convT_wgrad'] = round(flops / t / 1e9, 1)
         print(json.dumps(row), flush=True)
         out.append(row)
     return out
