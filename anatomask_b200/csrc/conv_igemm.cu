@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
     uint64_t* tempty_bar = tfull_bar + 2;                 // [2]
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
     float* s_stats = (float*)(ctrl + 256);                // [2][Cy] when stats requested
+    float* s_bias = s_stats + (P.stats ? 2 * p.Cy : 0);   // [Cy] (zeros without a bias): the epilogue reads it as float4
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
         prefetch_tmap(&P.w_map);
     }
     if (P.stats) for (int i = threadIdx.x; i < 2 * p.Cy; i += blockDim.x) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < p.Cy; i += blockDim.x) s_bias[i] = P.bias ? P.bias[i] : 0.f;
     if (warp == 2) tmem_alloc(tmem_slot, P.tmem_cols);
     tc_fence_before();
     __syncthreads();
@@ -329,15 +331,18 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                     tmem_ld_wait();
                     const int ncol = wide ? 32 : 16;
                     float v[32];
+                    const float4* bq = reinterpret_cast<const float4*>(s_bias + st.nt * P.NT + col);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float f = 0.f;
-                        if (j < ncol) {
-                            f = __uint_as_float(r[j]);
-                            if (P.bias) f += __ldg(P.bias + st.nt * P.NT + col + j);
-                            if (!on) f = 0.f;
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (j < ncol) b4 = bq[j >> 2];
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            float f = 0.f;
+                            if (j < ncol && on) f = __uint_as_float(r[j + jj]) + bb[jj];
+                            v[j + jj] = f;
                         }
-                        v[j] = f;
                     }
                     if (valid) {
 #pragma unroll
@@ -457,7 +462,8 @@ int igemm_conv(const Plan& p, const amb_conv_args* a) {
     if (slabs_full > n_slabs) n_slabs = slabs_full;
     if (int e = encode_weight_map(&P.w_map, a->w, n_slabs, p.Cy, p.Cx, KC, NT)) return e;
 
-    size_t smem = (size_t)P.stages * P.stage_bytes + 1024 + 256 + (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0);
+    size_t smem = (size_t)P.stages * P.stage_bytes + 1024 + 256 + (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0) +
+                  (size_t)p.Cy * sizeof(float);
     long tiles_upper = (((long)P.Tn * P.Tz * P.Ty * P.Tx + T - 1) / T) * p.n_groups * P.n_ntiles;
     int grid = (int)(tiles_upper < (long)num_sms() ? tiles_upper : (long)num_sms());
     cudaStream_t st = (cudaStream_t)a->stream;

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
     uint64_t* tempty = tfull + 2;                  // [2]
     uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
     float* s_stats = (float*)(ctrl + 512);
+    float* s_bias = s_stats + (P.stats ? 2 * P.Cy : 0);   // [Cy] (zeros without a bias): the epilogue reads it as float4
 
     if (threadIdx.x == 0) {
         const uint32_t nI = (uint32_t)P.issuers;          // every issuing warp commits to the consumer-side barriers
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
     }
     if (warp == 0 && lane == 0) { prefetch_tmap(&P.a_map); prefetch_tmap(&P.w_map); }
     if (P.stats) for (int i = threadIdx.x; i < 2 * P.Cy; i += blockDim.x) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < P.Cy; i += blockDim.x) s_bias[i] = P.bias ? P.bias[i] : 0.f;
     if (warp == 2) tmem_alloc(tmem_slot, P.tmem_cols);
     tc_fence_before();
     __syncthreads();
@@ -243,15 +245,18 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
                     tmem_ld_wait();
                     const int ncol = wide ? 32 : 16;
                     float v[32];
+                    const float4* bq = reinterpret_cast<const float4*>(s_bias + c.nt * P.NT + col);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float f = 0.f;
-                        if (j < ncol) {
-                            f = __uint_as_float(r[j]);
-                            if (P.bias) f += __ldg(P.bias + c.nt * P.NT + col + j);
-                            if (!on) f = 0.f;
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (j < ncol) b4 = bq[j >> 2];
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            float f = 0.f;
+                            if (j < ncol && on) f = __uint_as_float(r[j + jj]) + bb[jj];
+                            v[j + jj] = f;
                         }
-                        v[j] = f;
                     }
                     if (valid_xy) {
 #pragma unroll
@@ -373,10 +378,10 @@ int igemm3_conv(const Plan& p, const amb_conv_args* a) {
     P.a_slots = senv ? atoi(senv) : 10;
     if (P.a_slots < 7 || P.a_slots > V3_A_SLOTS_MAX) P.a_slots = 10;
     while (P.a_slots > 7 && (size_t)P.a_slots * V3_PLANE_BYTES + (size_t)V3_B_SLOTS * P.b_bytes + 1024 + 512 +
-                                    (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0) > 227 * 1024)
+                                    (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0) + (size_t)p.Cy * sizeof(float) > 227 * 1024)
         P.a_slots--;
     size_t smem = (size_t)P.a_slots * V3_PLANE_BYTES + (size_t)V3_B_SLOTS * P.b_bytes + 1024 + 512 +
-                  (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0);
+                  (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0) + (size_t)p.Cy * sizeof(float);
     if (smem > 227 * 1024) return 0;
     long units = (long)p.oN * P.Ty * P.Tx * P.Tzg * P.n_ntiles;
     int grid = (int)(units < (long)num_sms() ? units : (long)num_sms());

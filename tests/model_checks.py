@@ -89,7 +89,9 @@ def check_spark(name='tiny', batch=2, seed=3, verbose=True):
     assert res['loss_rel'] < 5e-3 and res['rec_rel'] < (6e-2 if wide else 3e-2) and res['per_patch_rel'] < 2e-2, res
     # 'tiny' pools its deepest norms over 6 voxels (3 visible patches x 2 samples): statistics that thin are noise-
     # dominated in any 16-bit implementation, so only a coarse bound applies there
-    deep, cmin = (1.0, 0.7) if name in ('tiny', 'L32', 'S_aniso') else (0.6, 0.9)
+    # elsewhere: measured cos 0.90-0.95 on the noisiest deep encoder tensor with +-0.02 run to run (the fp32 atomics of the
+    # split-K weight gradients and Σ/Σ² epilogues commit in a different order every launch), so the floor sits below that
+    deep, cmin = (1.0, 0.7) if name in ('tiny', 'L32', 'S_aniso') else (0.6, 0.85)
     scale = 2.0 if wide else 1.0
     bad = {n: v for n, v in worst.items()
            if v[0] > (deep if grad_bound(n) >= 0.6 else scale * grad_bound(n)) or v[1] < cmin}
