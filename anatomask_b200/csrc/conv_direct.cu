@@ -200,7 +200,7 @@ extern "C" int amb_conv(const amb_conv_args* a) {
         // halo-plane kernel (v2) for dense 3x3x3 s1; the per-tap kernel (v1) everywhere else, and wherever the
         // active-patch work-list lets it skip masked tiles outright (patch edge >= 8 at the output resolution)
         const bool list_pays = a->active_list != nullptr && p.lgPv >= 3;
-        if (a->impl != AMB_IMPL_TCGEN05_V1 && !list_pays) {
+        if (a->impl != AMB_IMPL_TCGEN05_V1 && (!list_pays || p.lgPv >= 4)) {   // v3 takes the list itself at edge >= 16
             int r3 = igemm3_conv(p, a);          // halo planes + 4 interleaved tiles: narrow dense 3x3x3 layers
             if (r3 < 0) return r3;
             if (r3 == 1) return 0;

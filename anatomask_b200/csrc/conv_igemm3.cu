@@ -33,6 +33,8 @@ struct Igemm3Params {
     long sN, sD, sH, sW;
     const float* bias;
     const uint8_t* active;
+    const int* list;                     // active-patch work-list (patch edge >= 16 output voxels) or nullptr = dense
+    const int* count;
     double* stats;
     int oN, oD, oH, oW, Cy;
     int lgPv, fd, fh, fw;
@@ -48,6 +50,23 @@ struct Unit3 {
 
 __device__ __forceinline__ void v3_decode(const Igemm3Params& P, uint32_t u, Unit3& c) {
     c.nt = (int)(u % (uint32_t)P.n_ntiles); u /= (uint32_t)P.n_ntiles;
+    if (P.list) {
+        // visible patches only: a patch of edge Pv holds (Pv/16) x (Pv/8) x (Pv/4) units of 16 x 8 x 4 voxels
+        const uint32_t ly = (uint32_t)P.lgPv - 4u, lx = (uint32_t)P.lgPv - 3u, lz = (uint32_t)P.lgPv - 2u;
+        const uint32_t ix = u & ((1u << lx) - 1u); u >>= lx;
+        const uint32_t iy = u & ((1u << ly) - 1u); u >>= ly;
+        const uint32_t iz = u & ((1u << lz) - 1u); u >>= lz;
+        const uint32_t pid = (uint32_t)P.list[u];
+        const uint32_t L = (uint32_t)(P.fd * P.fh * P.fw), hw = (uint32_t)(P.fh * P.fw);
+        const uint32_t n = pid / L, l = pid - n * L;
+        const uint32_t pz = l / hw, r2 = l - pz * hw;
+        const uint32_t py = r2 / (uint32_t)P.fw, px = r2 - py * (uint32_t)P.fw;
+        c.n = (int)n;
+        c.z0 = (int)((pz << P.lgPv) + iz * V3_T);
+        c.y0 = (int)((py << P.lgPv) + iy * 16u);
+        c.x0 = (int)((px << P.lgPv) + ix * 8u);
+        return;
+    }
     c.z0 = (int)(u % (uint32_t)P.Tzg) * V3_T; u /= (uint32_t)P.Tzg;
     c.x0 = (int)(u % (uint32_t)P.Tx) * 8; u /= (uint32_t)P.Tx;
     c.y0 = (int)(u % (uint32_t)P.Ty) * 16;
@@ -102,7 +121,8 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t nunits = (uint32_t)(P.oN * P.Ty * P.Tx * P.Tzg * P.n_ntiles);
+    const uint32_t nunits = P.list ? ((uint32_t)(*P.count) << (3 * P.lgPv - 9)) * (uint32_t)P.n_ntiles
+                                   : (uint32_t)(P.oN * P.Ty * P.Tx * P.Tzg * P.n_ntiles);
     const uint32_t kchunks = (uint32_t)P.kchunks, NT = (uint32_t)P.NT, b_bytes = P.b_bytes;
     const uint32_t a_ring_u32 = smem_u32(a_ring), b_ring_u32 = smem_u32(b_ring);
     const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty);
@@ -313,6 +333,10 @@ int igemm3_conv(const Plan& p, const amb_conv_args* a) {
     if (!((a->op == AMB_OP_CONV || a->op == AMB_OP_CONV_DGRAD) && a->k == 3 && a->stride == 1)) return 0;
     if (p.Cx % 32 != 0 || p.Cy % 16 != 0 || p.n_taps != 27 || p.n_in_views != 1 || p.n_groups != 1) return 0;
     if (p.oH < 16 || p.oW < 8 || p.oD < V3_T) return 0;
+    // active-patch work-list: usable when a patch holds whole 16 x 8 x 4 units; with a finer grid the per-tap kernel's list
+    // (2 x 8 x 8 tiles) still pays, so leave those layers to it
+    const bool use_list = a->active_list != nullptr && p.lgPv >= 4 && !getenv("AMB_V3_NO_LIST");
+    if (a->active_list != nullptr && p.lgPv >= 3 && !use_list) return 0;
     int NT = 0;
     for (int nt = 64; nt >= 16; nt -= 16) if (p.Cy % nt == 0) { NT = nt; break; }
     if (NT == 0 || p.Cy / NT > 1) return 0;          // one N tile: wider layers are already tensor-bound in the per-tap kernel
@@ -324,6 +348,8 @@ int igemm3_conv(const Plan& p, const amb_conv_args* a) {
     const View& ov = p.out_views[0];
     P.sN = ov.sN; P.sD = ov.sD; P.sH = ov.sH; P.sW = ov.sW;
     P.bias = a->bias; P.active = a->active; P.stats = a->stats;
+    P.list = use_list ? a->active_list : nullptr;
+    P.count = use_list ? a->active_count : nullptr;
     P.oN = p.oN; P.oD = p.oD; P.oH = p.oH; P.oW = p.oW; P.Cy = p.Cy;
     P.lgPv = p.lgPv; P.fd = p.fd; P.fh = p.fh; P.fw = p.fw;
     P.Ty = ceil_div(p.oH, 16); P.Tx = ceil_div(p.oW, 8); P.Tzg = ceil_div(p.oD, V3_T);
@@ -383,7 +409,8 @@ int igemm3_conv(const Plan& p, const amb_conv_args* a) {
     size_t smem = (size_t)P.a_slots * V3_PLANE_BYTES + (size_t)V3_B_SLOTS * P.b_bytes + 1024 + 512 +
                   (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0) + (size_t)p.Cy * sizeof(float);
     if (smem > 227 * 1024) return 0;
-    long units = (long)p.oN * P.Ty * P.Tx * P.Tzg * P.n_ntiles;
+    long units = use_list ? ((long)p.oN * p.fd * p.fh * p.fw << (3 * p.lgPv - 9)) * P.n_ntiles
+                          : (long)p.oN * P.Ty * P.Tx * P.Tzg * P.n_ntiles;
     int grid = (int)(units < (long)num_sms() ? units : (long)num_sms());
     AMB_CUDA(cudaFuncSetAttribute(igemm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     igemm3_kernel<<<grid, 256, smem, (cudaStream_t)a->stream>>>(P);

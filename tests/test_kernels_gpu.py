@@ -55,7 +55,10 @@ def test_norm_family(kw):
     dict(Cin=32, Cout=32, S=32, impl=T, masked=True), dict(Cin=64, Cout=64, S=16, impl=T, masked=True),
     dict(Cin=128, Cout=128, S=8, impl=T, masked=True), dict(Cin=32, Cout=64, S=32, stride=2, impl=T, masked=True),
     dict(Cin=32, Cout=64, S=32, k=1, stride=2, impl=T, masked=True),
-    dict(Cin=64, Cout=64, S=32, impl=T, masked=True, f=8)])
+    dict(Cin=64, Cout=64, S=32, impl=T, masked=True, f=8),
+    # halo-plane kernel walking the active-patch list (patch edge 16 and 32 voxels)
+    dict(Cin=64, Cout=64, S=32, impl=T, masked=True, f=2), dict(Cin=64, Cout=32, S=64, N=1, impl=T, masked=True, f=4),
+    dict(Cin=32, Cout=32, S=64, N=1, impl=T, masked=True, f=2)])
 def test_conv_fwd_dgrad_wgrad(kw):
     kc.check_conv(**kw)
 
