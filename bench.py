@@ -236,6 +236,10 @@ def run_ours(args):
         for i, (k, f, ms) in enumerate(rows):
             print(f'#LAUNCH {i:3d} {k:12s} {f / 1e9:9.1f} GF {ms:7.3f} ms {f / ms / 1e9:8.1f} TF/s', file=sys.stderr)
     peaks, peak_src = _peaks()
+    try:        # DRAM bytes of the family's dominant launch shape from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_ncu_traffic.json')))
+    except (OSError, ValueError):
+        traffic = {}
     peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1400.0)))
     igemm = [v for k, v in fam.items() if not k.endswith('wgrad')]
     fl, ms_k, n_k = sum(v[0] for v in igemm), sum(v[1] for v in igemm), sum(v[2] for v in igemm)
@@ -244,10 +248,11 @@ def run_ours(args):
     conv_fl = sum(v[0] for v in fam.values())
     roofline = {'bound': 'tensor', 'kernel': 'igemm_kernel (tcgen05 implicit-GEMM conv fwd/dgrad/convT family)',
                 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                'peak_source': f'{peak_src} bf16_tflops_sustained (kernel timed inside a long step)', 'traffic': None,
+                'peak_source': f'{peak_src} bf16_tflops_sustained (kernel timed inside a long step)',
+                'traffic': traffic.get('dram_bytes_per_launch'), 'traffic_note': traffic or None,
                 'launches_timed': n_k, 'avg_launch_ms': ms_k / max(1, n_k),
                 'all_conv_kernels': {'achieved': conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0,
-                                     'share_of_step': conv_ms / ms_eager_total, 'eager_pass_ms_per_step': ms_eager_total / args.steps,
+                                     'share_of_step': conv_ms / ms_total, 'eager_pass_ms_per_step': ms_eager_total / args.steps,
                                      'per_family_tflops': {k: v[0] / (v[1] * 1e-3) / 1e12 for k, v in fam.items() if v[1] > 0}},
                 'algorithmic_flops_per_step': conv_fl / args.steps}
     # ---- timed region 2: end to end through the public API, host buffers -----------------------------------
