@@ -46,6 +46,7 @@ _SIGNATURES = {
     'amb_ndhwc_bf16_to_ncdhw_f32': (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     'amb_pack_weight': (i32, [vp, vp, i32, i32, i32, i64, i64, i64, vp]),
     'amb_unpack_wgrad': (i32, [vp, vp, i32, i32, i32, i64, i64, i64, vp]),
+    'amb_pack_weights_batched': (i32, [vp, i32, i32, vp]),
     'amb_conv': (i32, [C.POINTER(ConvArgs)]),
     'amb_conv_wgrad': (i32, [C.POINTER(WgradArgs)]),
     'amb_stem_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),

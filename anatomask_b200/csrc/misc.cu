@@ -770,11 +770,9 @@ extern "C" int amb_adamw_step(float* p, const float* g, float* m, float* v, long
 // element-wise kernels above read with a stride of T floats and ran at ~1/4 of HBM speed.
 //   PACK  : fp32 parameters → bf16 packed          !PACK : fp32 packed gradient → fp32 parameter layout
 template <bool PACK, bool BFAST>
-__global__ void __launch_bounds__(256) repack_tiled_kernel(const float* __restrict__ src, void* __restrict__ dst_, int T,
-                                                           int A, int B, int tiles_b, int tchunks) {
-    __shared__ float tile[256][33];
+__device__ __forceinline__ void repack_tile(float (*tile)[33], const float* __restrict__ src, void* __restrict__ dst_, int T,
+                                            int A, int B, int tiles_b, int tchunks, uint32_t blk) {
     constexpr uint32_t TA = BFAST ? 4 : 16, TB = BFAST ? 64 : 16;     // powers of two: index splits are shifts
-    uint32_t blk = blockIdx.x;
     const int tcx = (int)(blk % (uint32_t)tchunks); blk /= (uint32_t)tchunks;
     const int a0 = (int)(blk / (uint32_t)tiles_b) * (int)TA, b0 = (int)(blk % (uint32_t)tiles_b) * (int)TB;
     const int t0 = tcx * 32;
@@ -831,6 +829,32 @@ __global__ void __launch_bounds__(256) repack_tiled_kernel(const float* __restri
     }
 }
 
+template <bool PACK, bool BFAST>
+__global__ void __launch_bounds__(256) repack_tiled_kernel(const float* __restrict__ src, void* __restrict__ dst, int T,
+                                                           int A, int B, int tiles_b, int tchunks) {
+    __shared__ float tile[256][33];
+    repack_tile<PACK, BFAST>(tile, src, dst, T, A, B, tiles_b, tchunks, blockIdx.x);
+}
+
+// every conv weight of a step packed by ONE launch: block → job by binary search over the jobs' first tile
+__global__ void __launch_bounds__(256) repack_batched_kernel(const amb_pack_job* __restrict__ jobs, int n_jobs) {
+    __shared__ float tile[256][33];
+    __shared__ int s_job;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = n_jobs - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (jobs[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+        }
+        s_job = lo;
+    }
+    __syncthreads();
+    const amb_pack_job J = jobs[s_job];
+    const uint32_t blk = blockIdx.x - (uint32_t)J.tile_begin;
+    if (J.b_fast) repack_tile<true, true>(tile, J.src, J.dst, J.T, J.A, J.B, J.tiles_b, J.tchunks, blk);
+    else repack_tile<true, false>(tile, J.src, J.dst, J.T, J.A, J.B, J.tiles_b, J.tchunks, blk);
+}
+
 // 1: b is the fast parameter axis, 0: a is, −1: layout not covered by the tiled kernel
 static int repack_case(int T, int A, int B, long st, long sa, long sb) {
     if (st != 1 || (B & 1)) return -1;
@@ -857,6 +881,13 @@ extern "C" int amb_pack_weight(const float* src, void* dst, int T, int A, int B,
     else
         pack_weight_kernel<<<grid_cap((long)T * A * B, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, T, A, B,
                                                                                                st, sa, sb);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_pack_weights_batched(const amb_pack_job* jobs_dev, int n_jobs, int total_tiles, void* stream) {
+    AMB_CHECK(jobs_dev != nullptr && n_jobs > 0 && total_tiles > 0, AMB_ERR_ARG, "amb_pack_weights_batched: empty job table");
+    repack_batched_kernel<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(jobs_dev, n_jobs);
     AMB_LAUNCH_CHECK();
     return 0;
 }

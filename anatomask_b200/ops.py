@@ -158,10 +158,64 @@ def to_ncdhw_f32(xi: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------------
 # convolutions
 # ----------------------------------------------------------------------------------------------------------------
+# Engine mode: the packed bf16 copies of ALL conv weights are refreshed by one launch at the start of the step
+# (PackPlan.run) and ConvFn looks them up here; outside a step (PACK_CACHE is None) every call packs its own weight.
+# PACK_RECORD collects the pack calls of one eager step so that the engine can build the plan without knowing the modules.
+PACK_CACHE = None
+PACK_RECORD = None
+
+
 def _pack(w: torch.Tensor, T: int, A: int, B: int, st: int, sa: int, sb: int) -> torch.Tensor:
+    key = (w.data_ptr(), T, A, B, sa, sb)
+    if PACK_CACHE is not None:
+        hit = PACK_CACHE.get(key)
+        if hit is not None:
+            return hit
     out = torch.empty((T, A, B), dtype=bf16, device=w.device)
     L.call('amb_pack_weight', _p(w), _p(out), T, A, B, st, sa, sb, _stream())
+    if PACK_RECORD is not None and st == 1:
+        PACK_RECORD.append((key, w))
     return out
+
+
+class PackPlan:
+    """One-launch packing of every conv weight a step uses (amb_pack_weights_batched).  Built from the (key, weight)
+    pairs recorded during one eager step; the weights are views of the parameter arenas, so their addresses are stable."""
+
+    def __init__(self, record):
+        import numpy as np
+        seen, jobs, self.cache, self._keep = set(), [], {}, []
+        tile = 0
+        for key, w in record:
+            if key in seen:
+                continue
+            ptr, T, A, B, sa, sb = key
+            if sb == T and sa == B * T:
+                b_fast = 1
+            elif sa == T and sb == A * T:
+                b_fast = 0
+            else:
+                continue                                   # layout outside the tiled kernel: stays a per-call pack
+            seen.add(key)
+            ta, tb = (4, 64) if b_fast else (16, 16)
+            tiles_a, tiles_b, tchunks = -(-A // ta), -(-B // tb), -(-T // 32)
+            out = torch.empty((T, A, B), dtype=bf16, device=w.device)
+            jobs.append((ptr, out.data_ptr(), T, A, B, b_fast, tile, tiles_b, tchunks, 0))
+            tile += tiles_a * tiles_b * tchunks
+            self.cache[key] = out
+            self._keep.append(w)
+        self.n_jobs, self.total_tiles = len(jobs), tile
+        dt = np.dtype([('src', np.uint64), ('dst', np.uint64), ('T', np.int32), ('A', np.int32), ('B', np.int32),
+                       ('b_fast', np.int32), ('tile_begin', np.int32), ('tiles_b', np.int32), ('tchunks', np.int32),
+                       ('pad', np.int32)])
+        assert dt.itemsize == 48
+        table = np.array(jobs, dtype=dt)
+        dev = record[0][1].device if record else 'cuda'
+        self.table = torch.from_numpy(table.view(np.uint8).copy()).to(dev) if jobs else None
+
+    def run(self):
+        if self.table is not None:
+            L.call('amb_pack_weights_batched', _p(self.table), self.n_jobs, self.total_tiles, _stream())
 
 
 def _conv_call(op, impl, dims, Cin, Cout, k, stride, x, y, w, bias=None, m: Optional[MaskCtx] = None, sparse=False,

@@ -185,6 +185,23 @@ class PretrainEngine:
         B = inp.shape[0]
         m = self.model
         Lp = m.fmap_h * m.fmap_w * m.fmap_d
+        # bf16 operand copies of every conv weight (student forward + dgrad forms, teacher forward form): one launch per
+        # step once the first step has recorded which packs the modules ask for
+        plan = getattr(self, '_pack_plan', None)
+        if plan is None:
+            ops.PACK_RECORD = []
+        else:
+            plan.run()
+            ops.PACK_CACHE = plan.cache
+        try:
+            return self._device_front_body(inp, len_loss_epoch, B, m, Lp)
+        finally:
+            if plan is None and ops.PACK_RECORD:
+                self._pack_plan = ops.PackPlan(ops.PACK_RECORD)
+            ops.PACK_RECORD = None
+            ops.PACK_CACHE = None
+
+    def _device_front_body(self, inp, len_loss_epoch, B, m, Lp):
         self.step_counter.add_(1)
         zeros = torch.zeros(B, Lp, dtype=torch.float32, device=inp.device)
         _, mk = ops.hard_mask(zeros, 0, m.len_keep, seed=0xA11CE, offset=0, offset_dev=self.step_counter)
