@@ -158,6 +158,22 @@ def to_ncdhw_f32(xi: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------------
 # convolutions
 # ----------------------------------------------------------------------------------------------------------------
+# Engine mode: the many small zero-initialised accumulators of a step (Σ/Σ² in fp64, bias / γ / β gradient sums) are carved
+# out of one pool that the engine clears with a single memset at the start of the step, instead of ~100 fill launches.
+ZERO_POOL = None          # {'buf': uint8 tensor, 'off': int} while a step runs
+
+
+def _zeros_small(numel: int, dtype, device) -> torch.Tensor:
+    pool = ZERO_POOL
+    if pool is not None and pool['buf'].device == device:
+        nbytes = (numel * torch.empty((), dtype=dtype).element_size() + 15) & ~15
+        off = pool['off']
+        if off + nbytes <= pool['buf'].numel():
+            pool['off'] = off + nbytes
+            return pool['buf'][off:off + nbytes].view(dtype)[:numel]
+    return torch.zeros(numel, dtype=dtype, device=device)
+
+
 # Engine mode: the packed bf16 copies of ALL conv weights are refreshed by one launch at the start of the step
 # (PackPlan.run) and ConvFn looks them up here; outside a step (PACK_CACHE is None) every call packs its own weight.
 # PACK_RECORD collects the pack calls of one eager step so that the engine can build the plan without knowing the modules.
@@ -233,7 +249,7 @@ def _conv_call(op, impl, dims, Cin, Cout, k, stride, x, y, w, bias=None, m: Opti
 def column_sums(x: torch.Tensor, m: Optional[MaskCtx]) -> torch.Tensor:
     """Σ over voxels per channel (fp32) — bias gradients."""
     Cc = x.shape[-1]
-    sums = torch.zeros(2 * Cc, dtype=torch.float64, device=x.device)
+    sums = _zeros_small(2 * Cc, torch.float64, x.device)
     g = m.geo(x, True) if m is not None else dense_geo(x)
     L.call('amb_norm_stats', C.byref(g), _p(x), _p(sums), _stream())
     return sums[:Cc].float()
@@ -366,7 +382,7 @@ def fused_stats_ok(cin: int, cout: int) -> bool:
 
 def new_stats(channels: int, device) -> torch.Tensor:
     """(Σy[C], Σy²[C], n) accumulator handed to a conv (fused epilogue) and then to the norm that follows it."""
-    return torch.zeros(2 * channels + 1, dtype=torch.float64, device=device)
+    return _zeros_small(2 * channels + 1, torch.float64, torch.device(device))
 
 
 def conv3d(x, weight, bias=None, k=3, stride=1, m: Optional[MaskCtx] = None, impl=L.IMPL_AUTO, stats=None,
@@ -454,7 +470,7 @@ class NormFn(torch.autograd.Function):
         sparse = m is not None
         g = m.geo(x, True) if sparse else dense_geo(x)
         if sums is None:            # not produced by the conv epilogue: one read pass over the visited voxels
-            sums = torch.zeros(2 * Cc + 1, dtype=torch.float64, device=dev)
+            sums = _zeros_small(2 * Cc + 1, torch.float64, dev)
             L.call('amb_norm_stats', C.byref(g), _p(x), _p(sums), _stream())
         ntot = None
         if group is not None:
@@ -488,7 +504,7 @@ class NormFn(torch.autograd.Function):
         sparse = m is not None
         g = m.geo(x, True) if sparse else dense_geo(x)
         scale, shift, saved = ss[:Cc], ss[Cc:2 * Cc], ss[2 * Cc:]
-        sums = torch.zeros(3 * Cc, dtype=torch.float64, device=dev)
+        sums = _zeros_small(3 * Cc, torch.float64, dev)
         L.call('amb_norm_bwd_reduce', C.byref(g), _p(dout), _p(x), _p(residual), _p(scale), _p(shift), _p(saved), act,
                int(fill), _p(sums), _p(sums[2 * Cc:]) if fill else C.c_void_p(0), _stream())
         gb = torch.empty(2 * Cc, dtype=torch.float32, device=dev)

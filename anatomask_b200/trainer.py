@@ -193,9 +193,14 @@ class PretrainEngine:
         else:
             plan.run()
             ops.PACK_CACHE = plan.cache
+        if getattr(self, '_zero_pool', None) is None:
+            self._zero_pool = torch.empty(4 << 20, dtype=torch.uint8, device=inp.device)
+        self._zero_pool.zero_()                    # every small accumulator of the step (ops._zeros_small): one memset
+        ops.ZERO_POOL = {'buf': self._zero_pool, 'off': 0}
         try:
             return self._device_front_body(inp, len_loss_epoch, B, m, Lp)
         finally:
+            ops.ZERO_POOL = None
             if plan is None and ops.PACK_RECORD:
                 self._pack_plan = ops.PackPlan(ops.PACK_RECORD)
             ops.PACK_RECORD = None
@@ -241,6 +246,17 @@ class PretrainEngine:
         out = self._device_front(inp, len_loss_epoch)
         self._allreduce_grads()
         self._device_tail()
+        return out
+
+    def device_step(self, inp: torch.Tensor, epoch: int = 0):
+        """The launch sequence graph_step() captures, issued eagerly (profilers, debugging): device RNG masks, device-side
+        scalars, batched weight packing — no host synchronisation."""
+        self.model.train()
+        self.teacher.mask_rng = 'device'
+        self.teacher.rng_counter = self.step_counter
+        self._set_hyper(epoch)
+        out = self._device_step(inp, epoch)
+        self.t += 1
         return out
 
     def _state_snapshot(self):

@@ -190,7 +190,7 @@ def run_ours(args):
             use_graph, graph_err = False, f'{type(e).__name__}: {e}'[:200]
             torch.cuda.synchronize()
     _mark(f'graph={use_graph} err={graph_err}')
-    run = (lambda x: eng.graph_step(x, epoch)) if use_graph else (lambda x: eng.step(x, epoch))
+    run = (lambda x: eng.graph_step(x, epoch)) if use_graph else (lambda x: eng.device_step(x, epoch))
     for _ in range(args.warmup):
         run(inp)
     barrier()
@@ -218,10 +218,7 @@ def run_ours(args):
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
     for _ in range(args.steps):
-        if use_graph:
-            eng._device_step(inp, epoch)      # the launch sequence the graph captured (batched weight pack, device scalars)
-        else:
-            eng.step(inp, epoch)
+        eng.device_step(inp, epoch)           # the launch sequence the graph captured (batched weight pack, device scalars)
     p1.record()
     barrier()
     ms_eager_total = p0.elapsed_time(p1)
