@@ -102,3 +102,40 @@ def test_checkpoint_keys_feed_the_reference_finetune_loader(tmp_path):
                 pool_op_kernel_sizes=[[2, 2, 2]] * 4 + [[1, 1, 1]], conv_kernel_sizes=[[3, 3, 3]] * 6)
     missing, unexpected = ft.load_state_dict(enc, strict=False)
     assert not unexpected and not missing
+
+
+def test_struct_layouts_match_the_c_header(tmp_path):
+    """ctypes mirrors (and the numpy job table of ops.PackPlan) against sizeof / offsetof taken from include/*.h by gcc."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    import numpy as np
+    from anatomask_b200 import _lib as L
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {'amb_conv_args': L.ConvArgs, 'amb_wgrad_args': L.WgradArgs, 'amb_geo': L.Geo}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include <stdint.h>', '#include "anatomask_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    job_fields = ['src', 'dst', 'T', 'A', 'B', 'b_fast', 'tile_begin', 'tiles_b', 'tchunks']
+    lines.append('  printf("amb_pack_job %zu", sizeof(amb_pack_job));')
+    lines += [f'  printf(" %zu", offsetof(amb_pack_job, {f}));' for f in job_fields]
+    lines += ['  printf("\\n");', '  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run([gcc, '-I', os.path.join(root, 'include'), str(src), '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    got = {ln.split()[0]: [int(v) for v in ln.split()[1:]] for ln in out}
+    for cname, cls in structs.items():
+        want = [C.sizeof(cls)] + [getattr(cls, f).offset for f, _ in cls._fields_]
+        assert got[cname] == want, (cname, got[cname], want)
+    dt = np.dtype([('src', np.uint64), ('dst', np.uint64), ('T', np.int32), ('A', np.int32), ('B', np.int32),
+                   ('b_fast', np.int32), ('tile_begin', np.int32), ('tiles_b', np.int32), ('tchunks', np.int32),
+                   ('pad', np.int32)])
+    assert got['amb_pack_job'] == [dt.itemsize] + [dt.fields[f][1] for f in job_fields]
