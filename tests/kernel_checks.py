@@ -43,7 +43,8 @@ def _up(mask, size):
     return mask.repeat_interleave(r, 2).repeat_interleave(r, 3).repeat_interleave(r, 4)
 
 
-def check_conv(Cin=64, Cout=64, k=3, stride=1, S=16, N=2, impl=2, masked=False, f=2, bias=True, seed=0, tol=1.5e-2):
+def check_conv(Cin=64, Cout=64, k=3, stride=1, S=16, N=2, impl=2, masked=False, f=2, bias=True, seed=0, tol=1.5e-2,
+               keep=0.4):
     """conv fwd + dgrad + wgrad (+bias grad) vs fp32 torch on the same bf16-rounded operands."""
     from anatomask_b200 import ops
     dev = _dev()
@@ -51,7 +52,7 @@ def check_conv(Cin=64, Cout=64, k=3, stride=1, S=16, N=2, impl=2, masked=False, 
     x = torch.randn(N, Cin, S, S, S, generator=g).to(bf16)
     w = (torch.randn(Cout, Cin, k, k, k, generator=g) / (Cin * k ** 3) ** 0.5)
     b = torch.randn(Cout, generator=g) * 0.1 if bias else None
-    mask = _rand_mask(N, f, seed=seed + 1) if masked else None
+    mask = _rand_mask(N, f, keep=keep, seed=seed + 1) if masked else None
     if masked:
         x = x * _up(mask, S).to(bf16)
     wq = w.to(bf16).float()

@@ -72,6 +72,15 @@ def test_conv_transpose(kw):
     kc.check_convT(**kw)
 
 
+@pytest.mark.parametrize('keep', [1.0, 0.7, 0.1])
+@pytest.mark.parametrize('kw', [dict(Cin=32, Cout=32, S=32, f=2), dict(Cin=64, Cout=64, S=32, f=4),
+                                dict(Cin=32, Cout=64, S=32, f=2, stride=2)])
+def test_masked_conv_over_mask_ratios(kw, keep):
+    """single masked layers from fully visible to 10 % visible (work-list kernels: igemm3 at patch edge 16,
+    per-tap kernel at edge 8, stride 2)"""
+    kc.check_conv(impl=T, masked=True, keep=keep, **kw)
+
+
 @pytest.mark.parametrize('kw', [dict(), dict(Cin=64, Cout=64, S=32)])
 def test_conv_epilogue_statistics(kw):
     kc.check_conv_stats(**kw)
