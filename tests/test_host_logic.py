@@ -139,3 +139,35 @@ def test_struct_layouts_match_the_c_header(tmp_path):
                    ('b_fast', np.int32), ('tile_begin', np.int32), ('tiles_b', np.int32), ('tchunks', np.int32),
                    ('pad', np.int32)])
     assert got['amb_pack_job'] == [dt.itemsize] + [dt.fields[f][1] for f in job_fields]
+
+
+def test_pack_plan_job_table():
+    """ops.PackPlan: duplicate requests collapse, layouts outside the tiled kernel are left to the per-call pack, tile
+    ranges are contiguous — checked on CPU tensors (the launch itself is GPU-only)."""
+    import numpy as np
+    from anatomask_b200 import ops
+    w1 = torch.zeros(64, 32, 27)          # conv (Cout, Cin, taps)
+    w2 = torch.zeros(16, 24, 64)          # ConvTranspose (Cin, Cout, taps)
+    w3 = torch.zeros(8, 8, 27)
+    rec = []
+    def ask(w, T, A, B, sa, sb):
+        rec.append(((w.data_ptr(), T, A, B, sa, sb), w))
+    ask(w1, 27, 64, 32, 32 * 27, 27)      # forward form  [t][co][ci]: b (= ci) is the fast parameter axis
+    ask(w1, 27, 32, 64, 27, 32 * 27)      # dgrad form    [t][ci][co]: a (= ci) is the fast axis
+    ask(w1, 27, 64, 32, 32 * 27, 27)      # asked again by the next step: same key
+    ask(w2, 64, 24, 16, 64, 24 * 64)      # ConvTranspose forward [t][co][ci] from (ci, co, t)
+    ask(w3, 27, 8, 8, 5, 7)               # strides the tiled kernel does not cover
+    plan = ops.PackPlan(rec)
+    assert plan.n_jobs == 3 and len(plan.cache) == 3
+    dt = np.dtype([('src', np.uint64), ('dst', np.uint64), ('T', np.int32), ('A', np.int32), ('B', np.int32),
+                   ('b_fast', np.int32), ('tile_begin', np.int32), ('tiles_b', np.int32), ('tchunks', np.int32),
+                   ('pad', np.int32)])
+    tab = plan.table.numpy().view(dt)
+    assert list(tab['b_fast']) == [1, 0, 0]
+    # tiles: 4x64 positions (b fast) or 16x16, x ceil(T / 32) tap chunks
+    tiles = [16 * 1 * 1, 2 * 4 * 1, 2 * 1 * 2]
+    assert list(tab['tile_begin']) == [0, tiles[0], tiles[0] + tiles[1]] and plan.total_tiles == sum(tiles)
+    assert list(tab['tiles_b']) == [1, 4, 1] and list(tab['tchunks']) == [1, 1, 2]
+    for (key, w), job in zip([rec[0], rec[1], rec[3]], tab):
+        assert int(job['src']) == w.data_ptr() and int(job['dst']) == plan.cache[key].data_ptr()
+        assert tuple(plan.cache[key].shape) == (key[1], key[2], key[3]) and plan.cache[key].dtype == torch.bfloat16
