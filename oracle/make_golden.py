@@ -131,5 +131,6 @@ if __name__ == '__main__':
     golden_spark('S64', rp.CONFIGS['S64'], batch=2, seed=5)      # BASELINE config 1
     golden_spark('S_aniso', rp.CONFIGS['S_aniso'], batch=2, seed=4)   # non-cubic, odd mask grid (3,5,2)
     golden_spark('L32', rp.CONFIGS['L32'], batch=2, seed=2)      # STUNet-L: depth 2 (identity-shortcut blocks), width 1024
+    golden_spark('B64', rp.CONFIGS['B64'], batch=2, seed=5)      # STUNet-B (the bench model) at 64^3, decoder width 512
     golden_anatomask('tiny', rp.CONFIGS['tiny'], batch=2, seed=7, epochs=20, epoch_list=[0, 9, 18])
     golden_anatomask('S64', rp.CONFIGS['S64'], batch=2, seed=9, epochs=1000, epoch_list=[0, 500, 998])

@@ -21,7 +21,7 @@ def _check_digest(t, d, rtol, atol_scale=1e-6):
     assert abs(float(t.norm()) - d['norm']) <= rtol * d['norm'] + 1e-9
 
 
-@pytest.mark.parametrize('name', ['tiny', 'S64', 'S_aniso', 'L32'])
+@pytest.mark.parametrize('name', ['tiny', 'S64', 'S_aniso', 'L32', 'B64'])
 def test_spark_forward_backward_matches_reference(golden_dir, name):
     g = _load(golden_dir, f'spark_{name}.pt')
     cfg = rp.Cfg(**g['cfg'])
