@@ -188,6 +188,10 @@ class PretrainEngine:
         # bf16 operand copies of every conv weight (student forward + dgrad forms, teacher forward form): one launch per
         # step once the first step has recorded which packs the modules ask for
         plan = getattr(self, '_pack_plan', None)
+        tag = (self.arena.flat.data_ptr(), self.tarena.flat.data_ptr())
+        if plan is not None and getattr(self, '_pack_plan_tag', None) != tag:
+            plan = self._pack_plan = None              # the arenas were rebuilt: recorded weight addresses are stale
+        self._pack_plan_tag = tag
         if plan is None:
             ops.PACK_RECORD = []
         else:
