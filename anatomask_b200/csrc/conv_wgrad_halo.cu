@@ -51,16 +51,34 @@ struct WgradHaloParams {
     int wide, mslabs, a_slabs, b_slots;   // wide: Cy >= 128, a unit is one tap x one 128-channel slab of dY (two 64-channel atoms)
     uint32_t plane_slab_bytes;
     int oN, oD, oH, oW, Ty, Tx;
-    uint32_t n_steps;                // columns × oD
+    uint32_t n_steps;                // columns × oD (dense walk)
     int ksplit;
+    const int* list;                 // active-patch work-list: columns are enumerated inside visible patches only and a
+    const int* count;                // column is one patch deep (2^lgPv z steps + 2 halo planes); nullptr = dense
+    int lgPv, fd, fh, fw;
     float* dw;
 };
 
 struct WhCol {
-    int n0, y0, x0;
+    int n0, y0, x0, z0;
 };
 __device__ __forceinline__ WhCol wh_column(const WgradHaloParams& P, uint32_t col) {
     WhCol c;
+    if (P.list) {
+        const uint32_t lt = (uint32_t)P.lgPv - 3u;                 // log2 of 8-voxel tiles per patch edge
+        const uint32_t tx = col & ((1u << lt) - 1u), ty = (col >> lt) & ((1u << lt) - 1u);
+        const uint32_t pid = (uint32_t)P.list[col >> (2u * lt)];
+        const uint32_t L = (uint32_t)(P.fd * P.fh * P.fw), hw = (uint32_t)(P.fh * P.fw);
+        const uint32_t n = pid / L, l = pid - n * L;
+        const uint32_t pz = l / hw, r2 = l - pz * hw;
+        const uint32_t py = r2 / (uint32_t)P.fw, px = r2 - py * (uint32_t)P.fw;
+        c.n0 = (int)n;
+        c.z0 = (int)(pz << P.lgPv);
+        c.y0 = (int)((py << P.lgPv) + ty * 8u);
+        c.x0 = (int)((px << P.lgPv) + tx * 8u);
+        return c;
+    }
+    c.z0 = 0;
     c.x0 = (int)(col % (uint32_t)P.Tx) * 8; col /= (uint32_t)P.Tx;
     c.y0 = (int)(col % (uint32_t)P.Ty) * 8;
     c.n0 = (int)(col / (uint32_t)P.Ty);
@@ -104,9 +122,11 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
     job %= (uint32_t)P.n_batches;
     const int unit_begin = P.batch_unit_begin[job], unit_count = P.batch_unit_count[job];
     const CUtensorMap* a_map = &P.a_maps[P.batch_class[job]];
-    const uint32_t s_begin = (uint32_t)((unsigned long long)P.n_steps * ks / (uint32_t)P.ksplit);
-    const uint32_t s_end = (uint32_t)((unsigned long long)P.n_steps * (ks + 1) / (uint32_t)P.ksplit);
-    const uint32_t oD = (uint32_t)P.oD;
+    // oD below = z steps per column: the whole depth when dense, one patch edge with the work-list
+    const uint32_t n_steps = P.list ? ((uint32_t)(*P.count) << (3 * P.lgPv - 6)) : P.n_steps;
+    const uint32_t s_begin = (uint32_t)((unsigned long long)n_steps * ks / (uint32_t)P.ksplit);
+    const uint32_t s_end = (uint32_t)((unsigned long long)n_steps * (ks + 1) / (uint32_t)P.ksplit);
+    const uint32_t oD = P.list ? (1u << P.lgPv) : (uint32_t)P.oD;
 
     if (warp == 0) {
         // dY planes: a segment [z, zend) of one column needs planes z−1 … zend (rows / planes outside the tensor are
@@ -124,7 +144,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
                     mbar_expect_tx(&a_full[slot], P.plane_bytes);
                     for (int j = 0; j < P.a_slabs; ++j)
                         tma_load_5d(a_ring + slot * P.plane_bytes + j * P.plane_slab_bytes, a_map, &a_full[slot],
-                                    mslab * 128 + j * 64, c.x0 - 1, c.y0 - 1, zp, c.n0);
+                                    mslab * 128 + j * 64, c.x0 - 1, c.y0 - 1, c.z0 + zp, c.n0);
                 }
                 __syncwarp();
                 if (++slot == A_SLOTS) { slot = 0; phase ^= 1u; }
@@ -145,7 +165,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
                     mbar_expect_tx(&b_full[slot], P.b_slab_bytes * (uint32_t)P.b_slabs);
                     for (int j = 0; j < P.b_slabs; ++j)
                         tma_load_5d(b_ring + slot * P.b_slot_bytes + j * P.b_slab_bytes, &P.b_map, &b_full[slot],
-                                    nchunk * P.NTw + j * P.nslabW, c.x0, c.y0, zp, c.n0);
+                                    nchunk * P.NTw + j * P.nslabW, c.x0, c.y0, c.z0 + zp, c.n0);
                 }
                 __syncwarp();
                 if (++slot == B_SLOTS) { slot = 0; phase ^= 1u; }
@@ -273,7 +293,11 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
 // returns 1 when handled, 0 when the shape is outside this kernel's scope, <0 on error
 int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a) {
     if (getenv("AMB_DISABLE_WH")) return 0;
-    if (a->active_list != nullptr) return 0;                       // sparse layers: the work-list kernel skips tiles
+    // sparse layers: this kernel can walk the active-patch list (a patch must hold whole 8x8 columns), parity-green, but
+    // opt-in (AMB_WH_LIST=1): measured no gain for the step (27.66 vs 27.54 ms) — the encoder weight gradients run on the
+    // side stream off the critical path and patch-deep columns pay 2 halo planes per 8-16 steps.  Default: per-tap kernel.
+    const bool use_list = a->active_list != nullptr && p.lgPv >= 3 && getenv("AMB_WH_LIST") != nullptr;
+    if (a->active_list != nullptr && !use_list) return 0;
     // a convolution (27 taps, one dY view) or a ConvTranspose k4 s2 (8 parity-class views of dY with 8 taps each)
     const bool is_conv = p.n_out_views == 1 && p.n_taps == 27;
     const bool is_convT = a->op == AMB_OP_CONVT && p.n_out_views == 8 && p.n_taps == 64 && !getenv("AMB_WH_NO_CONVT");
@@ -321,6 +345,9 @@ int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a) {
     P.oN = p.oN; P.oD = p.oD; P.oH = p.oH; P.oW = p.oW;
     P.Ty = p.oH / 8; P.Tx = p.oW / 8;
     P.dw = a->dw;
+    P.list = use_list ? a->active_list : nullptr;
+    P.count = use_list ? a->active_count : nullptr;
+    P.lgPv = p.lgPv; P.fd = p.fd; P.fh = p.fh; P.fw = p.fw;
     const char* ienv = getenv("AMB_WH_ISSUERS");
     P.issuers = (ienv && atoi(ienv) == 1) ? 1 : 2;
 
@@ -380,7 +407,7 @@ int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a) {
         if (int e = encode_view_map(&P.a_maps[v], a->dy, p.out_views[v], p.Cy, P.slabW, abox)) return e;
     if (int e = encode_view_map(&P.b_map, a->x, p.in_views[0], p.Cx, P.nslabW, bbox)) return e;
 
-    const long steps = (long)p.oN * P.Ty * P.Tx * p.oD;
+    const long steps = use_list ? ((long)p.oN * p.fd * p.fh * p.fw << (3 * p.lgPv - 6)) : (long)p.oN * P.Ty * P.Tx * p.oD;
     if (steps >= (1L << 31)) return 0;
     P.n_steps = (uint32_t)steps;
     const int base_jobs = P.mslabs * P.n_batches * P.n_nchunks;
