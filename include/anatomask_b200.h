@@ -65,7 +65,8 @@ int amb_ndhwc_bf16_to_ncdhw_f32(const void* src, float* dst, int N, int C, int D
 /* ---- weight packing: dst[t][a][b] (bf16) = src[t*st + a*sa + b*sb] (fp32); and the inverse for weight grads ---- */
 int amb_pack_weight(const float* src, void* dst, int T, int A, int B, long st, long sa, long sb, void* stream);
 int amb_unpack_wgrad(const float* src, float* dst, int T, int A, int B, long st, long sa, long sb, void* stream);
-/* All conv weights of a step in ONE launch (the reference re-reads its fp32 nn.Parameters every forward; here the bf16
+/* All conv weights of a step in ONE launch (the reference's nn.Conv3d / nn.ConvTranspose3d read their fp32 `weight`
+ * parameters in every forward — P/encoder3D.py:13, P/decoder3D.py:18-22, P/spark3D.py:82; here the bf16
  * operand copies are refreshed once per step).  A job packs one tensor whose taps are innermost (st == 1):
  * b_fast = 1: src[(a*B + b)*T + t], b_fast = 0: src[(b*A + a)*T + t]; tiles are 4x64 (b_fast) or 16x16 (a, b) positions
  * x 32 taps; tile_begin = first block of the job, tiles_b / tchunks = tiles along b / tap chunks.  The table lives in
