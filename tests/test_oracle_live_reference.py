@@ -1,0 +1,80 @@
+"""Oracle vs the LIVE reference modules (build container only: /root/reference is not on the GPU box, so these tests
+skip there).  Complements the committed golden fixtures with randomised cases: the hard-mask schedule and shuffles, the
+random mask, patchify and both per-patch losses are compared bit-for-bit / to fp32 round-off on fresh inputs every seed."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = '/root/reference/nnunetv2/training/nnUNetTrainer/variants/pretrain'
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present (GPU box)')
+
+sys.path.insert(0, ROOT)
+from oracle import reference_port as rp  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def ref_model():
+    """The unmodified reference AnatoMask.SparK for the 'tiny' config (oracle/make_golden.py:build_reference)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('make_golden', os.path.join(ROOT, 'oracle', 'make_golden.py'))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    with contextlib.redirect_stdout(io.StringIO()):
+        return mg.build_reference(rp.CONFIGS['tiny'], anatomask=True)
+
+
+@pytest.mark.parametrize('seed,epoch,epochs', [(0, 0, 20), (1, 3, 20), (2, 9, 20), (3, 18, 20), (4, 500, 1000), (5, 998, 1000)])
+def test_generate_mask_bit_exact_against_live_reference(ref_model, seed, epoch, epochs):
+    cfg = rp.CONFIGS['tiny']
+    B = 3
+    g = torch.Generator().manual_seed(seed)
+    mask1 = rp.random_mask(cfg, B, g)
+    loss_pred = torch.rand(B, cfg.L, generator=g) * mask1.logical_not().view(B, -1)     # zeros on visible patches
+    len_loss, _ = rp.hard_mask_lengths(cfg, epoch, epochs - 1)
+    np.random.seed(seed)
+    torch.manual_seed(seed)                       # the len_loss <= 0 branch draws torch.randn
+    want, _ = ref_model.generate_mask(loss_pred.clone(), guide=True, epoch=epoch, total_epoch=epochs - 1)
+    state_after_ref = np.random.get_state()[1].copy()
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    got = rp.generate_mask(cfg, loss_pred.clone(), epoch, epochs - 1)
+    assert torch.equal(got, want), (len_loss, int((got != want).sum()))
+    assert int(got.sum()) == B * cfg.len_keep
+    if len_loss > 0:                              # both consumed the numpy stream identically (two shuffles per sample)
+        assert np.array_equal(np.random.get_state()[1], state_after_ref)
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_patchify_and_losses_against_live_reference(ref_model, seed):
+    cfg = rp.CONFIGS['tiny']
+    B = 2
+    g = torch.Generator().manual_seed(100 + seed)
+    inp = torch.randn(B, cfg.in_ch, *cfg.input_size, generator=g)
+    rec = torch.randn(B, cfg.in_ch, *cfg.input_size, generator=g)
+    active = rp.random_mask(cfg, B, g)
+    assert torch.equal(rp.patchify(cfg, inp), ref_model.patchify(inp))
+    # AnatoMask.forward_loss takes patchified tensors (P/AnatoMask.py:190-202)
+    loss_r, pp_r = ref_model.forward_loss(ref_model.patchify(inp), ref_model.patchify(rec), active)
+    loss_o, pp_o = rp.patch_loss(cfg, inp, rec, active)
+    assert abs(float(loss_o) - float(loss_r)) <= 1e-6 * abs(float(loss_r))
+    assert torch.allclose(pp_o, pp_r, rtol=1e-6, atol=1e-7)
+    # teacher loss of the script (P/pretrain_AntoMask.py:423-425): raw patches
+    inp1, rec1 = ref_model.patchify(inp), ref_model.patchify(rec)
+    want = ((rec1 - inp1) ** 2).mean(dim=2) * active.logical_not().int().view(B, -1)
+    assert torch.allclose(rp.teacher_patch_loss(cfg, inp, rec, active), want, rtol=1e-6, atol=1e-7)
+
+
+def test_random_mask_matches_live_reference(ref_model):
+    cfg = rp.CONFIGS['tiny']
+    for seed in range(4):
+        torch.manual_seed(seed)
+        want = ref_model.mask(4, 'cpu')           # P/spark3D.py:92-96 draws from the default CPU generator
+        torch.manual_seed(seed)
+        got = rp.random_mask(cfg, 4, None)
+        assert torch.equal(got, want)
