@@ -78,3 +78,38 @@ def test_random_mask_matches_live_reference(ref_model):
         torch.manual_seed(seed)
         got = rp.random_mask(cfg, 4, None)
         assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize('name,seed', [('tiny', 11), ('tiny', 12), ('S64', 13)])
+def test_spark_step_against_live_reference_on_fresh_seeds(name, seed):
+    """The golden comparison of test_oracle_golden.py repeated on seeds that have no committed fixture: full tensors (not
+    digests) of rec, per-patch loss, every gradient and the BN buffers after the step."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('make_golden', os.path.join(ROOT, 'oracle', 'make_golden.py'))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    cfg = rp.CONFIGS[name]
+    torch.set_num_threads(8)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = mg.build_reference(cfg, anatomask=False)
+    state = rp.make_state(cfg, seed)
+    model.load_state_dict(state)
+    model.train()
+    inp = rp.make_input(cfg, 2, seed)
+    active = rp.random_mask(cfg, 2, torch.Generator().manual_seed(seed + 1))
+    loss = model(inp, active_b1ff=active)
+    loss.backward()
+    out = rp.spark_loss_and_grads(state, cfg, inp, active)
+    assert abs(float(out['loss']) - float(loss)) <= 2e-6 * abs(float(loss))
+    ref_grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert sorted(ref_grads) == sorted(out['grads'])
+    for k, gr in ref_grads.items():
+        go = out['grads'][k]
+        if float(gr.norm()) < 1e-6:                # analytically-zero bias gradients: noise on both sides
+            assert float(go.norm()) < 1e-5, k
+            continue
+        rel = float((go - gr).norm() / gr.norm())
+        assert rel < 5e-3, (k, rel)                # fp32 summation-order noise of 10^5-term reductions
+    sd = model.state_dict()
+    for k, v in out['new_buffers'].items():
+        assert torch.allclose(v.to(sd[k].dtype), sd[k], rtol=1e-5, atol=1e-6), k
