@@ -113,3 +113,40 @@ def test_spark_step_against_live_reference_on_fresh_seeds(name, seed):
     sd = model.state_dict()
     for k, v in out['new_buffers'].items():
         assert torch.allclose(v.to(sd[k].dtype), sd[k], rtol=1e-5, atol=1e-6), k
+
+
+def test_public_signatures_match_live_reference():
+    """Drop-in contract: the host mirror keeps the reference's class names, constructor and method signatures
+    (parameter names, order and defaults)."""
+    import importlib
+    import inspect
+    sys.path[:0] = [os.path.join(ROOT, 'oracle', 'timm_stub'), REF]
+    pairs = [('encoder3D', ['SparseEncoder', 'SparseConv3d', 'SparseBatchNorm3d', 'SparseSyncBatchNorm3d',
+                            'SparseInstanceNorm']),
+             ('decoder3D', ['LightDecoder', 'UNetBlock']),
+             ('STUNet_head', ['STUNet', 'BasicResBlock']),
+             ('spark3D', ['SparK']), ('AnatoMask', ['SparK'])]
+    methods = {'SparK': ['__init__', 'mask', 'forward', 'patchify', 'unpatchify', 'get_config', 'state_dict', 'load_state_dict',
+                         'forward_loss', 'generate_mask'],
+               'SparseEncoder': ['__init__', 'forward', 'dense_model_to_sparse'],
+               'LightDecoder': ['__init__', 'forward'], 'STUNet': ['__init__', 'forward', 'get_downsample_ratio',
+                                                                   'get_feature_map_channels'],
+               'SparseInstanceNorm': ['__init__', 'forward'], 'BasicResBlock': ['__init__', 'forward'],
+               'UNetBlock': ['__init__', 'forward']}
+
+    def sig(fn):
+        return [(p.name, p.kind, p.default if p.default is not inspect._empty else '<none>')
+                for p in inspect.signature(fn).parameters.values()]
+
+    for modname, classes in pairs:
+        ref_mod = importlib.import_module(modname)
+        our_mod = importlib.import_module('anatomask_b200.' + modname)
+        for cname in classes:
+            rc, oc = getattr(ref_mod, cname), getattr(our_mod, cname)
+            assert [b.__name__ for b in oc.__mro__ if b.__module__.startswith('torch')][:1] == \
+                   [b.__name__ for b in rc.__mro__ if b.__module__.startswith('torch')][:1], cname   # same torch base class
+            for m in methods.get(cname, ['__init__']):
+                if not hasattr(rc, m):
+                    continue
+                assert hasattr(oc, m), (modname, cname, m)
+                assert sig(getattr(oc, m)) == sig(getattr(rc, m)), (modname, cname, m, sig(getattr(oc, m)), sig(getattr(rc, m)))
