@@ -150,3 +150,31 @@ def test_public_signatures_match_live_reference():
                     continue
                 assert hasattr(oc, m), (modname, cname, m)
                 assert sig(getattr(oc, m)) == sig(getattr(rc, m)), (modname, cname, m, sig(getattr(oc, m)), sig(getattr(rc, m)))
+
+
+def test_mirror_host_side_methods_against_live_reference(ref_model):
+    """The parts of the host mirror that are plain torch (no kernel): mask(), patchify / unpatchify, get_config, the
+    len_loss <= 0 branch of generate_mask — same results as the reference module on CPU."""
+    from anatomask_b200.trainer import build_model
+    cfg = rp.CONFIGS['tiny']
+    ours = build_model(base=cfg.base, depth=cfg.depth, input_size=cfg.input_size, device='cpu', anatomask=True)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 1, *cfg.input_size, generator=g)
+    assert torch.equal(ours.patchify(x), ref_model.patchify(x))
+    assert torch.equal(ours.unpatchify(ours.patchify(x)), x)
+    assert torch.equal(ours.unpatchify(ours.patchify(x)), ref_model.unpatchify(ref_model.patchify(x)))
+    for seed in range(3):
+        torch.manual_seed(seed)
+        want = ref_model.mask(3, 'cpu')
+        torch.manual_seed(seed)
+        assert torch.equal(ours.mask(3, 'cpu'), want)
+    rc, oc = ref_model.get_config(), ours.get_config()
+    assert set(rc) == set(oc) and all(rc[k] == oc[k] for k in rc), (rc, oc)
+    # first epochs of a long schedule: len_loss = int(nm * keep_ratio) = 0 → torch.randn branch (P/AnatoMask.py:99-103)
+    ours.mask_rng = 'numpy'
+    loss_pred = torch.rand(2, cfg.L, generator=g)
+    torch.manual_seed(3)
+    want, _ = ref_model.generate_mask(loss_pred, guide=True, epoch=0, total_epoch=999)
+    torch.manual_seed(3)
+    got, _ = ours.generate_mask(loss_pred, guide=True, epoch=0, total_epoch=999)
+    assert torch.equal(got, want)
