@@ -178,3 +178,35 @@ def test_mirror_host_side_methods_against_live_reference(ref_model):
     torch.manual_seed(3)
     got, _ = ours.generate_mask(loss_pred, guide=True, epoch=0, total_epoch=999)
     assert torch.equal(got, want)
+
+
+def test_lr_schedule_matches_live_reference_scheduler():
+    """trainer.lr_at_epoch (closed form) vs the reference's LinearWarmupCosineAnnealingLR stepped once per epoch as the
+    scripts do (P/pretrain_AntoMask.py:359, N/training/lr_scheduler/LinearWarmupCosine.py:63-102), and the EMA decay
+    schedule vs the script's inline formula (P/pretrain_AntoMask.py:383-386)."""
+    import importlib.util
+    import warnings
+    from anatomask_b200.trainer import lr_at_epoch, ema_decay_at_epoch
+    path = '/root/reference/nnunetv2/training/lr_scheduler/LinearWarmupCosine.py'
+    spec = importlib.util.spec_from_file_location('ref_lwc', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for base_lr, warmup, epochs in [(1e-4, 20, 1000), (2e-4, 20, 300), (1e-3, 5, 40)]:
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.AdamW([p], lr=base_lr)
+        sch = mod.LinearWarmupCosineAnnealingLR(opt, warmup, epochs, 1e-6)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            for ep in range(epochs):
+                want = opt.param_groups[0]['lr']                 # the lr the script trains epoch `ep` with
+                got = lr_at_epoch(ep, base_lr, warmup=warmup, max_epochs=epochs, warmup_start_lr=1e-6)
+                assert got == pytest.approx(want, rel=1e-6, abs=1e-12), (base_lr, ep, got, want)
+                opt.step()
+                sch.step()
+    src = open(os.path.join(REF, 'pretrain_AntoMask.py')).read()
+    assert 'model_ema.decay = 0.999 + i / (epoch//4) * (0.9999 - 0.999)' in src      # the lines restated below
+    for epoch in (1000, 300, 40):
+        for i in range(epoch):
+            want = 0.999 + i / (epoch // 4) * (0.9999 - 0.999) if i < epoch // 4 else 0.9999
+            assert ema_decay_at_epoch(i, epoch) == pytest.approx(want, rel=0, abs=1e-15), (epoch, i)
+            assert rp.ema_decay(i, epoch) == pytest.approx(want, rel=0, abs=1e-15)
