@@ -19,8 +19,12 @@ def head_checkpoint(model: torch.nn.Module, engine=None, train_loss=None, val_lo
     ckpt = {'network_weights': sd, 'optimizer_state': None, 'grad_scaler_state': None, 'train_loss': train_loss,
             'val_loss': val_loss, 'current_epoch': epoch}
     if engine is not None:
+        from . import AnatoMask as _am
         ckpt['optimizer_state'] = {'exp_avg': engine.m.clone(), 'exp_avg_sq': engine.v.clone(), 'step': engine.t,
-                                   'layout': dict(engine.arena.offsets), 'n_live': engine.arena.n_live}
+                                   'layout': dict(engine.arena.offsets), 'n_live': engine.arena.n_live,
+                                   # device-RNG stream positions: without them a resumed run replays the masks of step 0
+                                   'rng': {'step_counter': int(engine.step_counter.item()), 'rng_calls': engine._rng_calls,
+                                           'mask_rng_offset': _am.SparK._rng_offset}}
         if engine.teacher is not None:
             ckpt['ema_weights'] = OrderedDict((k, v.detach().clone()) for k, v in engine.teacher.state_dict().items())
     return ckpt
@@ -46,6 +50,16 @@ def resume(engine, ckpt: Dict) -> None:
         engine.teacher.load_state_dict(ckpt['ema_weights'])
     opt: Optional[Dict] = ckpt.get('optimizer_state')
     if opt:
+        if opt.get('layout') is not None and (dict(opt['layout']) != dict(engine.arena.offsets)
+                                              or int(opt.get('n_live', -1)) != engine.arena.n_live):
+            raise RuntimeError('resume: the checkpoint\'s parameter-arena layout differs from this engine\'s (different '
+                               'model size or dead-parameter set) — the Adam moments would land on the wrong parameters')
+        rng = opt.get('rng')
+        if rng:
+            from . import AnatoMask as _am
+            engine.step_counter.fill_(int(rng['step_counter']))
+            engine._rng_calls = int(rng['rng_calls'])
+            _am.SparK._rng_offset = int(rng['mask_rng_offset'])
         engine.m.copy_(opt['exp_avg'])
         engine.v.copy_(opt['exp_avg_sq'])
         engine.t = int(opt['step'])

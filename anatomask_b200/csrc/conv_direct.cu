@@ -201,12 +201,12 @@ extern "C" int amb_conv(const amb_conv_args* a) {
         // active-patch work-list lets it skip masked tiles outright (patch edge >= 8 at the output resolution)
         const bool list_pays = a->active_list != nullptr && p.lgPv >= 3;
         if (a->impl != AMB_IMPL_TCGEN05_V1 && (!list_pays || p.lgPv >= 4)) {   // v3 takes the list itself at edge >= 16
-            int r3 = igemm3_conv(p, a);          // halo planes + 4 interleaved tiles: narrow dense 3x3x3 layers
+            int r4 = igemm4_conv(p, a);          // halo planes, dz taps stacked along N: narrow 3x3x3 s1 layers
+            if (r4 < 0) return r4;
+            if (r4 == 1) return 0;
+            int r3 = igemm3_conv(p, a);          // round-1 form (one MMA per tile and tap), kept as the A/B baseline
             if (r3 < 0) return r3;
             if (r3 == 1) return 0;
-            int r2 = igemm2_conv(p, a);
-            if (r2 < 0) return r2;
-            if (r2 == 1) return 0;
         }
         int r = igemm_conv(p, a);
         if (r < 0) return r;

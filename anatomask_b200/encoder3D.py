@@ -17,7 +17,7 @@ from . import ops
 from ._lib import ACT_NONE
 
 _cur_active: torch.Tensor = None            # B1fff bool, True = visible
-_ctx_cache = (None, None)
+_ctx_cache = (None, -1, None)
 
 
 def _mask_ctx() -> ops.MaskCtx:
@@ -26,9 +26,11 @@ def _mask_ctx() -> ops.MaskCtx:
         raise RuntimeError('encoder3D._cur_active is not set (SparK.forward sets it; P/spark3D.py:103)')
     if isinstance(_cur_active, ops.MaskCtx):
         return _cur_active
-    if _ctx_cache[0] is not _cur_active:
-        _ctx_cache = (_cur_active, ops.MaskCtx(_cur_active))
-    return _ctx_cache[1]
+    # keyed on the tensor AND its version counter: a static mask buffer updated in place (the usual pattern next to CUDA
+    # graphs) must rebuild the uint8 copy and the device work-list, like the reference recomputes from _cur_active per call
+    if _ctx_cache[0] is not _cur_active or _ctx_cache[1] != _cur_active._version:
+        _ctx_cache = (_cur_active, _cur_active._version, ops.MaskCtx(_cur_active))
+    return _ctx_cache[2]
 
 
 def _single(v):
@@ -159,49 +161,47 @@ class SparseEncoder(nn.Module):
 
     @staticmethod
     def dense_model_to_sparse(m: nn.Module, verbose=False, sbn=False):
-        oup = m
-        if isinstance(m, nn.Conv3d) and not isinstance(m, SparseConv3d):
-            if not getattr(m, 'skip_sparse_conversion', False):
-                bias = m.bias is not None
-                oup = SparseConv3d(m.in_channels, m.out_channels, kernel_size=m.kernel_size, stride=m.stride,
-                                   padding=m.padding, dilation=m.dilation, groups=m.groups, bias=bias,
-                                   padding_mode=m.padding_mode)
-                oup.weight.data.copy_(m.weight.data)
-                if bias:
-                    oup.bias.data.copy_(m.bias.data)
-        elif isinstance(m, nn.MaxPool3d):
-            oup = SparseMaxPooling(m.kernel_size, stride=m.stride, padding=m.padding, dilation=m.dilation,
-                                   return_indices=m.return_indices, ceil_mode=m.ceil_mode)
-        elif isinstance(m, nn.AvgPool3d):
-            oup = SparseAvgPooling(m.kernel_size, m.stride, m.padding, ceil_mode=m.ceil_mode,
-                                   count_include_pad=m.count_include_pad, divisor_override=m.divisor_override)
-        elif isinstance(m, nn.GroupNorm) and not isinstance(m, SparseGroupNorm):
-            oup = SparseGroupNorm(m.num_groups, m.num_channels, eps=m.eps)
-        elif isinstance(m, nn.InstanceNorm3d):
-            oup = SparseInstanceNorm(m.num_features, m.eps)
-            oup.weight.data.copy_(m.weight.data)
-            oup.bias.data.copy_(m.bias.data)
-        elif isinstance(m, (nn.BatchNorm3d, nn.SyncBatchNorm)) and not isinstance(m, SparseSyncBatchNorm3d):
-            oup = (SparseSyncBatchNorm3d if sbn else SparseBatchNorm3d)(
-                m.weight.shape[0], eps=m.eps, momentum=m.momentum, affine=m.affine,
-                track_running_stats=m.track_running_stats)
-            oup.weight.data.copy_(m.weight.data)
-            oup.bias.data.copy_(m.bias.data)
-            oup.running_mean.data.copy_(m.running_mean.data)
-            oup.running_var.data.copy_(m.running_var.data)
-            oup.num_batches_tracked.data.copy_(m.num_batches_tracked.data)
-            if hasattr(m, 'qconfig'):
-                oup.qconfig = m.qconfig
-        elif isinstance(m, nn.LayerNorm) and not isinstance(m, SparseConvNeXtLayerNorm):
-            oup = SparseConvNeXtLayerNorm(m.weight.shape[0], eps=m.eps)
-            oup.weight.data.copy_(m.weight.data)
-            oup.bias.data.copy_(m.bias.data)
-        elif isinstance(m, (nn.Conv1d,)):
+        """Recursive dense → sparse swap with the rules (and the errors) of P/encoder3D.py:298-364, written as a table:
+        (dense type, sparse type, constructor arguments taken from the dense layer, state to carry over)."""
+        bn_cls = SparseSyncBatchNorm3d if sbn else SparseBatchNorm3d
+        rules = (
+            (nn.Conv3d, SparseConv3d,
+             lambda d: dict(in_channels=d.in_channels, out_channels=d.out_channels, kernel_size=d.kernel_size, stride=d.stride,
+                            padding=d.padding, dilation=d.dilation, groups=d.groups, bias=d.bias is not None,
+                            padding_mode=d.padding_mode), ('weight', 'bias')),
+            (nn.MaxPool3d, SparseMaxPooling,
+             lambda d: dict(kernel_size=d.kernel_size, stride=d.stride, padding=d.padding, dilation=d.dilation,
+                            return_indices=d.return_indices, ceil_mode=d.ceil_mode), ()),
+            (nn.AvgPool3d, SparseAvgPooling,
+             lambda d: dict(kernel_size=d.kernel_size, stride=d.stride, padding=d.padding, ceil_mode=d.ceil_mode,
+                            count_include_pad=d.count_include_pad, divisor_override=d.divisor_override), ()),
+            (nn.GroupNorm, SparseGroupNorm, lambda d: dict(num_groups=d.num_groups, num_channels=d.num_channels, eps=d.eps), ()),
+            (nn.InstanceNorm3d, SparseInstanceNorm, lambda d: dict(num_features=d.num_features, eps=d.eps), ('weight', 'bias')),
+            ((nn.BatchNorm3d, nn.SyncBatchNorm), bn_cls,
+             lambda d: dict(num_features=d.weight.shape[0], eps=d.eps, momentum=d.momentum, affine=d.affine,
+                            track_running_stats=d.track_running_stats),
+             ('weight', 'bias', 'running_mean', 'running_var', 'num_batches_tracked')),
+            (nn.LayerNorm, SparseConvNeXtLayerNorm, lambda d: dict(normalized_shape=d.weight.shape[0], eps=d.eps), ('weight', 'bias')),
+        )
+        already_sparse = (SparseConv3d, SparseGroupNorm, SparseSyncBatchNorm3d, SparseConvNeXtLayerNorm)
+        if isinstance(m, nn.Conv1d):
             raise NotImplementedError
+        out = m
+        skip = isinstance(m, nn.Conv3d) and getattr(m, 'skip_sparse_conversion', False)      # honoured for convs only
+        if not isinstance(m, already_sparse) and not skip:
+            for dense_t, sparse_t, ctor_args, carried in rules:
+                if isinstance(m, dense_t):
+                    out = sparse_t(**ctor_args(m))
+                    for attr in carried:
+                        src = getattr(m, attr, None)
+                        if src is not None:
+                            getattr(out, attr).data.copy_(src.data)
+                    if hasattr(m, 'qconfig') and sparse_t is bn_cls:
+                        out.qconfig = m.qconfig
+                    break
         for name, child in m.named_children():
-            oup.add_module(name, SparseEncoder.dense_model_to_sparse(child, verbose=verbose, sbn=sbn))
-        del m
-        return oup
+            out.add_module(name, SparseEncoder.dense_model_to_sparse(child, verbose=verbose, sbn=sbn))
+        return out
 
     def forward(self, x):
         return self.sp_cnn(x, hierarchical=True)

@@ -137,7 +137,12 @@ class PretrainEngine:
         # clip + AdamW, EMA — ~430 launches) is replayed as ONE graph launch
         dev = self.arena.flat.device
         self.hyper = torch.zeros(16, dtype=torch.float32, device=dev)
-        self._hyper_host = torch.zeros(16, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else torch.zeros(16)
+        # the per-step scalars are staged through a RING of pinned host buffers, each guarded by an event recorded after its
+        # H2D copy: the host may run many steps ahead of the device (nothing in graph_step synchronises), and rewriting a
+        # single staging buffer would hand an earlier step the lr / bias corrections / EMA decay of a later one
+        self._hyper_ring = [[torch.zeros(16, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else torch.zeros(16), None]
+                            for _ in range(8)]
+        self._hyper_slot = 0
         self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self._graphs = {}
         self._static_inp = None
@@ -174,11 +179,19 @@ class PretrainEngine:
         b1, b2 = self.betas
         t = self.t + 1
         d = ema_decay_at_epoch(epoch, self.epochs)
-        h = self._hyper_host
+        slot = self._hyper_ring[self._hyper_slot]
+        self._hyper_slot = (self._hyper_slot + 1) % len(self._hyper_ring)
+        h, ev = slot
+        if ev is not None:
+            ev.synchronize()                       # blocks only when the host is a full ring ahead of the device
         h[0], h[1] = d, 1.0 - d
         h[2], h[3], h[4], h[5], h[6] = lr_at_epoch(epoch, self.lr, max_epochs=self.epochs), b1, b2, self.eps, self.wd
         h[7], h[8], h[9], h[10] = 1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t), self.clip, 1.0 / self.world
         self.hyper.copy_(h, non_blocking=True)
+        if self.hyper.is_cuda:
+            if ev is None:
+                ev = slot[1] = torch.cuda.Event()
+            ev.record()
 
     def _device_front(self, inp: torch.Tensor, len_loss_epoch: int):
         """Teacher forward → hard mask → student forward/backward, every per-step scalar read from device memory."""
@@ -325,6 +338,9 @@ class PretrainEngine:
     def step(self, inp: torch.Tensor, epoch: int = 0, mask1: Optional[torch.Tensor] = None):
         """P/pretrain_AntoMask.py:419-440.  Returns (loss, hard mask, teacher per-patch loss) — all on device."""
         self.model.train()
+        # host-driven RNG offsets here: the device step counter only advances inside device_step / graph_step, and a
+        # counter left attached would freeze the random fill of generate_mask at one stream position
+        self.teacher.rng_counter = None
         B = inp.shape[0]
         if mask1 is None:
             mask1 = self.random_mask(B, inp.device)

@@ -96,12 +96,12 @@ def test_direct_and_tcgen05_agree_exactly_on_integers():
     w = torch.randint(-2, 3, (64, 64, 3, 3, 3), generator=g).float().to(dev)
     wp = ops._pack(w, 27, 64, 64, 1, 64 * 27, 27)
     ys = []
-    for impl in (L.IMPL_DIRECT, L.IMPL_TCGEN05_V1):
+    for impl in (L.IMPL_DIRECT, L.IMPL_TCGEN05_V1, L.IMPL_TCGEN05):      # CUDA cores, per-tap tcgen05, N-stacked halo planes
         y = torch.empty(2, 16, 16, 16, 64, dtype=torch.bfloat16, device=dev)
         ops._conv_call(L.OP_CONV, impl, (2, 16, 16, 16), 64, 64, 3, 1, x, y, wp)
         ys.append(y)
     torch.cuda.synchronize()
-    assert torch.equal(ys[0], ys[1])
+    assert torch.equal(ys[0], ys[1]) and torch.equal(ys[0], ys[2])
 
 
 @pytest.mark.parametrize('name,seed', [('tiny', 3), ('S64', 5), ('B64', 5), ('S_aniso', 4), ('L32', 2)])
