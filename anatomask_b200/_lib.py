@@ -41,6 +41,7 @@ _SIGNATURES = {
     'amb_sm_arch': (i32, []),
     'amb_launch_count': (i64, []),
     'amb_reset_launch_count': (None, []),
+    'amb_last_conv_kernel': (C.c_char_p, []),
     'amb_build_active_list': (i32, [vp, i32, vp, vp, vp]),
     'amb_ncdhw_f32_to_ndhwc_bf16': (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     'amb_ndhwc_bf16_to_ncdhw_f32': (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),

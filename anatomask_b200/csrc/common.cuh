@@ -17,6 +17,7 @@ typedef __nv_bfloat16 bf16;
 // ------------------------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 extern int g_launch_count;                      // kernels launched by this library (bench.py's gpu_launches)
+extern const char* g_last_conv_kernel;          // kernel that served the last amb_conv / amb_conv_wgrad call (bench.py's roofline)
 
 #define AMB_CHECK(cond, code, ...)            \
     do {                                      \

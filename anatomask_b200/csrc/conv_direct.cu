@@ -157,6 +157,7 @@ static int direct_conv(const Plan& p, const amb_conv_args* a) {
     if (blocks > cap) blocks = cap;
     direct_conv_kernel<<<(int)blocks, 256, 0, (cudaStream_t)a->stream>>>(P);
     AMB_LAUNCH_CHECK();
+    g_last_conv_kernel = "direct_conv_kernel";
     return 0;
 }
 
@@ -175,6 +176,7 @@ static int direct_wgrad(const Plan& p, const amb_wgrad_args* a) {
     dim3 grid(bx, (unsigned)by);
     direct_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)a->stream>>>(P);
     AMB_LAUNCH_CHECK();
+    g_last_conv_kernel = "direct_wgrad_kernel";
     return 0;
 }
 

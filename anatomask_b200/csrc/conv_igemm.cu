@@ -478,6 +478,7 @@ int igemm_conv(const Plan& p, const amb_conv_args* a) {
         igemm_kernel<16><<<grid, 256, smem, st>>>(P);
     }
     AMB_LAUNCH_CHECK();
+    g_last_conv_kernel = "igemm_kernel";
     return 1;
 }
 

@@ -415,6 +415,7 @@ int igemm3_conv(const Plan& p, const amb_conv_args* a) {
     AMB_CUDA(cudaFuncSetAttribute(igemm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     igemm3_kernel<<<grid, 256, smem, (cudaStream_t)a->stream>>>(P);
     AMB_LAUNCH_CHECK();
+    g_last_conv_kernel = "igemm3_kernel";
     return 1;
 }
 

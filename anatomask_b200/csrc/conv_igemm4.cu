@@ -450,6 +450,7 @@ int igemm4_conv(const Plan& p, const amb_conv_args* a) {
         igemm4_kernel<4><<<grid, 256, smem, (cudaStream_t)a->stream>>>(P);
     }
     AMB_LAUNCH_CHECK();
+    g_last_conv_kernel = "igemm4_kernel";
     return 1;
 }
 

@@ -407,6 +407,7 @@ int igemm_wgrad(const Plan& p, const amb_wgrad_args* a) {
     AMB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wgrad_kernel<<<base_jobs * ksplit, 256, smem, (cudaStream_t)a->stream>>>(P);
     AMB_LAUNCH_CHECK();
+    g_last_conv_kernel = "wgrad_kernel";
     return 1;
 }
 

@@ -8,6 +8,7 @@ namespace amb {
 
 static thread_local char g_err[512] = "";
 int g_launch_count = 0;
+const char* g_last_conv_kernel = "";
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -682,6 +683,7 @@ extern "C" int amb_version(void) { return AMB_VERSION; }
 extern "C" int amb_sm_arch(void) { return 100; }
 extern "C" long amb_launch_count(void) { return g_launch_count; }
 extern "C" void amb_reset_launch_count(void) { g_launch_count = 0; }
+extern "C" const char* amb_last_conv_kernel(void) { return g_last_conv_kernel; }
 
 extern "C" int amb_patch_loss_fwd(const float* inp, const float* rec, const uint8_t* active, int N, int D, int H,
                                   int W, int normalize, float* per_patch, float* loss, float* patch_stats,

@@ -73,8 +73,39 @@ class _Timed:
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.e1.record()
-            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
+            kernel = (L.load().amb_last_conv_kernel() or b'').decode()      # which kernel the dispatcher picked
+            PROFILE.append((self.kind, self.flops, self.e0, self.e1, kernel))
         return False
+
+
+# Backward-progress marks: SparK.reconstruct threads its tensors through identity nodes at the two points where a whole
+# parameter group has finished its backward pass (decoder → densify → encoder, the order autograd runs them in).  The
+# engine sets MARK_CALLBACK for the duration of a step and starts that group's gradient all-reduce from the callback, so
+# the exchange overlaps the rest of the backward pass (the DDP reducer's job, P/pretrain_DDP.py:231-232).  None = no-op.
+MARK_CALLBACK = None
+
+
+class _MarkFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tag, *xs):
+        ctx.tag = tag
+        ctx.set_materialize_grads(False)
+        return tuple(x.view_as(x) for x in xs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        cb = MARK_CALLBACK
+        if cb is not None:
+            cb(ctx.tag)
+        return (None,) + gs
+
+
+def backward_mark(tag: str, *xs):
+    """Identity on xs; when the backward pass reaches this point `MARK_CALLBACK(tag)` fires (once, after ALL of xs have
+    their gradients).  Skipped entirely outside an engine step so the eager module path keeps its autograd graph."""
+    if MARK_CALLBACK is None or not any(x.requires_grad for x in xs):
+        return xs
+    return _MarkFn.apply(tag, *xs)
 
 
 def require_cuda(t: torch.Tensor):

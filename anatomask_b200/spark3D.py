@@ -105,7 +105,11 @@ class SparK(nn.Module):
         fea_bcffs: List[torch.Tensor] = self.sparse_encoder(inp_bchwd)
         fea_bcffs = list(reversed(fea_bcffs))
         n_live = len(self.dense_decoder.dec)
+        # backward reaches 'densify_done' once every live densify level has produced its gradient w.r.t. the encoder
+        # features, and 'decoder_done' once dec.0 — the last decoder block of the backward pass — has (ops.backward_mark)
+        fea_bcffs[:n_live] = ops.backward_mark('densify_done', *fea_bcffs[:n_live])
         to_dec = [self._densify_level(i, f, m) if i < n_live else None for i, f in enumerate(fea_bcffs)]
+        to_dec[0], = ops.backward_mark('decoder_done', to_dec[0])
         return self.dense_decoder(to_dec)
 
     def forward(self, inp_bchwd: torch.Tensor, active_b1ff=None, vis=False):

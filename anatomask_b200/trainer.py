@@ -132,6 +132,12 @@ class PretrainEngine:
             self.world = dist.get_world_size(process_group)
         self.mask_rng = mask_rng
         self._rng_calls = 0
+        self.buckets = None
+        if self.world > 1:
+            from .parallel import GradBuckets
+            dev0 = self.arena.flat.device
+            self.buckets = GradBuckets(self.arena.grad, self.arena.offsets, self.arena.n_live, process_group,
+                                       side_stream_fn=(lambda: ops._side_stream(dev0)) if dev0.type == 'cuda' else None)
         # CUDA-graph mode (no host sync in the step): per-step scalars live in `hyper` on the device, the RNG stream is
         # driven by a device step counter, and the whole step (teacher fwd, hard mask, student fwd/bwd, all-reduce,
         # clip + AdamW, EMA — ~430 launches) is replayed as ONE graph launch
@@ -161,9 +167,7 @@ class PretrainEngine:
 
     def _optimise(self, lr: float):
         a = self.arena
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(a.grad, group=self.group)
+        self._allreduce_grads()
         self.t += 1
         ops.adamw_step_(a.flat[:a.n_live], a.grad, self.m, self.v, lr, self.betas, self.eps, self.wd, self.t,
                         self.clip, 1.0 / self.world)
@@ -232,16 +236,9 @@ class PretrainEngine:
             rec1 = self.teacher.reconstruct(inp, mask1)
             recon = self.teacher.teacher_loss(inp, rec1, mask1)
         mask, _ = self.teacher.generate_mask(recon, guide=True, epoch=len_loss_epoch, total_epoch=self.epochs - 1)
-        rec = m.reconstruct(inp, mask)
-        loss, _ = m.forward_loss(inp, rec, mask)
-        self.arena.zero_grad()
-        ops.DEFER_WGRAD = True                     # wgrad chain → side stream, written straight into the arena views
-        try:
-            loss.backward()
-        finally:
-            ops.DEFER_WGRAD = False
+        loss = self._student_fwd_bwd(inp, mask, defer_wgrad=True)
         ops.join_side_stream(inp.device)
-        return loss.detach(), mask, recon
+        return loss, mask, recon
 
     def _device_tail(self):
         """Global-norm clip + AdamW + EMA from the (already all-reduced) gradient arena; scalars from `hyper`."""
@@ -255,9 +252,32 @@ class PretrainEngine:
             ta.iflat.copy_(ta.iflat * self.hyper[0] + self.hyper[1] * a.iflat)
 
     def _allreduce_grads(self):
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.arena.grad, group=self.group)
+        """Joins the bucketed gradient exchange: groups whose backward mark fired are already in flight (overlapped with
+        the rest of the backward pass), the remaining ones — the encoder group — start here."""
+        if self.buckets is not None:
+            ops.join_side_stream(self.arena.flat.device)
+            self.buckets.finish()
+
+    def _student_fwd_bwd(self, inp: torch.Tensor, mask: torch.Tensor, defer_wgrad: bool = False) -> torch.Tensor:
+        """Student forward + backward.  With more than one rank the gradient all-reduce of each parameter group is started
+        from the backward pass as soon as that group is complete (ops.backward_mark: decoder → densify → encoder; what the
+        DDP reducer's buckets do in P/pretrain_DDP.py:231-232) and joined by _allreduce_grads()."""
+        m = self.model
+        if self.buckets is not None:
+            from .parallel import MARK_OF_GROUP
+            group_of_mark = {mk: g for g, mk in MARK_OF_GROUP.items()}
+            self.buckets.begin_step()
+            ops.MARK_CALLBACK = lambda tag: self.buckets.start(group_of_mark[tag])
+        try:
+            rec = m.reconstruct(inp, mask)
+            loss, _ = ops.PatchLossFn.apply(inp, rec, mask[:, 0].to(torch.uint8).contiguous(), True)
+            self.arena.zero_grad()
+            ops.DEFER_WGRAD = defer_wgrad          # wgrad chain → side stream, written straight into the arena views
+            loss.backward()
+        finally:
+            ops.DEFER_WGRAD = False
+            ops.MARK_CALLBACK = None
+        return loss.detach()
 
     def _device_step(self, inp: torch.Tensor, len_loss_epoch: int):
         out = self._device_front(inp, len_loss_epoch)
@@ -286,8 +306,6 @@ class PretrainEngine:
         """Same semantics as step() in device-RNG mode, replayed from a CUDA graph.  Graphs are keyed by the number of
         hard patches (a launch parameter of the top-k kernel that changes every few epochs)."""
         m = self.model
-        if self.world > 1 and getattr(m, 'sbn', False):
-            return self.step(inp, epoch)                 # SyncBN all-reduces sit inside autograd: keep NCCL out of captures
         nm = m.fmap_h * m.fmap_w * m.fmap_d - m.len_keep
         len_loss = int(nm * (float((epoch + 1) / (self.epochs - 1)) * 0.5))
         self.model.train()
@@ -296,6 +314,14 @@ class PretrainEngine:
             self._graphs.clear()
         self._static_inp.copy_(inp, non_blocking=True)
         self._set_hyper(epoch)
+        # world > 1: the NCCL collectives (bucketed gradient all-reduce started from the backward pass, SyncBN statistics)
+        # are captured INTO the step graph, so a step stays one graph launch and the exchange overlaps the backward pass.
+        # AMB_NCCL_OUTSIDE_GRAPH=1 keeps NCCL out of the capture: front graph → eager all-reduce → tail graph (no overlap;
+        # not available with SyncBN, whose all-reduces sit inside the forward / backward).
+        import os
+        split = self.world > 1 and os.environ.get('AMB_NCCL_OUTSIDE_GRAPH') == '1'
+        if split and getattr(m, 'sbn', False):
+            return self.step(inp, epoch)
         if len_loss not in self._graphs:
             self._graphs.clear()                         # one resident graph (its private pool holds a full step)
             self.teacher.mask_rng = 'device'
@@ -303,23 +329,40 @@ class PretrainEngine:
             tensors, saved = self._state_snapshot()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):                # warm-up on a side stream (allocator, function attributes)
+            with torch.cuda.stream(side):                # warm-up on a side stream (allocator, function attributes, NCCL)
                 for _ in range(2):
                     self._device_step(self._static_inp, epoch)
             torch.cuda.current_stream().wait_stream(side)
-            # the NCCL all-reduce stays OUTSIDE the captured region (front graph → eager all-reduce → tail graph)
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1):
-                out = self._device_front(self._static_inp, epoch)
-            with torch.cuda.graph(g2):
-                self._device_tail()
+            if self.world > 1:
+                torch.cuda.synchronize()                 # nothing of the warm-up may still be polled by NCCL's watchdog
+            mode = {'capture_error_mode': 'thread_local'} if self.world > 1 else {}
+            if split:
+                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                keep, self.buckets = self.buckets, None  # no collective may be issued while capturing
+                try:
+                    with torch.cuda.graph(g1, **mode):
+                        out = self._device_front(self._static_inp, epoch)
+                    with torch.cuda.graph(g2, **mode):
+                        self._device_tail()
+                finally:
+                    self.buckets = keep
+                graphs = (g1, g2)
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, **mode):
+                    out = self._device_step(self._static_inp, epoch)
+                graphs = (g,)
             for t, s0 in zip(tensors, saved):            # warm-up / capture must not count as training steps
                 t.copy_(s0)
-            self._graphs[len_loss] = (g1, g2, out)
-        g1, g2, out = self._graphs[len_loss]
-        g1.replay()
-        self._allreduce_grads()
-        g2.replay()
+            self._graphs[len_loss] = (graphs, out)
+        graphs, out = self._graphs[len_loss]
+        if len(graphs) == 2:
+            graphs[0].replay()
+            self.buckets.begin_step()
+            self._allreduce_grads()
+            graphs[1].replay()
+        else:
+            graphs[0].replay()
         self.t += 1
         return out
 
@@ -328,12 +371,9 @@ class PretrainEngine:
         self.model.train()
         if active is None:
             active = self.random_mask(inp.shape[0], inp.device)
-        rec = self.model.reconstruct(inp, active)
-        loss, _ = ops.PatchLossFn.apply(inp, rec, active[:, 0].to(torch.uint8).contiguous(), True)
-        self.arena.zero_grad()
-        loss.backward()
+        loss = self._student_fwd_bwd(inp, active)
         self._optimise(lr_at_epoch(epoch, self.lr, max_epochs=self.epochs))
-        return loss.detach()
+        return loss
 
     def step(self, inp: torch.Tensor, epoch: int = 0, mask1: Optional[torch.Tensor] = None):
         """P/pretrain_AntoMask.py:419-440.  Returns (loss, hard mask, teacher per-patch loss) — all on device."""
@@ -348,10 +388,7 @@ class PretrainEngine:
             rec1 = self.teacher.reconstruct(inp, mask1)
             recon = self.teacher.teacher_loss(inp, rec1, mask1)
         mask, _ = self.teacher.generate_mask(recon, guide=True, epoch=epoch, total_epoch=self.epochs - 1)
-        rec = self.model.reconstruct(inp, mask)
-        loss, _ = self.model.forward_loss(inp, rec, mask)
-        self.arena.zero_grad()
-        loss.backward()
+        loss = self._student_fwd_bwd(inp, mask)
         self._optimise(lr_at_epoch(epoch, self.lr, max_epochs=self.epochs))
         self.ema_update(ema_decay_at_epoch(epoch, self.epochs))
-        return loss.detach(), mask, recon
+        return loss, mask, recon

@@ -7,7 +7,12 @@
 A step = teacher forward (eval) → per-patch teacher loss → hard-mask top-k → student forward/backward → global-norm clip
 + AdamW → EMA teacher update, on a batch of 2 synthetic N(0,1) volumes of 1×128³ per GPU (weak scaling), epoch 500 of
 1000 (len_loss = 76 hard patches).  `value`: inputs resident in HBM.  `e2e`: the same step through the public API with
-the batch coming from pinned host memory every step and the loss read back to the host.
+the batch coming from pinned host memory every step (a different host batch each step) and the loss read back to the host.
+
+  --model L --sbn      BASELINE config 4: STUNet-L, decoder SyncBN (P/pretrain_DDP.py:224-225), batch-sharded over N GPUs
+  --gpu-reference      also times the oracle port on the SAME GPU through torch + cuDNN under bf16 autocast (SURVEY §8d:
+                       "the real kernel-to-beat"); reported as `gpu_reference`, separate from `cpu_baseline`
+  --sweep              also times the step at epochs 0 / 998 (len_loss 0 / 153; the headline epoch 500 has len_loss 76)
 """
 from __future__ import annotations
 
@@ -132,6 +137,36 @@ def cpu_baseline_sample():
             'sample': f'1 AnatoMask step of 1 volume (1x128^3) with the oracle port (PyTorch fp32, {cores} threads): {dt:.1f} s'}
 
 
+def gpu_reference_sample(dev, batch: int, steps: int = 3):
+    """The oracle port (plain PyTorch restatement of the reference modules) running the same AnatoMask step on THIS GPU
+    through torch's own kernels (cuDNN convolutions) under torch.autocast(bfloat16) — P/pretrain.py:394-401 is the
+    reference's autocast site.  Context for the hand-written kernels; never part of the product path."""
+    from oracle import reference_port as rp
+    import numpy as np
+    cfg = rp.CONFIGS['B128']
+    tr = rp.RefTrainer(cfg, {k: v.to(dev) for k, v in rp.make_state(cfg, 0).items()}, lr=1e-4, epochs=1000, anatomask=True)
+    np.random.seed(0)
+    inp = rp.make_input(cfg, batch, 0).to(dev)
+    times = []
+    for i in range(steps + 1):
+        mask1 = rp.random_mask(cfg, batch, torch.Generator().manual_seed(i)).to(dev)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            with torch.no_grad():                                   # P/pretrain_AntoMask.py:419-441 over the port
+                rec1 = rp.forward(tr.ema, cfg, inp, mask1, training=False)
+                recon = rp.teacher_patch_loss(cfg, inp, rec1.float(), mask1)
+            mask = rp.generate_mask(cfg, recon.float().cpu(), 500, 999, True, np.random).to(dev)
+            tr.spark_step(inp, mask)
+        rp.ema_update(tr.ema, tr.state, rp.ema_decay(500, 1000))
+        torch.cuda.synchronize()
+        if i > 0:
+            times.append(time.time() - t0)
+    dt = sorted(times)[len(times) // 2]
+    return {'value': batch / dt, 'unit': UNIT, 'kind': 'port on cuda (torch + cuDNN, bf16 autocast)', 'ms_per_step': dt * 1e3,
+            'sample': f'median of {steps} AnatoMask steps of {batch} volumes (1x128^3) with the oracle port on the same GPU'}
+
+
 def _mark(msg):
     if os.environ.get('AMB_BENCH_VERBOSE'):
         print(f'[bench r{os.environ.get("RANK", "0")}] {msg} t={time.time():.1f}', file=sys.stderr, flush=True)
@@ -155,14 +190,15 @@ def run_ours(args):
     lib = _lib.load()
     B, S = args.batch, args.size
     torch.manual_seed(1234 + rank)
-    model = build_model(args.model, (S, S, S), anatomask=True)
+    model = build_model(args.model, (S, S, S), anatomask=True, sbn=args.sbn)
     if world > 1:                                    # identical initial weights on every rank (DDP broadcast)
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
     _mark('model built + broadcast')
     eng = PretrainEngine(model, lr=1e-4, epochs=1000, anatomask=True, mask_rng='device', process_group=group)
     inp = torch.randn(B, 1, S, S, S, device=dev)
-    host = torch.randn(B, 1, S, S, S).pin_memory()
+    hosts = [torch.randn(B, 1, S, S, S).pin_memory() for _ in range(3)]      # e2e: a different host batch every step
+    host = hosts[0]
     epoch = 500
 
     def barrier():
@@ -197,12 +233,16 @@ def run_ours(args):
     # ---- timed region 1: inputs resident in HBM -----------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         run(inp)
+        marks[i].record()
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+    per_step = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))
+    ms_median = max_over_ranks(per_step[len(per_step) // 2])
     _mark(f'timed region done {ms_total:.1f} ms')
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
@@ -226,31 +266,48 @@ def run_ours(args):
     prof, ops.PROFILE = ops.PROFILE, None
     ops.NO_SIDE = False
     # ---- roofline of the dominant kernel family (live CUDA-event timing of every launch in the timed region) ----
-    fam = {}
-    for kind, flops, a, b in prof:
+    fam, kern = {}, {}
+    for kind, flops, a, b, kname in prof:
+        ms = a.elapsed_time(b)
         d = fam.setdefault(kind, [0.0, 0.0, 0])
-        d[0] += flops; d[1] += a.elapsed_time(b); d[2] += 1
+        d[0] += flops; d[1] += ms; d[2] += 1
+        d = kern.setdefault(kname, [0.0, 0.0, 0])
+        d[0] += flops; d[1] += ms; d[2] += 1
     if os.environ.get('AMB_BENCH_DUMP') and rank == 0:           # per-launch table of the last profiled step
         n_per = len(prof) // args.steps
-        rows = [(k, f, a.elapsed_time(b)) for k, f, a, b in prof[-n_per:]]
-        for i, (k, f, ms) in enumerate(rows):
-            print(f'#LAUNCH {i:3d} {k:12s} {f / 1e9:9.1f} GF {ms:7.3f} ms {f / ms / 1e9:8.1f} TF/s', file=sys.stderr)
+        rows = [(k, f, a.elapsed_time(b), kn) for k, f, a, b, kn in prof[-n_per:]]
+        for i, (k, f, ms, kn) in enumerate(rows):
+            print(f'#LAUNCH {i:3d} {k:12s} {f / 1e9:9.1f} GF {ms:7.3f} ms {f / ms / 1e9:8.1f} TF/s  {kn}', file=sys.stderr)
     peaks, peak_src = _peaks()
-    try:        # DRAM bytes of the family's dominant launch shape from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_ncu_traffic.json')))
-    except (OSError, ValueError):
-        traffic = {}
+    # DRAM bytes per launch of the dominant kernel's dominant shape: a CONSTANT read from the committed ncu --set full
+    # capture (profiles/*_ncu_traffic.json), not measured in this run — ncu cannot run inside the timed bench
+    traffic = {}
+    for name in ('r2_ncu_traffic.json', 'r1_ncu_traffic.json'):
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', name)))
+            break
+        except (OSError, ValueError):
+            continue
     peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1400.0)))
+    burst = float(peaks.get('bf16_tflops', peak))
+    tf = lambda v: v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0
+    # the dominant kernel = the single kernel with the largest share of the step's device time
+    dom = max(kern, key=lambda k: kern[k][1]) if kern else ''
+    dv = kern.get(dom, [0.0, 0.0, 0])
     igemm = [v for k, v in fam.items() if not k.endswith('wgrad')]
-    fl, ms_k, n_k = sum(v[0] for v in igemm), sum(v[1] for v in igemm), sum(v[2] for v in igemm)
-    achieved = fl / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0
+    fam_v = [sum(v[0] for v in igemm), sum(v[1] for v in igemm), sum(v[2] for v in igemm)]
     conv_ms = sum(v[1] for v in fam.values())
     conv_fl = sum(v[0] for v in fam.values())
-    roofline = {'bound': 'tensor', 'kernel': 'igemm_kernel (tcgen05 implicit-GEMM conv fwd/dgrad/convT family)',
-                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                'peak_source': f'{peak_src} bf16_tflops_sustained (kernel timed inside a long step)',
-                'traffic': traffic.get('dram_bytes_per_launch'), 'traffic_note': traffic or None,
-                'launches_timed': n_k, 'avg_launch_ms': ms_k / max(1, n_k),
+    roofline = {'bound': 'tensor', 'kernel': dom, 'achieved': tf(dv), 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf(dv) / peak,
+                'frac_of_burst_peak': tf(dv) / burst,
+                'peak_source': f'{peak_src} bf16_tflops_sustained (kernel timed inside a long step); burst = bf16_tflops',
+                'traffic': traffic.get('dram_bytes_per_launch'),
+                'traffic_note': dict(traffic, measured_in_this_run=False) if traffic else None,
+                'launches_timed': dv[2], 'avg_launch_ms': dv[1] / max(1, dv[2]), 'share_of_step': dv[1] / ms_total,
+                'per_kernel': {k: {'tflops': tf(v), 'frac': tf(v) / peak, 'launches': v[2], 'share_of_step': v[1] / ms_total}
+                               for k, v in sorted(kern.items(), key=lambda kv: -kv[1][1])},
+                'conv_fwd_dgrad_family': {'achieved': tf(fam_v), 'frac': tf(fam_v) / peak, 'frac_of_burst_peak': tf(fam_v) / burst,
+                                          'launches_timed': fam_v[2]},
                 'all_conv_kernels': {'achieved': conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0,
                                      'share_of_step': conv_ms / ms_total, 'eager_pass_ms_per_step': ms_eager_total / args.steps,
                                      'per_family_tflops': {k: v[0] / (v[1] * 1e-3) / 1e12 for k, v in fam.items() if v[1] > 0}},
@@ -258,8 +315,8 @@ def run_ours(args):
     # ---- timed region 2: end to end through the public API, host buffers -----------------------------------
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        x = host.to(dev, non_blocking=True)
+    for i in range(args.steps):
+        x = hosts[i % len(hosts)].to(dev, non_blocking=True)
         loss, _, _ = run(x)
         lv = loss.item()                       # device → host read of the step's result
     e1.record()
@@ -267,17 +324,43 @@ def run_ours(args):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e = {'value': B * world / (ms_e2e / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': host.numel() * 4 * world,
            'd2h_bytes_per_step': 4 * world, 'ms_per_step': ms_e2e, 'last_loss': lv}
-    out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-           'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
-           'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+    # ---- easy→hard schedule: the same step at the first and last epochs (len_loss 0 and 153 hard patches) ----------
+    sweep = None
+    if args.sweep and use_graph:
+        sweep = {'76': value}
+        for ep, ll in ((0, '0'), (998, '153')):
+            for _ in range(3):
+                eng.graph_step(inp, ep)
+            barrier()
+            e0.record()
+            for _ in range(5):
+                eng.graph_step(inp, ep)
+            e1.record()
+            barrier()
+            sweep[ll] = B * world / (max_over_ranks(e0.elapsed_time(e1)) / 5 / 1e3)
+    label = 'METRIC' if (args.model == 'B' and not args.sbn) else None
+    metric = METRIC if label else f'128^3 volumes/sec, STUNet-{args.model} AnatoMask pretraining step' + (', decoder SyncBN' if args.sbn else '')
+    out = {'metric': metric, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+           'warmup': args.warmup, 'ms_per_step': ms_step, 'ms_per_step_median': ms_median, 'higher_is_better': True,
+           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
            'config': {'workload': f'STUNet-{args.model} AnatoMask step (teacher fwd + hard mask + student fwd/bwd + clip + '
-                                  f'AdamW + EMA), 1x{S}^3 volumes, batch {B}/GPU, mask 0.6, epoch 500/1000 (len_loss 76)',
+                                  f'AdamW + EMA), 1x{S}^3 volumes, batch {B}/GPU, mask 0.6, epoch 500/1000 (len_loss 76)'
+                                  + (', decoder SyncBN (sbn=True)' if args.sbn else ''),
+                      'gradient_exchange': None if world == 1 else 'bucketed NCCL all-reduce (decoder / densify / encoder groups) '
+                                                                   'started from the backward pass, captured in the step graph',
                       'global_batch': B * world, 'parallelism': f'dp{world}',
                       'cuda_graph': use_graph, 'graph_error': graph_err,
                       'l2': 'per-step working set (multi-GB activations) >> 126 MB L2; no flush needed',
                       'algorithmic_tflop_per_volume': 4 * F_FWD_GF / 1e3 if (args.model == 'B' and S == 128) else None},
            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline}
+    if sweep is not None:
+        out['len_loss_sweep'] = {'unit': UNIT, 'by_len_loss': sweep,
+                                 'note': 'epochs 0 / 500 / 998 of 1000 → 0 / 76 / 153 hard patches of 307 masked (SURVEY §8d C3)'}
     if rank == 0:
+        if world == 1 and args.gpu_reference:
+            del eng, model
+            torch.cuda.empty_cache()
+            out['gpu_reference'] = gpu_reference_sample(dev, B)
         if world == 1 and not args.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline_sample()
         print(json.dumps(out))
@@ -296,6 +379,9 @@ if __name__ == '__main__':
     ap.add_argument('--batch', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--sbn', action='store_true', help='decoder nn.SyncBatchNorm (BASELINE config 4)')
+    ap.add_argument('--sweep', action='store_true', help='also time epochs 0 and 998 (len_loss 0 / 153)')
+    ap.add_argument('--gpu-reference', action='store_true', help='also time the oracle port on this GPU (torch+cuDNN, bf16 autocast)')
     a = ap.parse_args()
     if a.impl == 'reference':
         run_reference(a)

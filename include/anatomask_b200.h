@@ -54,6 +54,7 @@ int amb_version(void);
 int amb_sm_arch(void);                 /* 100: the only architecture this library is built for */
 long amb_launch_count(void);           /* kernels launched by this library since the last reset */
 void amb_reset_launch_count(void);
+const char* amb_last_conv_kernel(void); /* name of the kernel that served the last amb_conv / amb_conv_wgrad call */
 
 /* ---- work-list: replaces `_get_active_ex_or_ii(...).nonzero()` (host sync) — P/encoder3D.py:7-10 ------------- */
 int amb_build_active_list(const uint8_t* active, int n_patches, int* list, int* count, void* stream);

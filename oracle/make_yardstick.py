@@ -5,7 +5,7 @@ The north star asks for "parameter gradients within 1e-2 relative in bf16".  The
 and on this network that mode does not meet 1e-2 itself: the backward pass amplifies rounding noise ~5x per BatchNorm.
 This script MEASURES that: it runs the oracle port twice on identical seeded inputs, once in fp32 and once under
 `torch.autocast('cpu', torch.bfloat16)`, and records per parameter tensor the relative L2 error and the cosine of the
-autocast gradient against the fp32 one (plus loss / rec / per-patch errors).  The GPU parity tests then hold the CUDA
+autocast gradient against the fp32 one and the fp32 gradient's norm (plus loss / rec / per-patch errors).  The GPU parity tests then hold the CUDA
 path to   err_cuda(tensor) <= max(1e-2, FACTOR * err_autocast(tensor))   — see tests/model_checks.py.
 
     python -m oracle.make_yardstick            → tests/golden/autocast_yardstick.json
@@ -54,7 +54,8 @@ def measure(name: str, batch: int, seed: int) -> dict:
     for k, g in ref['grads'].items():
         if float(g.norm()) < 1e-6:
             continue
-        out['grads'][k] = [round(_rel(ac['grads'][k].float(), g), 6), round(_cos(ac['grads'][k].float(), g), 6)]
+        out['grads'][k] = [round(_rel(ac['grads'][k].float(), g), 6), round(_cos(ac['grads'][k].float(), g), 6),
+                           float(g.double().norm())]            # (rel L2 error, cosine, ||g_fp32||) — the norm lets tests pool tensors
     return out
 
 

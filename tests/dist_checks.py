@@ -1,10 +1,16 @@
-"""2-rank NCCL checks (run under torchrun on a 2-GPU box):  python -m torch.distributed.run --nproc-per-node 2 tests/dist_checks.py
+"""2-rank NCCL checks (run under torchrun on a 2-GPU box; tests/test_kernels_gpu.py::test_two_gpu_ddp_and_syncbn_checks
+wraps this file):   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_checks.py
 
 1. SyncBN path: with sbn=True and IDENTICAL inputs/masks on both ranks the pooled statistics equal the local ones, so
    loss and gradients must match the single-process sbn=False run (validates the (Σx, Σx², n) and (Σg, Σg·x̂)
    all-reduces, forward and backward).
-2. Data-parallel step: after one engine step with different per-rank batches, parameters are identical on both ranks
-   (one SUM all-reduce of the gradient arena, 1/world folded into AdamW)."""
+2. Data-parallel engine step: bucketed gradient exchange started from the backward pass — eagerly and captured inside the
+   step graph — leaves parameters and the EMA teacher bit-identical on both ranks; the in-graph exchange agrees with the
+   unbucketed one-shot exchange outside the graph (AMB_NCCL_OUTSIDE_GRAPH=1) up to atomics noise.
+3. SyncBN + graph: the sbn=True engine step is captured as one graph (NCCL statistics all-reduces inside the capture).
+4. Script-level drop-in: the literal step body of P/pretrain_DDP.py (forward under torch DDP with
+   find_unused_parameters=True, broadcast_buffers=False; P/pretrain_DDP.py:231-232) on different per-rank batches — the
+   DDP-averaged gradients equal the oracle's gradients averaged over the two ranks' batches on the well-conditioned block."""
 import os
 import sys
 
@@ -16,15 +22,25 @@ from oracle import reference_port as rp  # noqa: E402
 from anatomask_b200.trainer import PretrainEngine, build_model  # noqa: E402
 
 
+def _same_on_all_ranks(t: torch.Tensor) -> bool:
+    other = t.clone()
+    dist.broadcast(other, 0)
+    ok = torch.tensor([int(torch.equal(t, other))], device=t.device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    return bool(ok.item())
+
+
 def main():
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
     dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))
+    say = (lambda *a: print(*a, flush=True)) if rank == 0 else (lambda *a: None)
     cfg = rp.CONFIGS['S64']
     st = {k: v.cuda() for k, v in rp.make_state(cfg, 5).items()}
     inp = rp.make_input(cfg, 2, 5).cuda()
     active = rp.random_mask(cfg, 2, torch.Generator().manual_seed(6)).cuda()
 
+    # ---- 1. SyncBN statistics ------------------------------------------------------------------------------------
     def run(sbn):
         m = build_model(base=cfg.base, depth=cfg.depth, input_size=cfg.input_size, anatomask=True, sbn=sbn)
         m.load_state_dict(st)
@@ -44,33 +60,101 @@ def main():
     rel = lambda a, b: max(float((a[k] - b[k]).norm() / (b[k].norm() + 1e-12)) for k in keys)
     noise, worst = rel(g0b, g0), rel(g1, g0)
     ok1 = abs(l1 - l0) <= 2e-4 * abs(l0) and worst < max(5e-2, 5 * noise)
-    if rank == 0:
-        print(f'RESULT run-to-run noise on dec.3/proj grads {noise:.2e}')
-    if rank == 0:
-        print(f'RESULT syncbn loss {l0:.6f} vs {l1:.6f}; worst grad rel {worst:.2e}; ok={ok1}')
+    say(f'RESULT run-to-run noise on dec.3/proj grads {noise:.2e}')
+    say(f'RESULT syncbn loss {l0:.6f} vs {l1:.6f}; worst grad rel {worst:.2e}; ok={ok1}')
+
+    # ---- 2. data-parallel engine steps: bucketed exchange, eager and in-graph -----------------------------------------
+    def engine(sbn=False):
+        m = build_model(base=cfg.base, depth=cfg.depth, input_size=cfg.input_size, anatomask=True, sbn=sbn)
+        m.load_state_dict(st)
+        return PretrainEngine(m, epochs=1000, anatomask=True, mask_rng='device', process_group=dist.group.WORLD)
 
     torch.manual_seed(100 + rank)
-    m = build_model(base=cfg.base, depth=cfg.depth, input_size=cfg.input_size, anatomask=True)
-    m.load_state_dict(st)
-    eng = PretrainEngine(m, epochs=1000, anatomask=True, mask_rng='device', process_group=dist.group.WORLD)
-    x = torch.randn(2, 1, *cfg.input_size, device='cuda')
+    x = torch.randn(2, 1, *cfg.input_size, device='cuda')                # different batch on every rank
+    eng = engine()
+    say(f'RESULT bucket ranges {[(g, eng.buckets.ranges[g]) for g in eng.buckets.order]}')
     for _ in range(2):
         eng.step(x, epoch=500)
+    for _ in range(3):
+        loss_g, _, _ = eng.graph_step(x, epoch=500)
+    torch.cuda.synchronize()
+    same = _same_on_all_ranks(eng.arena.flat[:eng.arena.n_live])          # parameters only: BN running stats stay rank-local
+    same_t = _same_on_all_ranks(eng.tarena.flat[:eng.tarena.n_live])
+    say(f'RESULT ddp (bucketed, in-graph NCCL): params identical across ranks={same} teacher identical={same_t} '
+        f'loss {float(loss_g):.5f}')
+    # the same three graph steps with NCCL outside the capture (one-shot exchange between two graphs)
+    os.environ['AMB_NCCL_OUTSIDE_GRAPH'] = '1'
+    eng2 = engine()
     for _ in range(2):
-        eng.graph_step(x, epoch=500)
-    flat = eng.arena.flat[:eng.arena.n_live].clone()        # parameters only: BN running stats stay rank-local by design
-    other = flat.clone()
-    dist.broadcast(other, 0)
-    same = bool(torch.equal(flat, other))
-    tf = eng.tarena.flat[:eng.tarena.n_live].clone()
-    to = tf.clone()
-    dist.broadcast(to, 0)
-    same_t = bool(torch.equal(tf, to))
-    if rank == 0 or not (same and same_t):
-        print(f'RESULT ddp rank{rank}: params identical across ranks={same} teacher identical={same_t}')
+        eng2.step(x, epoch=500)
+    for _ in range(3):
+        loss_s, _, _ = eng2.graph_step(x, epoch=500)
+    del os.environ['AMB_NCCL_OUTSIDE_GRAPH']
+    torch.cuda.synchronize()
+    a, b = eng.arena.flat[:eng.arena.n_live], eng2.arena.flat[:eng2.arena.n_live]
+    upd = (a - st_flat(eng, st)).norm()
+    drel = float((a - b).norm() / (upd + 1e-30))
+    ok2 = same and same_t and abs(float(loss_g) - float(loss_s)) <= 5e-3 * abs(float(loss_s))
+    say(f'RESULT in-graph vs outside-graph exchange: loss {float(loss_g):.5f} vs {float(loss_s):.5f}; '
+        f'param diff / update size {drel:.3e}; ok={ok2}')
+
+    # ---- 3. SyncBN engine step captured as one graph ----------------------------------------------------------------------
+    eng3 = engine(sbn=True)
+    for _ in range(3):
+        loss_b, mask_b, _ = eng3.graph_step(x, epoch=500)
+    torch.cuda.synchronize()
+    captured = len(eng3._graphs) == 1
+    same3 = _same_on_all_ranks(eng3.arena.flat[:eng3.arena.n_live])
+    ok3 = captured and same3 and bool(torch.isfinite(loss_b)) and int(mask_b.sum()) == 2 * cfg.len_keep
+    say(f'RESULT syncbn engine graph step: captured={captured} params identical={same3} loss {float(loss_b):.5f}; ok={ok3}')
+
+    # ---- 4. the DDP script's step body under torch DDP ---------------------------------------------------------------------
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    # decoder sbn=False as in P/pretrain_AnatoMask_DDP.py:228-229: every rank's forward is then independent and the exact
+    # reference for the DDP-averaged gradient is the mean of the per-rank oracle gradients
+    model_without_ddp = build_model(base=cfg.base, depth=cfg.depth, input_size=cfg.input_size, anatomask=False, sbn=False)
+    model_without_ddp.load_state_dict(st)
+    model = DDP(model_without_ddp, device_ids=[int(os.environ['LOCAL_RANK'])], find_unused_parameters=True,
+                broadcast_buffers=False)                                       # P/pretrain_DDP.py:231-232
+    model.train()
+    params_req_grad = [p for p in model.parameters() if p.requires_grad]
+    optimizer = torch.optim.AdamW(params_req_grad, lr=2e-4, betas=(0.9, 0.999), weight_decay=1e-5)
+    inp_r = rp.make_input(cfg, 2, 40 + rank)
+    torch.manual_seed(900 + rank)
+    act_r = rp.random_mask(cfg, 2, None)
+    ref = rp.spark_loss_and_grads({k: v.cpu() for k, v in st.items()}, cfg, inp_r, act_r)     # this rank's oracle
+    torch.manual_seed(900 + rank)
+    loss = model(inp_r.cuda(), active_b1ff=None, vis=False)                    # P/pretrain_DDP.py step body, verbatim
+    optimizer.zero_grad()
+    loss.backward()
+    grads = {n: p.grad.clone() for n, p in model_without_ddp.named_parameters() if p.grad is not None}
+    torch.nn.utils.clip_grad_norm_(params_req_grad, 12.0)
+    optimizer.step()
+    torch.cuda.synchronize()
+    loss_rel = abs(float(loss) - float(ref['loss'])) / abs(float(ref['loss']))
+    worst4 = 0.0
+    for k in ('dense_decoder.proj.weight', 'dense_decoder.dec.3.conv.3.weight', 'dense_decoder.dec.3.conv.4.weight'):
+        want = ref['grads'][k].cuda()
+        dist.all_reduce(want)
+        want /= world                                                          # DDP averages the ranks' gradients
+        worst4 = max(worst4, float((grads[k] - want).norm() / want.norm()))
+    ok4 = loss_rel <= 2e-3 and worst4 < 3e-2
+    say(f'RESULT script-level DDP step: rank-0 loss rel {loss_rel:.2e}; DDP-averaged dec.3/proj grads vs mean of the per-rank '
+        f'oracle grads: worst rel {worst4:.3e}; ok={ok4}')
+    same4 = _same_on_all_ranks(torch.cat([p.detach().flatten() for p in params_req_grad]))
+    say(f'RESULT script-level DDP step: params identical across ranks after optimizer.step()={same4}')
     dist.barrier()
     dist.destroy_process_group()
-    assert ok1 and same and same_t
+    assert ok1 and ok2 and ok3 and ok4 and same4
+
+
+def st_flat(eng, st):
+    """The initial parameters in arena order (to express parameter differences relative to the update size)."""
+    out = torch.empty_like(eng.arena.flat[:eng.arena.n_live])
+    for n, (o, k) in eng.arena.offsets.items():
+        if o < eng.arena.n_live and n in st:
+            out[o:o + k] = st[n].flatten().to(out.device)
+    return out
 
 
 if __name__ == '__main__':

@@ -372,6 +372,60 @@ def check_layout(Cc=24, S=12, N=2):
     return {'ok': 1}
 
 
+def check_sparse_bn(Cc=32, S=16, N=2, f=2, seed=0, tol=1.2e-2):
+    """SparseBatchNorm3d as a MODULE (P/encoder3D.py:17-25,39-41): training mode normalises with the statistics of the
+    visible voxels only and updates running_mean / running_var (unbiased) / num_batches_tracked from them; eval mode uses
+    the running statistics on visible voxels and leaves masked voxels exactly zero.  Oracle: the reference's own recipe —
+    gather the visible voxels, run torch's BatchNorm1d over them, scatter back into zeros."""
+    from anatomask_b200 import encoder3D
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    mask = _rand_mask(N, f, seed=seed + 1)
+    up = _up(mask, S)
+    res = {}
+    bn_ref = torch.nn.BatchNorm1d(Cc)
+    bn = encoder3D.SparseBatchNorm3d(Cc).to(dev)
+    with torch.no_grad():
+        bn_ref.weight.copy_(1 + 0.2 * torch.randn(Cc, generator=g)); bn_ref.bias.copy_(0.2 * torch.randn(Cc, generator=g))
+        bn_ref.running_mean.copy_(0.1 * torch.randn(Cc, generator=g)); bn_ref.running_var.copy_(1 + 0.3 * torch.rand(Cc, generator=g))
+    bn.load_state_dict({k: v.to(dev) for k, v in bn_ref.state_dict().items()})
+
+    def reference(x, train):
+        bn_ref.train(train)
+        ii = up[:, 0].nonzero(as_tuple=True)                                    # (b, d, h, w) of the visible voxels
+        bhwc = x.permute(0, 2, 3, 4, 1)
+        nc = bn_ref(bhwc[ii])
+        out = torch.zeros_like(bhwc)
+        out[ii] = nc
+        return out.permute(0, 4, 1, 2, 3)
+
+    for step, train in enumerate((True, True, False)):
+        x = ((torch.randn(N, Cc, S, S, S, generator=g) * 1.5 + 0.3) * up).to(bf16)
+        gy = (torch.randn(N, Cc, S, S, S, generator=g) * up).to(bf16)
+        xr = x.float().requires_grad_(True)
+        yr = reference(xr, train)
+        bn.train(train)
+        encoder3D._cur_active = mask.to(dev)
+        xi = x.to(dev).requires_grad_(True)
+        y = bn(xi)
+        if train:
+            yr.backward(gy.float())
+            y.backward(gy.to(dev))
+            res[f'dx_{step}'] = _rel(xi.grad.float().cpu() * up, xr.grad * up)
+            res[f'dgamma_{step}'] = _rel(bn.weight.grad.cpu(), bn_ref.weight.grad)
+            res[f'dbeta_{step}'] = _rel(bn.bias.grad.cpu(), bn_ref.bias.grad)
+            bn.zero_grad(); bn_ref.zero_grad()
+        torch.cuda.synchronize()
+        res[f'fwd_{step}_{"train" if train else "eval"}'] = _rel(y.float().cpu(), yr.detach())
+        assert float(y.float().cpu().abs().mul((~up).float()).max()) == 0.0, 'masked voxels must stay exactly zero'
+        res[f'rmean_{step}'] = _maxerr(bn.running_mean.cpu(), bn_ref.running_mean)
+        res[f'rvar_{step}'] = _maxerr(bn.running_var.cpu(), bn_ref.running_var)
+        assert int(bn.num_batches_tracked) == int(bn_ref.num_batches_tracked)
+    bad = {k_: v for k_, v in res.items() if not (v < tol)}
+    assert not bad, f'SparseBatchNorm3d C={Cc} S={S}: {res}'
+    return res
+
+
 CHECKS = {n[6:]: f for n, f in list(globals().items()) if n.startswith('check_')}
 
 if __name__ == '__main__':

@@ -1,4 +1,5 @@
-"""Short ncu target: the dominant conv shape (64->64 @128^3, batch 2) forward x3, dgrad x3, wgrad x3."""
+"""Short ncu target: one conv shape (default the dominant 64->64 @128^3, batch 2; AMB_NT_CI / AMB_NT_CO / AMB_NT_S override)
+forward x3, dgrad x3, wgrad x3."""
 import ctypes as C
 import os
 import sys
@@ -9,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from anatomask_b200 import ops, _lib as L  # noqa: E402
 
 dev = torch.device('cuda:0')
-N, S, ci, co = 2, 128, 64, 64
+N, S, ci, co = 2, int(os.environ.get('AMB_NT_S', 128)), int(os.environ.get('AMB_NT_CI', 64)), int(os.environ.get('AMB_NT_CO', 64))
 x = torch.randn(N, S, S, S, ci, device=dev).to(torch.bfloat16)
 dy = torch.randn(N, S, S, S, co, device=dev).to(torch.bfloat16)
 w = torch.randn(co, ci, 3, 3, 3, device=dev) / (27 * ci) ** 0.5

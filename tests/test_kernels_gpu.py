@@ -104,9 +104,43 @@ def test_direct_and_tcgen05_agree_exactly_on_integers():
     assert torch.equal(ys[0], ys[1]) and torch.equal(ys[0], ys[2])
 
 
-@pytest.mark.parametrize('name,seed', [('tiny', 3), ('S64', 5), ('B64', 5), ('S_aniso', 4), ('L32', 2)])
+@pytest.mark.parametrize('kw', [dict(), dict(Cc=64, S=32, f=4, seed=3)])
+def test_sparse_batchnorm3d_module_train_and_eval(kw):
+    """SparseBatchNorm3d under a mask — batch statistics + running-stat update in train, running stats in eval"""
+    kc.check_sparse_bn(**kw)
+
+
+# (config, seed): the triples of oracle/make_yardstick.py.  B128 batch 2 is the BASELINE headline configuration
+# (CPU oracle ~40 s on 8 threads), L64 the STUNet-L encoder/decoder widths of BASELINE config 4.
+@pytest.mark.parametrize('name,seed', [('tiny', 3), ('S64', 5), ('B64', 5), ('S_aniso', 4), ('L32', 2), ('L64', 2), ('B128', 5)])
 def test_spark_step_matches_oracle(name, seed):
+    """loss <= max(1e-3, torch-bf16's own error); every gradient tensor <= max(1e-2, 1.25 x torch-bf16-autocast's error on that
+    tensor) — tests/golden/autocast_yardstick.json, see tests/model_checks.py"""
     mc.check_spark(name=name, seed=seed, verbose=False)
+
+
+def test_script_step_bodies_under_the_module_wrapper():
+    """The literal step bodies of P/pretrain.py:404-409 and P/pretrain_AntoMask.py:419-441 with the mirror under LocalDDP"""
+    mc.check_script_spark()
+    mc.check_script_anatomask()
+
+
+def test_two_gpu_ddp_and_syncbn_checks(tmp_path):
+    """tests/dist_checks.py under torchrun on 2 GPUs (NCCL): SyncBN forward/backward all-reduces, bucketed gradient exchange
+    captured in the step graph, the literal script step under torch DDP.  Skipped on a 1-GPU box; its retained log from a
+    2-GPU gpurun call is profiles/r2_dist_checks_2gpu.log."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29533', os.path.join(root, 'tests', 'dist_checks.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    log = out.stdout + out.stderr
+    os.makedirs(os.path.join(root, 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(root, 'gpurun_out', 'dist_checks_2gpu.log'), 'w') as f:
+        f.write(log)
+    assert out.returncode == 0, log[-3000:]
 
 
 def test_anatomask_steps_match_oracle():
