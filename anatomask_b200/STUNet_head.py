@@ -54,13 +54,15 @@ class BasicResBlock(nn.Module):
             # Σy / Σy² of the visible outputs come out of the conv epilogue (no separate statistics pass)
             s1 = ops.new_stats(c1.out_channels, xi.device) if ops.fused_stats_ok(c1.in_channels, c1.out_channels) else None
             # conv outputs feed pooled masked norms only (visible voxels), so their masked voxels may stay unwritten
-            y = ops.conv3d(xi, c1.weight, c1.bias, c1.kernel_size[0], stride, m, stats=s1, zero_inactive=False)
+            y = ops.conv3d(xi, c1.weight, c1.bias, c1.kernel_size[0], stride, m, stats=s1, zero_inactive=False, zero_bias_grad=True)
             sc = ops.conv3d(xi, c3.weight, c3.bias, 1, stride, m, zero_inactive=False) if c3 is not None else xi
         if c1.in_channels == 1:
             s1 = None
         y = ops.masked_norm(y, self.norm1.weight, self.norm1.bias, self.norm1.eps, m, ACT_LRELU, sums=s1)
         s2 = ops.new_stats(c2.out_channels, y.device) if ops.fused_stats_ok(c2.in_channels, c2.out_channels) else None
-        y = ops.conv3d(y, c2.weight, c2.bias, c2.kernel_size[0], 1, m, stats=s2, zero_inactive=False)
+        # conv1 / conv2 feed SparseInstanceNorm only (batch statistics in train AND eval): their bias gradients are
+        # identically zero, so no Σdy pass is run for them (ops.conv3d zero_bias_grad)
+        y = ops.conv3d(y, c2.weight, c2.bias, c2.kernel_size[0], 1, m, stats=s2, zero_inactive=False, zero_bias_grad=True)
         y = ops.masked_norm(y, self.norm2.weight, self.norm2.bias, self.norm2.eps, m, ACT_LRELU, residual=sc, sums=s2)
         return ops.to_external(y)
 

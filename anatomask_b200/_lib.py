@@ -21,7 +21,7 @@ class ConvArgs(C.Structure):
     _fields_ = [('op', i32), ('impl', i32), ('N', i32), ('D', i32), ('H', i32), ('W', i32), ('Cin', i32),
                 ('Cout', i32), ('k', i32), ('stride', i32), ('x', vp), ('y', vp), ('w', vp), ('bias', vp),
                 ('active', vp), ('fd', i32), ('fh', i32), ('fw', i32), ('active_list', vp), ('active_count', vp),
-                ('stats', vp), ('stream', vp)]
+                ('stats', vp), ('ep_scale', vp), ('ep_act', i32), ('pad_', i32), ('stream', vp)]
 
 
 class WgradArgs(C.Structure):

@@ -110,6 +110,14 @@ __device__ __forceinline__ void store8(bf16* p, const float* f) {
     *reinterpret_cast<uint4*>(p) = v;
 }
 
+// fused output transform of the conv epilogues: act(acc * scale + shift)
+__device__ __forceinline__ float ep_apply(float acc, float scale, float shift, int act) {
+    float f = fmaf(acc, scale, shift);
+    if (act == AMB_ACT_RELU6) f = fminf(fmaxf(f, 0.f), 6.f);
+    else if (act == AMB_ACT_LRELU) f = f > 0.f ? f : 0.01f * f;
+    return f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -11,6 +11,8 @@ struct DirectParams {
     bf16* y;
     const bf16* w;
     const float* bias;
+    const float* ep_scale;
+    int ep_act;
     const uint8_t* active;
     const int* list;
     const int* count;
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(256) direct_conv_kernel(const __grid_constant_
         bf16* yrow = P.y + ov.base + n * ov.sN + z * ov.sD + y * ov.sH + x * ov.sW;
         const bool on = (p.lgPv < 0 || P.active == nullptr) ? true : out_voxel_active(p, P.active, n, z, y, x);
         for (int r = lane; r < p.Cy; r += 32) {
-            float acc = P.bias ? P.bias[r] : 0.f;
+            float acc = 0.f;
             if (on) {
                 for (int t = G.tap_begin; t < G.tap_begin + G.tap_count; ++t) {
                     const Tap& T = p.taps[t];
@@ -73,8 +75,7 @@ __global__ void __launch_bounds__(256) direct_conv_kernel(const __grid_constant_
                         for (int j = 0; j < 8; ++j) acc = fmaf(a[j], b[j], acc);
                     }
                 }
-            } else {
-                acc = 0.f;
+                acc = ep_apply(acc, P.ep_scale ? P.ep_scale[r] : 1.f, P.bias ? P.bias[r] : 0.f, P.ep_act);
             }
             yrow[r] = __float2bfloat16(acc);
         }
@@ -149,7 +150,7 @@ static int direct_conv(const Plan& p, const amb_conv_args* a) {
     AMB_CHECK(a->stats == nullptr, AMB_ERR_UNSUPPORTED, "conv: fused stats need the tcgen05 path");
     DirectParams P;
     P.plan = p;
-    P.x = (const bf16*)a->x; P.y = (bf16*)a->y; P.w = (const bf16*)a->w; P.bias = a->bias;
+    P.x = (const bf16*)a->x; P.y = (bf16*)a->y; P.w = (const bf16*)a->w; P.bias = a->bias; P.ep_scale = a->ep_scale; P.ep_act = a->ep_act;
     P.active = a->active; P.list = a->active_list; P.count = a->active_count;
     long warps = (long)p.oN * p.oD * p.oH * p.oW * p.n_groups;
     long blocks = (warps + 7) / 8;

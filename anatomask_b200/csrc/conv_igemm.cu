@@ -85,6 +85,8 @@ struct IgemmParams {
     const int* list;
     const int* count;
     double* stats;
+    const float* ep_scale;               // optional fused epilogue y = act(acc·scale + bias) (inference-mode BN folded in)
+    int ep_act;
     int lgbn, lgbd, lgbh, lgbw;      // log2 of the tile box
     int Tn, Tz, Ty, Tx;              // dense tiling of an out view
     int n_ntiles, NT;
@@ -186,6 +188,8 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
     float* s_stats = (float*)(ctrl + 256);                // [2][Cy] when stats requested
     float* s_bias = s_stats + (P.stats ? 2 * p.Cy : 0);   // [Cy] (zeros without a bias): the epilogue reads it as float4
+    float* s_scale = s_bias + p.Cy;                       // [Cy] (ones without ep_scale)
+    const bool ep = P.ep_scale != nullptr || P.ep_act != 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
         prefetch_tmap(&P.w_map);
     }
     if (P.stats) for (int i = threadIdx.x; i < 2 * p.Cy; i += blockDim.x) s_stats[i] = 0.f;
-    for (int i = threadIdx.x; i < p.Cy; i += blockDim.x) s_bias[i] = P.bias ? P.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < p.Cy; i += blockDim.x) { s_bias[i] = P.bias ? P.bias[i] : 0.f; s_scale[i] = P.ep_scale ? P.ep_scale[i] : 1.f; }
     if (warp == 2) tmem_alloc(tmem_slot, P.tmem_cols);
     tc_fence_before();
     __syncthreads();
@@ -332,15 +336,16 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                     const int ncol = wide ? 32 : 16;
                     float v[32];
                     const float4* bq = reinterpret_cast<const float4*>(s_bias + st.nt * P.NT + col);
+                    const float4* sq4 = reinterpret_cast<const float4*>(s_scale + st.nt * P.NT + col);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (j < ncol) b4 = bq[j >> 2];
-                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                        if (j < ncol) { b4 = bq[j >> 2]; if (ep) s4 = sq4[j >> 2]; }
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
                             float f = 0.f;
-                            if (j < ncol && on) f = __uint_as_float(r[j + jj]) + bb[jj];
+                            if (j < ncol && on) f = ep ? ep_apply(__uint_as_float(r[j + jj]), ss[jj], bb[jj], P.ep_act) : __uint_as_float(r[j + jj]) + bb[jj];
                             v[j + jj] = f;
                         }
                     }
@@ -450,7 +455,7 @@ int igemm_conv(const Plan& p, const amb_conv_args* a) {
     P.y = (bf16*)a->y; P.bias = a->bias; P.active = a->active;
     P.list = use_list ? a->active_list : nullptr;
     P.count = use_list ? a->active_count : nullptr;
-    P.stats = a->stats;
+    P.stats = a->stats; P.ep_scale = a->ep_scale; P.ep_act = a->ep_act;
 
     const int box[4] = {bn, bd, bh, bw};
     for (int i = 0; i < p.n_in_views; ++i)
@@ -463,7 +468,7 @@ int igemm_conv(const Plan& p, const amb_conv_args* a) {
     if (int e = encode_weight_map(&P.w_map, a->w, n_slabs, p.Cy, p.Cx, KC, NT)) return e;
 
     size_t smem = (size_t)P.stages * P.stage_bytes + 1024 + 256 + (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0) +
-                  (size_t)p.Cy * sizeof(float);
+                  2 * (size_t)p.Cy * sizeof(float);
     long tiles_upper = (((long)P.Tn * P.Tz * P.Ty * P.Tx + T - 1) / T) * p.n_groups * P.n_ntiles;
     int grid = (int)(tiles_upper < (long)num_sms() ? tiles_upper : (long)num_sms());
     cudaStream_t st = (cudaStream_t)a->stream;

@@ -330,6 +330,7 @@ typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 int igemm3_conv(const Plan& p, const amb_conv_args* a) {
     const char* dis = getenv("AMB_DISABLE_V3");
     if (dis && atoi(dis) == 1) return 0;
+    if (a->ep_scale || a->ep_act) return 0;              // fused output transforms: conv_igemm4.cu / conv_igemm.cu
     if (!((a->op == AMB_OP_CONV || a->op == AMB_OP_CONV_DGRAD) && a->k == 3 && a->stride == 1)) return 0;
     if (p.Cx % 32 != 0 || p.Cy % 16 != 0 || p.n_taps != 27 || p.n_in_views != 1 || p.n_groups != 1) return 0;
     if (p.oH < 16 || p.oW < 8 || p.oD < V3_T) return 0;

@@ -38,6 +38,8 @@ struct Igemm4Params {
     const int* list;                     // active-patch work-list (patch edge >= 16 output voxels) or nullptr = dense
     const int* count;
     double* stats;
+    const float* ep_scale;               // optional fused epilogue y = act(acc·scale + bias) (inference-mode BN folded in)
+    int ep_act;
     int oN, oD, oH, oW, Cy;
     int lgPv, fd, fh, fw;
     int Ty, Tx, Tzg, NT, kchunks, b_slots, order;
@@ -109,6 +111,8 @@ __global__ void __launch_bounds__(256, 1) igemm4_kernel(const __grid_constant__ 
     uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
     float* s_stats = (float*)(ctrl + 512);
     float* s_bias = s_stats + (P.stats ? 2 * P.Cy : 0);   // [Cy] (zeros without a bias): the epilogue reads it as float4
+    float* s_scale = s_bias + P.Cy;                       // [Cy] (ones without ep_scale)
+    const bool ep = P.ep_scale != nullptr || P.ep_act != 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2 * NP; ++s) mbar_init(&a_full[s], 1);
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(256, 1) igemm4_kernel(const __grid_constant__ 
     }
     if (warp == 0 && lane == 0) { prefetch_tmap(&P.a_map); prefetch_tmap(&P.w_map); }
     if (P.stats) for (int i = threadIdx.x; i < 2 * P.Cy; i += blockDim.x) s_stats[i] = 0.f;
-    for (int i = threadIdx.x; i < P.Cy; i += blockDim.x) s_bias[i] = P.bias ? P.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < P.Cy; i += blockDim.x) { s_bias[i] = P.bias ? P.bias[i] : 0.f; s_scale[i] = P.ep_scale ? P.ep_scale[i] : 1.f; }
     if (warp == 2) tmem_alloc(tmem_slot, P.tmem_cols);
     tc_fence_before();
     __syncthreads();
@@ -282,15 +286,16 @@ __global__ void __launch_bounds__(256, 1) igemm4_kernel(const __grid_constant__ 
                     const int ncol = wide ? 32 : 16;
                     float v[32];
                     const float4* bq = reinterpret_cast<const float4*>(s_bias + col);
+                    const float4* sq4 = reinterpret_cast<const float4*>(s_scale + col);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (j < ncol) b4 = bq[j >> 2];
-                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                        if (j < ncol) { b4 = bq[j >> 2]; if (ep) s4 = sq4[j >> 2]; }
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
                             float f = 0.f;
-                            if (j < ncol && on) f = __uint_as_float(r[j + jj]) + bb[jj];
+                            if (j < ncol && on) f = ep ? ep_apply(__uint_as_float(r[j + jj]), ss[jj], bb[jj], P.ep_act) : __uint_as_float(r[j + jj]) + bb[jj];
                             v[j + jj] = f;
                         }
                     }
@@ -371,7 +376,7 @@ int igemm4_conv(const Plan& p, const amb_conv_args* a) {
     P.y = (bf16*)a->y;
     const View& ov = p.out_views[0];
     P.sN = ov.sN; P.sD = ov.sD; P.sH = ov.sH; P.sW = ov.sW;
-    P.bias = a->bias; P.active = a->active; P.stats = a->stats;
+    P.bias = a->bias; P.active = a->active; P.stats = a->stats; P.ep_scale = a->ep_scale; P.ep_act = a->ep_act;
     P.list = use_list ? a->active_list : nullptr;
     P.count = use_list ? a->active_count : nullptr;
     P.oN = p.oN; P.oD = p.oD; P.oH = p.oH; P.oW = p.oW; P.Cy = p.Cy;
@@ -433,7 +438,7 @@ int igemm4_conv(const Plan& p, const amb_conv_args* a) {
     }
     // shared memory: two plane sets (the next chunk streams in under the current one) + as many weight slabs as fit
     const size_t fixed = 2u * (size_t)(T + 2) * V4_SLOT + 1024 + 512 +
-                         (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0) + (size_t)p.Cy * sizeof(float);
+                         (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0) + 2 * (size_t)p.Cy * sizeof(float);
     int b_slots = env_int("AMB_V4_B_SLOTS", V4_B_SLOTS_MAX);
     if (b_slots > V4_B_SLOTS_MAX) b_slots = V4_B_SLOTS_MAX;
     while (b_slots > 2 && fixed + (size_t)b_slots * P.b_bytes > 227 * 1024) b_slots--;

@@ -188,5 +188,6 @@ int igemm3_conv(const Plan& p, const amb_conv_args* a);
 int igemm4_conv(const Plan& p, const amb_conv_args* a);
 int igemm_wgrad(const Plan& p, const amb_wgrad_args* a);
 int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a);
+int igemm_wgrad_ns(const Plan& p, const amb_wgrad_args* a);
 
 }  // namespace amb

@@ -299,6 +299,7 @@ static bool chan_ok(int c) { return c == 16 || c == 32 || c == 64 || c % 128 == 
 
 int igemm_wgrad(const Plan& p, const amb_wgrad_args* a) {
     // dense 3x3x3 s1 with narrow dY: halo-plane kernel (conv_wgrad_halo.cu)
+    if (int r = igemm_wgrad_ns(p, a)) return r;          // dz taps stacked along N: 64->64 / 64->32 dense 3x3x3
     if (int r = igemm_wgrad_halo(p, a)) return r;
     // roles here: dY has p.Cy channels (M), X has p.Cx channels (N)
     if (!chan_ok(p.Cx) || !chan_ok(p.Cy)) {

@@ -428,6 +428,94 @@ stem_fwd_kernel(Geo g, const float* __restrict__ inp, const float* __restrict__ 
     }
 }
 
+// Same stem, one thread = 8 consecutive voxels of a patch row x one group of 8 channels.  The first kernel above issued
+// 27 input loads + 27 visibility tests + 54 shared-memory weight loads per VOXEL and channel group and was issue-bound
+// (0.31 ms for 215 MB of output, 7 % of DRAM speed).  Here the 9 input rows are loaded once per 8 voxels as 2×float4 + 2
+// scalars, visibility is resolved once per row, and every weight pair read from shared memory feeds 8 voxels:
+// ~250 instead of ~550 instructions per voxel and channel group.
+__global__ void __launch_bounds__(256)
+stem_fwd_run8_kernel(Geo g, const float* __restrict__ inp, const float* __restrict__ w1, const float* __restrict__ b1,
+                     const float* __restrict__ w3, const float* __restrict__ b3, bf16* __restrict__ out1,
+                     bf16* __restrict__ out3) {
+    extern __shared__ float sw[];      // [27][C] w1 transposed, then b1[C], w3[C], b3[C]
+    const int C = g.C, CG = C / 8;
+    for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) sw[i] = w1[(i % C) * 27 + i / C];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        sw[27 * C + i] = b1[i];
+        sw[28 * C + i] = w3[i];
+        sw[29 * C + i] = b3[i];
+    }
+    __syncthreads();
+    const long runs = geo_num_runs(g);
+    const int segs = g.P >> 3;                                  // 8-voxel segments per run (P is a multiple of 8)
+    const uint32_t total = (uint32_t)(runs * segs * CG);
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x) {
+        const int cg = (int)(item % (uint32_t)CG);
+        const uint32_t t = item / (uint32_t)CG;
+        const int seg = (int)(t % (uint32_t)segs);
+        RunPos r = decode_run(g, (long)(t / (uint32_t)segs));
+        const long voxel = r.voxel + seg * 8;
+        uint32_t vq = (uint32_t)voxel;
+        const int x = (int)(vq % (uint32_t)g.W); vq /= (uint32_t)g.W;
+        const int y = (int)(vq % (uint32_t)g.H); vq /= (uint32_t)g.H;
+        const int z = (int)(vq % (uint32_t)g.D);
+        const int px = x >> g.lgP, xin = x & (g.P - 1);
+        float acc[8][8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[v][j] = sw[27 * C + cg * 8 + j];
+        float center[8];
+#pragma unroll
+        for (int r9 = 0; r9 < 9; ++r9) {
+            const int iz = z + r9 / 3 - 1, iy = y + r9 % 3 - 1;
+            float xv[10];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) xv[i] = 0.f;
+            if ((unsigned)iz < (unsigned)g.D && (unsigned)iy < (unsigned)g.H) {
+                const uint8_t* arow = g.active + ((r.n * g.fd + (iz >> g.lgP)) * g.fh + (iy >> g.lgP)) * g.fw;
+                const float* row = inp + (((long)r.n * g.D + iz) * g.H + iy) * g.W + x;
+                const bool a_mid = arow[px] != 0;
+                const bool a_lo = xin == 0 ? (px > 0 && arow[px - 1] != 0) : a_mid;
+                const bool a_hi = xin + 8 == g.P ? (px + 1 < g.fw && arow[px + 1] != 0) : a_mid;
+                if (a_mid) {
+                    const float4 q0 = __ldg(reinterpret_cast<const float4*>(row));
+                    const float4 q1 = __ldg(reinterpret_cast<const float4*>(row + 4));
+                    xv[1] = q0.x; xv[2] = q0.y; xv[3] = q0.z; xv[4] = q0.w;
+                    xv[5] = q1.x; xv[6] = q1.y; xv[7] = q1.z; xv[8] = q1.w;
+                }
+                if (a_lo) xv[0] = __ldg(row - 1);
+                if (a_hi) xv[9] = __ldg(row + 8);
+            }
+            if (r9 == 4) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) center[v] = xv[v + 1];
+            }
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const float4 wa = *reinterpret_cast<const float4*>(&sw[(r9 * 3 + dx) * C + cg * 8]);
+                const float4 wb = *reinterpret_cast<const float4*>(&sw[(r9 * 3 + dx) * C + cg * 8 + 4]);
+                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int v = 0; v < 8; ++v)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[v][j] = fmaf(xv[v + dx], wv[j], acc[v][j]);
+            }
+        }
+        float w3v[8], b3v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { w3v[j] = sw[28 * C + cg * 8 + j]; b3v[j] = sw[29 * C + cg * 8 + j]; }
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            float o3[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o3[j] = fmaf(center[v], w3v[j], b3v[j]);
+            store8(out1 + (voxel + v) * C + cg * 8, acc[v]);
+            store8(out3 + (voxel + v) * C + cg * 8, o3);
+        }
+    }
+}
+
 // thread = (voxel lane, channel group, "slot"): slots 0..26 = conv1 taps, 27 = db1, 28 = dw3, 29 = db3
 __global__ void __launch_bounds__(1024)
 stem_wgrad_kernel(Geo g, const float* __restrict__ inp, const bf16* __restrict__ dy1, const bf16* __restrict__ dy3,
@@ -913,6 +1001,12 @@ extern "C" int amb_stem_fwd(const float* inp, const uint8_t* active, const int* 
     if (int e = stem_geo(g, active, active_list, active_count, N, D, H, W, fd, fh, fw, C)) return e;
     int block = (256 / (C / 8)) * (C / 8);
     AMB_CHECK((long)N * D * H * W * (C / 8) < (1L << 31), AMB_ERR_ARG, "stem: tensor too large for 32-bit indexing");
+    if (g.P % 8 == 0 && W % 4 == 0 && !getenv("AMB_STEM_FWD_V1")) {       // 8 voxels per thread (float4 input rows)
+        stem_fwd_run8_kernel<<<grid_cap((long)N * D * H * W / 8 * (C / 8), block, 4), block, 30 * C * sizeof(float),
+                               (cudaStream_t)stream>>>(g, inp, w1, b1, w3, b3, (bf16*)out1, (bf16*)out3);
+        AMB_LAUNCH_CHECK();
+        return 0;
+    }
     stem_fwd_kernel<<<grid_cap((long)N * D * H * W * (C / 8), block, 8), block, 30 * C * sizeof(float),
                       (cudaStream_t)stream>>>(g, inp, w1, b1, w3, b3, (bf16*)out1, (bf16*)out3);
     AMB_LAUNCH_CHECK();

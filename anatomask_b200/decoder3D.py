@@ -45,6 +45,12 @@ class UNetBlock(nn.Module):
     def forward_internal(self, x):
         x = ops.conv_transpose3d(x, self.up_sample.weight, self.up_sample.bias)
         c0, c3 = self.conv[0], self.conv[3]
+        b1, b4 = self.conv[1], self.conv[4]
+        if not torch.is_grad_enabled() and all(isinstance(b, (nn.BatchNorm3d, nn.SyncBatchNorm)) and not b.training
+                                               and b.track_running_stats for b in (b1, b4)):
+            # inference (the EMA teacher): each BatchNorm (+ReLU6) is folded into the epilogue of the conv that feeds it
+            x = ops.conv3d_bn_eval(x, c0.weight, b1.weight, b1.bias, b1.running_mean, b1.running_var, b1.eps, ACT_RELU6)
+            return ops.conv3d_bn_eval(x, c3.weight, b4.weight, b4.bias, b4.running_mean, b4.running_var, b4.eps, ACT_NONE)
         # training-mode BN statistics come out of the conv epilogue (Σy, Σy² per channel)
         s0 = ops.new_stats(c0.out_channels, x.device) if (self.conv[1].training and ops.fused_stats_ok(c0.in_channels, c0.out_channels)) else None
         x = ops.conv3d(x, c0.weight, None, 3, 1, stats=s0)

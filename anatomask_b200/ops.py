@@ -266,14 +266,15 @@ class PackPlan:
 
 
 def _conv_call(op, impl, dims, Cin, Cout, k, stride, x, y, w, bias=None, m: Optional[MaskCtx] = None, sparse=False,
-               stats=None):
+               stats=None, ep_scale=None, ep_act=0):
     N, D, H, W = dims
     a = L.ConvArgs(op, impl, N, D, H, W, Cin, Cout, k, stride, x.data_ptr(), y.data_ptr(), w.data_ptr(),
                    0 if bias is None else bias.data_ptr(), 0 if m is None else m.active.data_ptr(),
                    1 if m is None else m.fd, 1 if m is None else m.fh, 1 if m is None else m.fw,
                    m.list.data_ptr() if (m is not None and sparse) else 0,
                    m.count.data_ptr() if (m is not None and sparse) else 0,
-                   0 if stats is None else stats.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                   0 if stats is None else stats.data_ptr(), 0 if ep_scale is None else ep_scale.data_ptr(), ep_act, 0,
+                   torch.cuda.current_stream().cuda_stream)
     L.call('amb_conv', C.byref(a))
 
 
@@ -293,7 +294,7 @@ class ConvFn(torch.autograd.Function):
     2×8×8 tile fits a patch — masked tiles are never computed."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, k, stride, m, transposed, impl, stats=None, zero_inactive=True):
+    def forward(ctx, x, weight, bias, k, stride, m, transposed, impl, stats=None, zero_inactive=True, zero_bias_grad=False):
         require_cuda(x)
         x = x.contiguous()
         N, D, H, W, Cin = x.shape
@@ -323,6 +324,7 @@ class ConvFn(torch.autograd.Function):
         ctx.weight_ref = weight
         ctx.flops = flops
         ctx.cfg = (k, stride, m, transposed, impl, bias is not None)
+        ctx.zero_bias_grad = zero_bias_grad
         return y
 
     @staticmethod
@@ -365,7 +367,13 @@ class ConvFn(torch.autograd.Function):
                     dw_ = torch.empty_like(weight) if dst_w is None else dst_w
                     L.call('amb_unpack_wgrad', _p(dwp), _p(dw_), k3, Cout, Cin, 1, Cin * k3, k3, _stream())
             if has_bias and ctx.needs_input_grad[2]:
-                db_ = column_sums(dy, m if not transposed else None)
+                if ctx.zero_bias_grad:
+                    # the conv feeds a batch-statistics norm: dy is that norm's input gradient, whose per-channel sum over the
+                    # pooled voxels is identically zero (the mean subtraction) — the reference's own value here is fp32
+                    # rounding noise (~1e-9 relative to the weights' gradients).  No pass over dy.
+                    db_ = _zeros_small(dy.shape[-1], torch.float32, dy.device)
+                else:
+                    db_ = column_sums(dy, m if not transposed else None)
             return dw_, db_
 
         deferred = False
@@ -376,7 +384,7 @@ class ConvFn(torch.autograd.Function):
             with torch.cuda.stream(side):
                 dw, db = weight_branch(wref.grad if can_defer else None)
                 if can_defer:
-                    if db is not None:
+                    if db is not None and not ctx.zero_bias_grad:     # (an identically-zero bias gradient: the arena is already zero)
                         bias_ref.grad.copy_(db)
                     deferred = True
             for t in (dw, db, dy, x):
@@ -403,7 +411,7 @@ class ConvFn(torch.autograd.Function):
             main.wait_stream(side)
         elif side is None and need_w:
             dw, db = weight_branch()
-        return dx, dw, db, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None
 
 
 def fused_stats_ok(cin: int, cout: int) -> bool:
@@ -417,8 +425,9 @@ def new_stats(channels: int, device) -> torch.Tensor:
 
 
 def conv3d(x, weight, bias=None, k=3, stride=1, m: Optional[MaskCtx] = None, impl=L.IMPL_AUTO, stats=None,
-           zero_inactive=True):
-    return ConvFn.apply(x, weight, bias, k, stride, m, False, impl, stats, zero_inactive)
+           zero_inactive=True, zero_bias_grad=False):
+    """zero_bias_grad: the caller guarantees the output goes ONLY into a norm that uses batch statistics (then ∂loss/∂bias ≡ 0)."""
+    return ConvFn.apply(x, weight, bias, k, stride, m, False, impl, stats, zero_inactive, zero_bias_grad)
 
 
 def conv_transpose3d(x, weight, bias=None, impl=L.IMPL_AUTO):
@@ -442,6 +451,7 @@ class StemFn(torch.autograd.Function):
                _p(w1), _p(b1), _p(w3), _p(b3), _p(out1), _p(out3), _stream())
         ctx.save_for_backward(inp)
         ctx.m, ctx.C = m, Cc
+        ctx.param_refs = (w1, b1, w3, b3)
         return out1, out3
 
     @staticmethod
@@ -450,6 +460,12 @@ class StemFn(torch.autograd.Function):
         m, Cc = ctx.m, ctx.C
         N, _, D, H, W = inp.shape
         d1, d3 = d1.contiguous(), d3.contiguous()
+        refs = ctx.param_refs
+        if DEFER_WGRAD and all(isinstance(r, torch.nn.Parameter) and r.grad is not None and r.grad.is_contiguous() for r in refs):
+            # engine mode: accumulate straight into the (pre-zeroed) arena .grad views
+            L.call('amb_stem_wgrad', _p(inp), _p(m.active), _p(m.list), _p(m.count), N, D, H, W, m.fd, m.fh, m.fw, Cc,
+                   _p(d1), _p(d3), _p(refs[0].grad), _p(refs[1].grad), _p(refs[2].grad), _p(refs[3].grad), _stream())
+            return None, None, None, None, None, None, None
         g = torch.zeros(Cc * 30, dtype=torch.float32, device=inp.device)
         dw1, db1, dw3, db3 = g[:Cc * 27], g[Cc * 27:Cc * 28], g[Cc * 28:Cc * 29], g[Cc * 29:]
         L.call('amb_stem_wgrad', _p(inp), _p(m.active), _p(m.list), _p(m.count), N, D, H, W, m.fd, m.fh, m.fw, Cc,
@@ -467,6 +483,7 @@ class ProjFn(torch.autograd.Function):
         rec = torch.empty((N, 1, D, H, W), dtype=torch.float32, device=x.device)
         L.call('amb_proj_fwd', _p(x), _p(w), _p(b), _p(rec), N * D * H * W, Cc, _stream())
         ctx.save_for_backward(x, w)
+        ctx.param_refs = (w, b)
         return rec
 
     @staticmethod
@@ -475,6 +492,11 @@ class ProjFn(torch.autograd.Function):
         drec = drec.contiguous()
         N, D, H, W, Cc = x.shape
         dx = torch.empty_like(x)
+        w_ref, b_ref = ctx.param_refs
+        if DEFER_WGRAD and w_ref.grad is not None and b_ref.grad is not None and w_ref.grad.is_contiguous():
+            # engine mode: the kernel accumulates into the (pre-zeroed) arena .grad views directly
+            L.call('amb_proj_bwd', _p(x), _p(w), _p(drec), _p(dx), _p(w_ref.grad), _p(b_ref.grad), N * D * H * W, Cc, _stream())
+            return dx, None, None
         g = torch.zeros(Cc + 1, dtype=torch.float32, device=x.device)
         L.call('amb_proj_bwd', _p(x), _p(w), _p(drec), _p(dx), _p(g[:Cc]), _p(g[Cc:]), N * D * H * W, Cc, _stream())
         return dx, g[:Cc].view_as(w), g[Cc:]
@@ -523,6 +545,7 @@ class NormFn(torch.autograd.Function):
                _stream())
         ctx.save_for_backward(x, residual, ss, ntot)
         ctx.cfg = (act, m, fill, token.shape if fill else None, group)
+        ctx.param_refs = (gamma, beta, token)
         return out
 
     @staticmethod
@@ -538,7 +561,13 @@ class NormFn(torch.autograd.Function):
         sums = _zeros_small(3 * Cc, torch.float64, dev)
         L.call('amb_norm_bwd_reduce', C.byref(g), _p(dout), _p(x), _p(residual), _p(scale), _p(shift), _p(saved), act,
                int(fill), _p(sums), _p(sums[2 * Cc:]) if fill else C.c_void_p(0), _stream())
-        gb = torch.empty(2 * Cc, dtype=torch.float32, device=dev)
+        # engine mode: γ / β gradients are written straight into the parameters' (pre-zeroed, arena-resident) .grad views and
+        # autograd gets None for them — no temporaries, no accumulate-add launches (each norm parameter is used exactly once)
+        g_ref, b_ref, t_ref = ctx.param_refs
+        direct = DEFER_WGRAD and group is None and g_ref.grad is not None and b_ref.grad is not None and \
+            g_ref.grad.is_contiguous() and b_ref.grad.is_contiguous() and g_ref.grad.dtype == torch.float32
+        gb = None if direct else torch.empty(2 * Cc, dtype=torch.float32, device=dev)
+        p_dgamma, p_dbeta = (_p(g_ref.grad), _p(b_ref.grad)) if direct else (_p(gb[:Cc]), _p(gb[Cc:]))
         local_gb = None
         if group is not None:       # parameter grads stay rank-local (DDP averages them); dx needs the pooled sums
             import torch.distributed as dist
@@ -549,12 +578,19 @@ class NormFn(torch.autograd.Function):
         if residual is not None:
             dres = torch.zeros_like(x) if sparse else torch.empty_like(x)
         L.call('amb_norm_bwd_apply', C.byref(g), _p(dout), _p(x), _p(residual), _p(scale), _p(shift), _p(saved),
-               _p(sums), act, int(fill), _p(dx), _p(dres), _p(gb[:Cc]), _p(gb[Cc:]), _p(ntot), _stream())
+               _p(sums), act, int(fill), _p(dx), _p(dres), p_dgamma, p_dbeta, _p(ntot), _stream())
         if local_gb is not None:
             dbeta, dgamma = local_gb[:Cc], local_gb[Cc:]
+        elif direct:
+            dgamma = dbeta = None
         else:
             dgamma, dbeta = gb[:Cc], gb[Cc:]
-        dtoken = sums[2 * Cc:].float().view(tshape) if fill else None
+        dtoken = None
+        if fill:
+            if direct and t_ref.grad is not None and t_ref.grad.is_contiguous():
+                t_ref.grad.view(-1).copy_(sums[2 * Cc:])           # fp64 sums → fp32 .grad, one launch
+            else:
+                dtoken = sums[2 * Cc:].float().view(tshape)
         return dx, dgamma, dbeta, dres, dtoken, None, None, None, None, None, None, None
 
 
@@ -585,6 +621,24 @@ def norm_eval(x, gamma, beta, rm, rv, eps, act, m: Optional[MaskCtx] = None, tok
     L.call('amb_norm_apply', C.byref(g), _p(x), _p(ss[:Cc]), _p(ss[Cc:]), C.c_void_p(0), _p(tok), act, _p(out),
            _stream())
     return out
+
+
+def conv3d_bn_eval(x, weight, gamma, beta, rm, rv, eps, act, k=3, impl=L.IMPL_AUTO):
+    """Conv3d (no bias, stride 1) followed by an inference-mode BatchNorm (+activation) as ONE kernel: the BN's
+    scale = γ/√(σ²+eps) and shift = β − μ·scale are applied per output channel in the conv epilogue, so the normalised
+    tensor is written once and never re-read (the teacher's decoder: P/decoder3D.py:19-22 under model_ema.ema.eval(),
+    P/pretrain_AntoMask.py:422).  No autograd: inference only."""
+    require_cuda(x)
+    x = x.contiguous()
+    N, D, H, W, Cin = x.shape
+    Cout = weight.shape[0]
+    ss = torch.empty(2 * Cout, dtype=torch.float32, device=x.device)
+    L.call('amb_norm_eval', _p(gamma), _p(beta), _p(rm), _p(rv), eps, _p(ss[:Cout]), _p(ss[Cout:]), Cout, _stream())
+    wp = _pack(weight, k ** 3, Cout, Cin, 1, Cin * k ** 3, k ** 3)
+    y = torch.empty((N, D, H, W, Cout), dtype=bf16, device=x.device)
+    with _Timed('conv_fwd', 2.0 * N * D * H * W * k ** 3 * Cin * Cout):
+        _conv_call(L.OP_CONV, impl, (N, D, H, W), Cin, Cout, k, 1, x, y, wp, ss[Cout:], ep_scale=ss[:Cout], ep_act=act)
+    return y
 
 
 def batch_norm_eval(x, gamma, beta, rm, rv, eps, act):

@@ -106,6 +106,13 @@ typedef struct amb_conv_args {
     const int* active_list;
     const int* active_count;
     double* stats;
+    /* optional fused output transform  y = act(acc · ep_scale[r] + bias[r])  applied before the mask: an inference-mode
+     * BatchNorm (+ReLU6) folded into the producing convolution (scale = γ/√(σ²+eps), bias = β − μ·scale) — the teacher's
+     * decoder in eval mode (P/pretrain_AntoMask.py:422, P/decoder3D.py:19-22).  ep_scale == NULL: scale 1.  `stats`, when
+     * given together with it, sees the transformed values. */
+    const float* ep_scale;
+    int ep_act;                 /* AMB_ACT_* */
+    int pad_;
     void* stream;
 } amb_conv_args;
 int amb_conv(const amb_conv_args* a);

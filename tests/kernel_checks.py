@@ -426,6 +426,27 @@ def check_sparse_bn(Cc=32, S=16, N=2, f=2, seed=0, tol=1.2e-2):
     return res
 
 
+def check_conv_bn_eval(Cin=64, Cout=64, S=16, N=2, act=2, impl=0, seed=0, tol=1.2e-2):
+    """Conv3d (no bias) + inference-mode BatchNorm (+ReLU6) fused in the conv epilogue (the EMA teacher's decoder) against
+    fp32 torch conv3d → batch_norm(eval) → relu6 on the same bf16-rounded operands."""
+    from anatomask_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, Cin, S, S, S, generator=g).to(bf16)
+    w = (torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (Cin * 27) ** 0.5).to(bf16).float()
+    gamma, beta = 1 + 0.3 * torch.randn(Cout, generator=g), 0.3 * torch.randn(Cout, generator=g)
+    rm, rv = 0.2 * torch.randn(Cout, generator=g), 0.5 + torch.rand(Cout, generator=g)
+    yr = F.batch_norm(F.conv3d(x.float(), w, None, 1, 1), rm, rv, gamma, beta, False, 0.1, 1e-5)
+    yr = F.relu6(yr) if act == 2 else yr
+    xi = x.to(dev).permute(0, 2, 3, 4, 1).contiguous()
+    with torch.no_grad():
+        y = ops.conv3d_bn_eval(xi, w.to(dev), gamma.to(dev), beta.to(dev), rm.to(dev), rv.to(dev), 1e-5, act, impl=impl)
+    torch.cuda.synchronize()
+    res = {'fwd': _rel(y.permute(0, 4, 1, 2, 3).cpu(), yr)}
+    assert res['fwd'] < tol, f'conv+BN(eval) Cin={Cin} Cout={Cout} S={S} act={act} impl={impl}: {res}'
+    return res
+
+
 CHECKS = {n[6:]: f for n, f in list(globals().items()) if n.startswith('check_')}
 
 if __name__ == '__main__':

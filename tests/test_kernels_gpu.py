@@ -81,6 +81,13 @@ def test_masked_conv_over_mask_ratios(kw, keep):
     kc.check_conv(impl=T, masked=True, keep=keep, **kw)
 
 
+@pytest.mark.parametrize('kw', [dict(), dict(Cin=64, Cout=32, S=16, act=0), dict(Cin=128, Cout=128, S=8), dict(Cin=512, Cout=256, S=8, act=0),
+                                dict(Cin=16, Cout=24, S=8, impl=D), dict(Cin=32, Cout=32, S=20, N=1)])
+def test_conv_with_fused_inference_batchnorm(kw):
+    """teacher decoder: BN(eval)+ReLU6 folded into the conv epilogue — N-stacked halo kernel, per-tap kernel, CUDA-core kernel"""
+    kc.check_conv_bn_eval(**kw)
+
+
 @pytest.mark.parametrize('kw', [dict(), dict(Cin=64, Cout=64, S=32)])
 def test_conv_epilogue_statistics(kw):
     kc.check_conv_stats(**kw)
