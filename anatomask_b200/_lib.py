@@ -21,7 +21,8 @@ class ConvArgs(C.Structure):
     _fields_ = [('op', i32), ('impl', i32), ('N', i32), ('D', i32), ('H', i32), ('W', i32), ('Cin', i32),
                 ('Cout', i32), ('k', i32), ('stride', i32), ('x', vp), ('y', vp), ('w', vp), ('bias', vp),
                 ('active', vp), ('fd', i32), ('fh', i32), ('fw', i32), ('active_list', vp), ('active_count', vp),
-                ('stats', vp), ('ep_scale', vp), ('ep_act', i32), ('pad_', i32), ('stream', vp)]
+                ('stats', vp), ('ep_scale', vp), ('ep_act', i32), ('pad_', i32), ('workspace', vp), ('workspace_bytes', i64),
+                ('stream', vp)]
 
 
 class WgradArgs(C.Structure):
@@ -49,6 +50,7 @@ _SIGNATURES = {
     'amb_unpack_wgrad': (i32, [vp, vp, i32, i32, i32, i64, i64, i64, vp]),
     'amb_pack_weights_batched': (i32, [vp, i32, i32, vp]),
     'amb_conv': (i32, [C.POINTER(ConvArgs)]),
+    'amb_conv_workspace_bytes': (i64, [C.POINTER(ConvArgs)]),
     'amb_conv_wgrad': (i32, [C.POINTER(WgradArgs)]),
     'amb_stem_fwd': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     'amb_stem_wgrad': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),

@@ -220,6 +220,21 @@ extern "C" int amb_conv(const amb_conv_args* a) {
     return direct_conv(p, a);
 }
 
+extern "C" long amb_conv_workspace_bytes(const amb_conv_args* a) {
+    if (!a || a->impl == AMB_IMPL_DIRECT || a->Cin % 8 != 0 || a->Cout % 8 != 0) return 0;
+    Plan p;
+    if (build_plan(p, a->op, a->N, a->D, a->H, a->W, a->Cin, a->Cout, a->k, a->stride)) return 0;
+    if (a->active && (a->op == AMB_OP_CONV || a->op == AMB_OP_CONV_DGRAD)) {
+        int fD = a->op == AMB_OP_CONV ? a->D / a->stride : a->D;
+        int fH = a->op == AMB_OP_CONV ? a->H / a->stride : a->H;
+        int fW = a->op == AMB_OP_CONV ? a->W / a->stride : a->W;
+        if (plan_set_mask(p, fD, fH, fW, a->fd, a->fh, a->fw)) return 0;
+    }
+    // the active-patch work-list (patch edge >= 8) and split-K exclude each other: listed layers have plenty of tiles
+    const bool sparse_list = a->active_list != nullptr && p.lgPv >= 3;
+    return igemm_workspace_bytes(p, sparse_list);
+}
+
 extern "C" int amb_conv_wgrad(const amb_wgrad_args* a) {
     AMB_CHECK(a && a->x && a->dy && a->dw, AMB_ERR_ARG, "amb_conv_wgrad: null argument");
     AMB_CHECK(a->op == AMB_OP_CONV || a->op == AMB_OP_CONVT, AMB_ERR_ARG, "amb_conv_wgrad: op must be CONV or CONVT");

@@ -92,6 +92,8 @@ struct IgemmParams {
     int n_ntiles, NT;
     int T;                           // spatial tiles (independent TMEM accumulators) interleaved per CTA iteration
     int kchunks;                     // Cx / KC
+    int ksplit;                      // > 1: the taps of a tile are split over ksplit work items (small spatial extents), fp32
+    float* ws;                       //      partial sums are added into ws (same element offsets as y) and finalised by split_finalize_kernel
     int stages;
     uint32_t stage_bytes, a_bytes, b_bytes, b_tx;   // b_bytes: smem footprint (1 KB aligned), b_tx: bytes the TMA delivers
     uint32_t tmem_cols;
@@ -147,12 +149,20 @@ __device__ __forceinline__ void decode_spatial(const IgemmParams& P, uint32_t t,
 struct SuperTile {
     int g, nt;
     uint32_t s0;
+    int tap_begin, tap_end;          // the taps this work item contracts over (all of the group's unless split-K)
 };
 __device__ __forceinline__ void decode_super(const IgemmParams& P, uint32_t w, uint32_t n_super, SuperTile& st) {
-    const uint32_t q = w / n_super;
+    uint32_t q = w / n_super;
     st.s0 = (w - q * n_super) * (uint32_t)P.T;
+    const uint32_t ksp = q % (uint32_t)P.ksplit;
+    q /= (uint32_t)P.ksplit;
     st.g = (int)(q / (uint32_t)P.n_ntiles);
     st.nt = (int)(q - (uint32_t)st.g * (uint32_t)P.n_ntiles);
+    const Group& G = P.plan.groups[st.g];
+    const int per = (G.tap_count + P.ksplit - 1) / P.ksplit;
+    const int b = (int)ksp * per, e = b + per;
+    st.tap_begin = G.tap_begin + (b < G.tap_count ? b : G.tap_count);
+    st.tap_end = G.tap_begin + (e < G.tap_count ? e : G.tap_count);
 }
 
 // transpose-reduce: every lane holds v[0..31] (one row, 32 columns); afterwards lane L holds Σ_rows column L in v[0]
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
     const uint32_t n_spatial = num_spatial(P);
     const uint32_t Tn_ = (uint32_t)P.T;
     const uint32_t n_super = (n_spatial + Tn_ - 1) / Tn_;
-    const uint32_t nwork = n_super * (uint32_t)(p.n_groups * P.n_ntiles);
+    const uint32_t nwork = n_super * (uint32_t)(p.n_groups * P.n_ntiles * P.ksplit);
     // loop-invariant parameters, hoisted into registers
     const uint32_t stages = (uint32_t)P.stages, stage_bytes = P.stage_bytes, a_bytes = P.a_bytes, b_bytes = P.b_bytes;
     const uint32_t NT = (uint32_t)P.NT, kchunks = (uint32_t)P.kchunks, idesc = P.idesc;
@@ -232,8 +242,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                 }
                 const uint32_t tx_bytes = nv * a_bytes + P.b_tx;
                 const int ncol = st.nt * (int)NT;
-                const int tap_end = p.groups[st.g].tap_begin + p.groups[st.g].tap_count;
-                for (int ti = p.groups[st.g].tap_begin; ti < tap_end; ++ti) {
+                for (int ti = st.tap_begin; ti < st.tap_end; ++ti) {
                     const Tap tap = p.taps[ti];
                     const CUtensorMap* amap = &P.in_maps[tap.view];
                     for (uint32_t kc = 0; kc < kchunks; ++kc) {
@@ -261,16 +270,16 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
             const uint32_t desc_hi = (uint32_t)(umma_desc(0, 16, SBO, LAYOUT) >> 32);
             const uint32_t desc_lo_const = (uint32_t)(umma_desc(0, 16, SBO, LAYOUT) & 0xFFFFFFFFu);
             for (uint32_t w = blockIdx.x; w < nwork; w += gridDim.x, ++iter) {
-                const uint32_t q = w / n_super;
-                const uint32_t s0 = (w - q * n_super) * Tn_;
+                SuperTile st;
+                decode_super(P, w, n_super, st);
+                const uint32_t s0 = st.s0;
                 const uint32_t left = n_spatial - s0;
                 const uint32_t nv = left < Tn_ ? left : Tn_;
-                const int g = (int)(q / (uint32_t)P.n_ntiles);
                 const uint32_t acc = iter & 1u;
                 mbar_wait_u32(smem_u32(&tempty_bar[acc]), ((iter >> 1) & 1u) ^ 1u, 2);
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + acc * Tn_ * NT;
-                const uint32_t kblocks = (uint32_t)p.groups[g].tap_count * kchunks;
+                const uint32_t kblocks = (uint32_t)(st.tap_end - st.tap_begin) * kchunks;
                 for (uint32_t kb = 0; kb < kblocks; ++kb) {
                     mbar_wait_u32(full0 + stage * 8u, phase, 3);
                     tc_fence_after();
@@ -327,6 +336,26 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                 bf16* yrow = P.y + ov.base + (long)n * ov.sN + (long)z * ov.sD + (long)y * ov.sH + (long)x * ov.sW +
                              (long)st.nt * P.NT;
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (acc * Tn_ + t) * NT;
+                if (P.ksplit > 1) {
+                    // split-K: raw fp32 partial sums into the workspace (bias / mask / bf16 / Σ,Σ² happen in the finalise pass)
+                    if (st.tap_end > st.tap_begin) {
+                        float* wrow = P.ws + (yrow - P.y);
+                        for (int col = 0; col < P.NT; col += 16) {
+                            uint32_t r[16];
+                            tmem_ld_x16(t_addr + col, r);
+                            tmem_ld_wait();
+                            if (valid && on) {
+#pragma unroll
+                                for (int j = 0; j < 16; j += 4)
+                                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + col + j),
+                                                 "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])),
+                                                 "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                                                 : "memory");
+                            }
+                        }
+                    }
+                    continue;
+                }
                 for (int col = 0; col < P.NT; col += 32) {
                     uint32_t r[32];
                     const bool wide = (P.NT - col) >= 32;
@@ -406,6 +435,102 @@ static int pick_nt(int Cy) {
     return 0;
 }
 
+// tile box (128 voxels) and accumulator interleave of the per-tap kernel for a plan — shared by the launch and by
+// amb_conv_workspace_bytes()
+struct IgemmGeo {
+    int KC, NT, bw, bh, bd, bn, T;
+    long items;                      // work items without split-K
+    int max_taps;
+};
+static bool igemm_geometry(const Plan& p, IgemmGeo& g) {
+    if (p.Cx % 16 != 0 || p.Cy % 16 != 0) return false;
+    g.KC = p.Cx % 64 == 0 ? 64 : (p.Cx % 32 == 0 ? 32 : 16);
+    g.NT = pick_nt(p.Cy);
+    if (g.NT == 0) return false;
+    g.bw = pow2_ceil(p.oW) < 8 ? pow2_ceil(p.oW) : 8;
+    g.bh = pow2_ceil(p.oH) < 8 ? pow2_ceil(p.oH) : 8;
+    const int rem = 128 / (g.bw * g.bh);
+    g.bd = pow2_ceil(p.oD) < rem ? pow2_ceil(p.oD) : rem;
+    g.bn = rem / g.bd;
+    int T = 256 / g.NT;
+    if (T > 4) T = 4;
+    if (T < 1) T = 1;
+    const uint32_t a_bytes = 128u * g.KC * 2u, b_bytes = ((uint32_t)g.NT * g.KC * 2u + 1023u) & ~1023u;
+    while (T > 1 && 3u * (T * a_bytes + b_bytes) > 200u * 1024u) T >>= 1;
+    g.T = T;
+    const long tiles = (long)ceil_div(p.oN, g.bn) * ceil_div(p.oD, g.bd) * ceil_div(p.oH, g.bh) * ceil_div(p.oW, g.bw);
+    g.items = tiles * p.n_groups * (p.Cy / g.NT);       // split-K runs with T = 1 (one tile per work item)
+    g.max_taps = 0;
+    for (int i = 0; i < p.n_groups; ++i) if (p.groups[i].tap_count > g.max_taps) g.max_taps = p.groups[i].tap_count;
+    return true;
+}
+// taps split over this many work items (1 = no split): only when the tiles alone leave most SMs idle
+static int igemm_ksplit(const Plan& p, const IgemmGeo& g, bool sparse_list) {
+    if (getenv("AMB_NO_SPLITK") || sparse_list) return 1;
+    if (g.items * 2 > (long)num_sms() || (long)g.max_taps * (p.Cx / g.KC) < 16) return 1;
+    int ks = (int)((long)num_sms() / g.items);
+    if (ks > g.max_taps) ks = g.max_taps;
+    return ks < 2 ? 1 : ks;
+}
+long igemm_workspace_bytes(const Plan& p, bool sparse_list) {
+    IgemmGeo g;
+    if (!igemm_geometry(p, g) || igemm_ksplit(p, g, sparse_list) == 1) return 0;
+    long elems = 0;                                     // the workspace mirrors the output tensor's element offsets
+    for (int v = 0; v < p.n_out_views; ++v) {
+        const View& ov = p.out_views[v];
+        const long last = ov.base + (long)(ov.N - 1) * ov.sN + (long)(ov.D - 1) * ov.sD + (long)(ov.H - 1) * ov.sH +
+                          (long)(ov.W - 1) * ov.sW + p.Cy;
+        if (last > elems) elems = last;
+    }
+    return elems * 4;
+}
+
+// split-K finish: y = mask · act(ws · scale + bias) in bf16, Σy / Σy² per channel over the written values
+__global__ void __launch_bounds__(256) split_finalize_kernel(const float* __restrict__ ws, bf16* __restrict__ y, long voxels, int Cy,
+                                                             const float* __restrict__ bias, const float* __restrict__ ep_scale,
+                                                             int ep_act, const uint8_t* __restrict__ active, int lgP, int D, int H,
+                                                             int W, int fd, int fh, int fw, double* __restrict__ stats) {
+    extern __shared__ float s_acc[];                    // [2][Cy] when stats
+    const int CG = Cy / 8;
+    if (stats) for (int i = threadIdx.x; i < 2 * Cy; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+    const long total = voxels * CG;
+    for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(item % CG);
+        const long vox = item / CG;
+        bool on = true;
+        if (active) {
+            uint32_t t = (uint32_t)vox;
+            const uint32_t x = t % (uint32_t)W; t /= (uint32_t)W;
+            const uint32_t yy = t % (uint32_t)H; t /= (uint32_t)H;
+            const uint32_t z = t % (uint32_t)D;
+            const uint32_t n = t / (uint32_t)D;
+            on = active[((n * fd + (z >> lgP)) * fh + (yy >> lgP)) * fw + (x >> lgP)] != 0;
+        }
+        float v[8];
+        const float4 a0 = *reinterpret_cast<const float4*>(ws + vox * Cy + cg * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(ws + vox * Cy + cg * 8 + 4);
+        const float in[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cg * 8 + j;
+            v[j] = on ? ep_apply(in[j], ep_scale ? ep_scale[c] : 1.f, bias ? bias[c] : 0.f, ep_act) : 0.f;
+        }
+        store8(y + vox * Cy + cg * 8, v);
+        if (stats && on) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                atomicAdd(&s_acc[cg * 8 + j], v[j]);
+                atomicAdd(&s_acc[Cy + cg * 8 + j], v[j] * v[j]);
+            }
+        }
+    }
+    __syncthreads();
+    if (stats)
+        for (int i = threadIdx.x; i < 2 * Cy; i += blockDim.x)
+            if (s_acc[i] != 0.f) atomicAdd(&stats[i], (double)s_acc[i]);
+}
+
 int igemm_conv(const Plan& p, const amb_conv_args* a) {
     // shapes the tensor-core kernel takes
     if (p.Cx % 16 != 0 || p.Cy % 16 != 0) {
@@ -443,6 +568,17 @@ int igemm_conv(const Plan& p, const amb_conv_args* a) {
     const char* tenv = getenv("AMB_IGEMM_T");
     if (tenv && atoi(tenv) >= 1 && atoi(tenv) <= T) T = atoi(tenv);
     while (T > 1 && 3u * (T * P.a_bytes + P.b_bytes) > 200u * 1024u) T >>= 1;     // keep >= 3 pipeline stages
+    // split-K for the 8^3 / 16^3 stages: 16-64 tiles cannot fill 148 SMs and each of them walks all 27 (64) taps serially
+    P.ksplit = 1;
+    {
+        IgemmGeo geo;
+        const int ks = igemm_geometry(p, geo) ? igemm_ksplit(p, geo, use_list) : 1;
+        if (ks > 1 && a->workspace != nullptr && a->workspace_bytes >= igemm_workspace_bytes(p, use_list)) {
+            P.ksplit = ks;
+            P.ws = (float*)a->workspace;
+            T = 1;
+        }
+    }
     P.T = T;
     P.stage_bytes = (uint32_t)T * P.a_bytes + P.b_bytes;
     int stages = (int)((200u * 1024u) / P.stage_bytes);
@@ -469,7 +605,7 @@ int igemm_conv(const Plan& p, const amb_conv_args* a) {
 
     size_t smem = (size_t)P.stages * P.stage_bytes + 1024 + 256 + (a->stats ? 2 * (size_t)p.Cy * sizeof(float) : 0) +
                   2 * (size_t)p.Cy * sizeof(float);
-    long tiles_upper = (((long)P.Tn * P.Tz * P.Ty * P.Tx + T - 1) / T) * p.n_groups * P.n_ntiles;
+    long tiles_upper = (((long)P.Tn * P.Tz * P.Ty * P.Tx + T - 1) / T) * p.n_groups * P.n_ntiles * P.ksplit;
     int grid = (int)(tiles_upper < (long)num_sms() ? tiles_upper : (long)num_sms());
     cudaStream_t st = (cudaStream_t)a->stream;
     if (KC == 64) {
@@ -483,6 +619,22 @@ int igemm_conv(const Plan& p, const amb_conv_args* a) {
         igemm_kernel<16><<<grid, 256, smem, st>>>(P);
     }
     AMB_LAUNCH_CHECK();
+    if (P.ksplit > 1) {
+        // finish: the whole output tensor (dims of the FULL-resolution produced tensor, mask grid at that resolution)
+        int fD = a->D, fH = a->H, fW = a->W;
+        if (a->op == AMB_OP_CONV) { fD /= a->stride; fH /= a->stride; fW /= a->stride; }
+        if (a->op == AMB_OP_CONVT) { fD *= 2; fH *= 2; fW *= 2; }
+        const long voxels = (long)a->N * fD * fH * fW;
+        int lgP = 0;
+        if (a->active) while ((fD / a->fd) >> (lgP + 1)) lgP++;
+        const long items = voxels * (p.Cy / 8);
+        long blocks = (items + 255) / 256, cap = (long)num_sms() * 8;
+        if (blocks > cap) blocks = cap;
+        split_finalize_kernel<<<(int)blocks, 256, a->stats ? 2 * p.Cy * sizeof(float) : 0, st>>>(
+            P.ws, (bf16*)a->y, voxels, p.Cy, a->bias, a->ep_scale, a->ep_act, a->active, lgP, fD, fH, fW, a->fd, a->fh, a->fw,
+            a->stats);
+        AMB_LAUNCH_CHECK();
+    }
     g_last_conv_kernel = "igemm_kernel";
     return 1;
 }

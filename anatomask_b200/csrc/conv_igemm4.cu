@@ -357,7 +357,10 @@ int igemm4_conv(const Plan& p, const amb_conv_args* a) {
     if (env_int("AMB_DISABLE_V4", 0) == 1) return 0;
     if (!((a->op == AMB_OP_CONV || a->op == AMB_OP_CONV_DGRAD) && a->k == 3 && a->stride == 1)) return 0;
     if (p.Cx % 32 != 0 || p.Cy % 16 != 0 || p.n_taps != 27 || p.n_in_views != 1 || p.n_groups != 1) return 0;
-    if (p.Cy > 64) return 0;                          // one N tile: wider layers are tensor-bound in the per-tap kernel
+    // one N tile of Cy columns: T·Cy·2 <= 512 TMEM columns → Cy <= 64: T = 4 (6), Cy = 128: T = 2 (N = 128 / 256 MMAs),
+    // Cy = 256: T = 1 (no stacking left, but the halo planes still cut the operand traffic of the per-tap kernel 9x)
+    const int wide_max = env_int("AMB_V4_WIDE", 256);
+    if (p.Cy > 64 && !((p.Cy == 128 || p.Cy == 256) && p.Cy <= wide_max)) return 0;
     if (p.oH < 16 || p.oW < 8 || p.oD < 4) return 0;
     // active-patch work-list: usable when a patch holds whole 16 x 8 x 4 units; with a finer grid the per-tap kernel's list
     // (2 x 8 x 8 tiles) still pays, so leave those layers to it
@@ -370,6 +373,9 @@ int igemm4_conv(const Plan& p, const amb_conv_args* a) {
     int T = (NT <= 32 && !use_list && p.oD >= 12) ? 6 : 4;
     const int t_env = env_int("AMB_V4_T", 0);
     if (t_env == 4) T = 4;
+    if (NT == 128) T = 2;
+    if (NT == 256) T = 1;
+    if (use_list && T != 4) return 0;
 
     static Igemm4Params P;
     memset(&P, 0, sizeof(P));
@@ -392,7 +398,7 @@ int igemm4_conv(const Plan& p, const amb_conv_args* a) {
     P.b_bytes = (3u * P.blk_bytes + 1023u) & ~1023u;
     P.tmem_cols = 32;
     while (P.tmem_cols < (uint32_t)(2 * T * NT)) P.tmem_cols <<= 1;
-    for (int c = 1; c <= 3; ++c) P.idesc[c - 1] = umma_idesc_bf16(128, c * NT, 0, 0);
+    for (int c = 1; c <= 3; ++c) P.idesc[c - 1] = c * NT <= 256 ? umma_idesc_bf16(128, c * NT, 0, 0) : 0u;   // (c <= T)
     // in-plane taps in the order of the dz = -1 taps of the plan; the same (dy,dx) is then looked up for dz = 0, +1
     int n9 = 0;
     int8_t t_dy[9], t_dx[9];
@@ -450,6 +456,12 @@ int igemm4_conv(const Plan& p, const amb_conv_args* a) {
     if (T == 6) {
         AMB_CUDA(cudaFuncSetAttribute(igemm4_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         igemm4_kernel<6><<<grid, 256, smem, (cudaStream_t)a->stream>>>(P);
+    } else if (T == 2) {
+        AMB_CUDA(cudaFuncSetAttribute(igemm4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        igemm4_kernel<2><<<grid, 256, smem, (cudaStream_t)a->stream>>>(P);
+    } else if (T == 1) {
+        AMB_CUDA(cudaFuncSetAttribute(igemm4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        igemm4_kernel<1><<<grid, 256, smem, (cudaStream_t)a->stream>>>(P);
     } else {
         AMB_CUDA(cudaFuncSetAttribute(igemm4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         igemm4_kernel<4><<<grid, 256, smem, (cudaStream_t)a->stream>>>(P);

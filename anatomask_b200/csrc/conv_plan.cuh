@@ -184,6 +184,7 @@ static inline int plan_set_mask(Plan& p, int full_oD, int full_oH, int full_oW, 
 // implemented in conv_igemm.cu / conv_wgrad_tc.cu: return 1 when the tcgen05 path handled the call, 0 when the shape is
 // not supported by it (caller falls back to the CUDA-core kernel), <0 on error.
 int igemm_conv(const Plan& p, const amb_conv_args* a);
+long igemm_workspace_bytes(const Plan& p, bool sparse_list);
 int igemm3_conv(const Plan& p, const amb_conv_args* a);
 int igemm4_conv(const Plan& p, const amb_conv_args* a);
 int igemm_wgrad(const Plan& p, const amb_wgrad_args* a);

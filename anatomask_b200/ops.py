@@ -274,7 +274,11 @@ def _conv_call(op, impl, dims, Cin, Cout, k, stride, x, y, w, bias=None, m: Opti
                    m.list.data_ptr() if (m is not None and sparse) else 0,
                    m.count.data_ptr() if (m is not None and sparse) else 0,
                    0 if stats is None else stats.data_ptr(), 0 if ep_scale is None else ep_scale.data_ptr(), ep_act, 0,
-                   torch.cuda.current_stream().cuda_stream)
+                   0, 0, torch.cuda.current_stream().cuda_stream)
+    need = L.load().amb_conv_workspace_bytes(C.byref(a))       # > 0: small spatial extent, the kernel splits the taps over CTAs
+    if need > 0:
+        ws = torch.zeros(need // 4, dtype=torch.float32, device=y.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), need
     L.call('amb_conv', C.byref(a))
 
 

@@ -113,9 +113,15 @@ typedef struct amb_conv_args {
     const float* ep_scale;
     int ep_act;                 /* AMB_ACT_* */
     int pad_;
+    /* optional fp32 scratch, ZERO-INITIALISED by the caller, of amb_conv_workspace_bytes(a) bytes: layers whose output has
+     * too few 128-voxel tiles to fill the GPU (the 8³ / 16³ stages: 16-64 tiles for 148 SMs) split their taps over several
+     * CTAs, add fp32 partial sums into it and finish with one small pass (bias / mask / bf16 / Σ,Σ²).  NULL: no split. */
+    void* workspace;
+    long workspace_bytes;
     void* stream;
 } amb_conv_args;
 int amb_conv(const amb_conv_args* a);
+long amb_conv_workspace_bytes(const amb_conv_args* a);   /* 0 when the call would not split (pointers in `a` are not read) */
 
 /* weight gradient of CONV / CONVT: dw [taps][Cout][Cin] fp32 (accumulated into, caller zeroes), from the
  * operator's input x and output gradient dy, dims as in the table above.  With `active_list` only active

@@ -51,6 +51,8 @@ def test_norm_family(kw):
     dict(Cin=32, Cout=64, S=16, k=1, stride=2, impl=T), dict(Cin=64, Cout=64, S=16, k=1, impl=T),
     dict(Cin=64, Cout=64, S=32, impl=T), dict(Cin=64, Cout=32, S=24, impl=T),
     dict(Cin=64, Cout=64, S=18, impl=T), dict(Cin=32, Cout=16, S=20, impl=T), dict(Cin=128, Cout=64, S=32, N=1, impl=T),
+    # N-stacked halo kernel with wide outputs: Cout = 128 (2 tiles per unit, N = 128 / 256) and 256 (1 tile, N = 256)
+    dict(Cin=128, Cout=128, S=16, impl=T), dict(Cin=64, Cout=256, S=16, N=1, impl=T), dict(Cin=256, Cout=128, S=24, N=1, impl=T),
     # masked: active-tile work-list (patch edge >= 8) and dense tiles + epilogue mask (patch edge 4)
     dict(Cin=32, Cout=32, S=32, impl=T, masked=True), dict(Cin=64, Cout=64, S=16, impl=T, masked=True),
     dict(Cin=128, Cout=128, S=8, impl=T, masked=True), dict(Cin=32, Cout=64, S=32, stride=2, impl=T, masked=True),
