@@ -12,9 +12,6 @@
 //
 //   role 1 (Cx = Cy = 64): A = dY plane z shifted by −(dy,dx)   B = X tiles z−1, z, z+1       D[(tap, co), (dz, ci)]   N = 192
 //   role 2 (Cx = 64, Cy = 32): A = X plane z shifted by +(dy,dx)   B = dY tiles z−1, z, z+1   D[(tap, ci), (dz, co)]   N = 96
-//   role 1 with 32-channel planes (Cx = Cy = 32, encoder stage 0): the three sx windows of one sy stacked along M (4th atom
-//   discarded), N = 96, three units = 288 columns
-// Sparse encoder layers walk the active-patch work-list: a column is one patch deep (P steps + 2 halo tiles).
 //
 // TMEM holds 512 columns.  Role 1 needs 4.5 units of 192 columns, split over TWO CTA kinds of equal work so that both walk
 // the same voxels in lockstep and share them through L2: {pair, pair, pair₃·(dz −1,0)} and {pair, single, pair₃·(dz +1)}
@@ -41,7 +38,7 @@ struct NsUnit {
     int32_t lbo;                     // bytes between the two stacked windows
     int16_t blk0, nblk;              // N blocks (ring slots) blk0 .. blk0+nblk-1 of the (z−1, z, z+1) triple
     int16_t d_col, pad;
-    int16_t w[4][3];                 // weight slab per (atom, block), −1 = discarded
+    int16_t w[2][3];                 // weight slab per (atom, block), −1 = discarded
 };
 
 struct WgradNsParams {
@@ -57,9 +54,6 @@ struct WgradNsParams {
     int oD, Ty, Tx;
     uint32_t n_steps;
     int ksplit;
-    const int* list;                 // active-patch work-list (patch edge 2^lgPv >= 8): columns live inside visible patches and
-    const int* count;                // are one patch deep; nullptr = dense walk over full-depth columns
-    int lgPv, fd, fh, fw;
     float* dw;
 };
 
@@ -94,28 +88,12 @@ __global__ void __launch_bounds__(256, 1) wgrad_ns_kernel(const __grid_constant_
     const int batch = (int)(blockIdx.x % (uint32_t)P.n_batches);
     const uint32_t ks = blockIdx.x / (uint32_t)P.n_batches;
     const int unit_begin = P.batch_begin[batch], unit_count = P.batch_count[batch];
-    const uint32_t n_steps = P.list ? ((uint32_t)(*P.count) << (3 * P.lgPv - 6)) : P.n_steps;
-    const uint32_t s_begin = (uint32_t)((unsigned long long)n_steps * ks / (uint32_t)P.ksplit);
-    const uint32_t s_end = (uint32_t)((unsigned long long)n_steps * (ks + 1) / (uint32_t)P.ksplit);
-    const uint32_t oD = P.list ? (1u << P.lgPv) : (uint32_t)P.oD;        // steps per column
+    const uint32_t s_begin = (uint32_t)((unsigned long long)P.n_steps * ks / (uint32_t)P.ksplit);
+    const uint32_t s_end = (uint32_t)((unsigned long long)P.n_steps * (ks + 1) / (uint32_t)P.ksplit);
+    const uint32_t oD = (uint32_t)P.oD;
 
-    // a segment = the steps [z, zend) this CTA takes inside one column; (n, y0, x0) and the column's first plane z0
-    auto column = [&](uint32_t col, int& n0, int& y0, int& x0, int& z0) {
-        if (P.list) {
-            const uint32_t lt = (uint32_t)P.lgPv - 3u;                   // log2 of 8-voxel tiles per patch edge
-            const uint32_t tx = col & ((1u << lt) - 1u), ty = (col >> lt) & ((1u << lt) - 1u);
-            const uint32_t pid = (uint32_t)P.list[col >> (2u * lt)];
-            const uint32_t L = (uint32_t)(P.fd * P.fh * P.fw), hw = (uint32_t)(P.fh * P.fw);
-            const uint32_t n = pid / L, l = pid - n * L;
-            const uint32_t pz = l / hw, r2 = l - pz * hw;
-            const uint32_t py = r2 / (uint32_t)P.fw, px = r2 - py * (uint32_t)P.fw;
-            n0 = (int)n;
-            z0 = (int)(pz << P.lgPv);
-            y0 = (int)((py << P.lgPv) + ty * 8u);
-            x0 = (int)((px << P.lgPv) + tx * 8u);
-            return;
-        }
-        z0 = 0;
+    // a segment = the steps [z, zend) this CTA takes inside one column (n, y0, x0)
+    auto column = [&](uint32_t col, int& n0, int& y0, int& x0) {
         x0 = (int)(col % (uint32_t)P.Tx) * 8; col /= (uint32_t)P.Tx;
         y0 = (int)(col % (uint32_t)P.Ty) * 8;
         n0 = (int)(col / (uint32_t)P.Ty);
@@ -129,13 +107,13 @@ __global__ void __launch_bounds__(256, 1) wgrad_ns_kernel(const __grid_constant_
             const int z = (int)(s - col * oD);
             const uint32_t rem = s_end - s;
             const int zend = (oD - (uint32_t)z) < rem ? (int)oD : z + (int)rem;
-            int n0, y0, x0, z0;
-            column(col, n0, y0, x0, z0);
+            int n0, y0, x0;
+            column(col, n0, y0, x0);
             for (int zp = z; zp < zend; ++zp) {
                 mbar_wait(&a_empty[slot], phase ^ 1u, 51);
                 if (elect_one()) {
                     mbar_expect_tx(&a_full[slot], P.a_tx);
-                    tma_load_5d(a_ring + slot * P.a_slot_bytes, &P.a_map, &a_full[slot], 0, x0 - 1, y0 - 1, z0 + zp, n0);
+                    tma_load_5d(a_ring + slot * P.a_slot_bytes, &P.a_map, &a_full[slot], 0, x0 - 1, y0 - 1, zp, n0);
                 }
                 __syncwarp();
                 if (++slot == NS_A_SLOTS) { slot = 0; phase ^= 1u; }
@@ -150,17 +128,17 @@ __global__ void __launch_bounds__(256, 1) wgrad_ns_kernel(const __grid_constant_
             const int z = (int)(s - col * oD);
             const uint32_t rem = s_end - s;
             const int zend = (oD - (uint32_t)z) < rem ? (int)oD : z + (int)rem;
-            int n0, y0, x0, z0;
-            column(col, n0, y0, x0, z0);
+            int n0, y0, x0;
+            column(col, n0, y0, x0);
             for (int zp = z - 1; zp <= zend; ++zp, ++q) {
                 const uint32_t slot = q % NS_B_RING, phase = (q / NS_B_RING) & 1u;
                 mbar_wait(&b_empty[slot], phase ^ 1u, 52);
                 if (elect_one()) {
                     const bool mirror = slot < 2;
                     mbar_expect_tx(&b_full[slot], mirror ? 2u * P.b_slot_bytes : P.b_slot_bytes);
-                    tma_load_5d(b_ring + slot * P.b_slot_bytes, &P.b_map, &b_full[slot], 0, x0, y0, z0 + zp, n0);
+                    tma_load_5d(b_ring + slot * P.b_slot_bytes, &P.b_map, &b_full[slot], 0, x0, y0, zp, n0);
                     if (mirror)
-                        tma_load_5d(b_ring + (NS_B_RING + slot) * P.b_slot_bytes, &P.b_map, &b_full[slot], 0, x0, y0, z0 + zp, n0);
+                        tma_load_5d(b_ring + (NS_B_RING + slot) * P.b_slot_bytes, &P.b_map, &b_full[slot], 0, x0, y0, zp, n0);
                 }
                 __syncwarp();
             }
@@ -236,7 +214,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_ns_kernel(const __grid_constant_
         mbar_wait(acc_full, 0, 56);
         tc_fence_after();
         if (s_end > s_begin) {
-            const int atom = m / P.CA, r = m % P.CA;          // CA = 64: two atoms of 64 rows; CA = 32: four of 32
+            const int atom = m / P.CA, r = m % P.CA;          // CA = 64: two atoms of 64 rows
             for (int u = 0; u < unit_count; ++u) {
                 const NsUnit& U = P.units[unit_begin + u];
                 for (int blk = 0; blk < U.nblk; ++blk) {
@@ -278,16 +256,14 @@ __global__ void __launch_bounds__(256, 1) wgrad_ns_kernel(const __grid_constant_
 // returns 1 when handled, 0 when the shape is outside this kernel's scope, <0 on error
 int igemm_wgrad_ns(const Plan& p, const amb_wgrad_args* a) {
     if (getenv("AMB_DISABLE_WNS")) return 0;
-    if (a->op != AMB_OP_CONV) return 0;
-    const bool use_list = a->active_list != nullptr;
-    if (use_list && (p.lgPv < 3 || getenv("AMB_WNS_NO_LIST"))) return 0;
+    if (a->active_list != nullptr || a->op != AMB_OP_CONV) return 0;
     if (p.n_out_views != 1 || p.n_in_views != 1 || p.n_taps != 27) return 0;
     for (int i = 0; i < 27; ++i) {
         const Tap& T = p.taps[i];
         if (T.dz < -1 || T.dz > 1 || T.dy < -1 || T.dy > 1 || T.dx < -1 || T.dx > 1) return 0;
     }
     int role = 0;
-    if ((p.Cx == 64 && p.Cy == 64) || (p.Cx == 32 && p.Cy == 32)) role = 1;
+    if (p.Cx == 64 && p.Cy == 64) role = 1;
     else if (p.Cx == 64 && p.Cy == 32) role = 2;
     if (role == 0) return 0;
     if (p.oH % 8 != 0 || p.oW % 8 != 0 || p.oH < 16 || p.oW < 16 || p.oD < 4) return 0;
@@ -298,15 +274,15 @@ int igemm_wgrad_ns(const Plan& p, const amb_wgrad_args* a) {
     memset(&P, 0, sizeof(P));
     P.role = role;
     P.Cx = p.Cx; P.Cy = p.Cy;
-    P.CA = role == 1 ? p.Cy : p.Cx;               // plane operand: dY (role 1) or X (role 2); 64 channels = SW128 atoms, 32 = SW64
+    P.CA = 64;                                    // plane operand: dY (role 1) or X (role 2), 64 channels = one SW128 atom
     P.CB = role == 1 ? p.Cx : p.Cy;               // tile operand: X (64) or dY (32)
     const char* pwenv = getenv("AMB_WNS_PW");
     const int PW = (pwenv && atoi(pwenv) == 16) ? 16 : 10;
-    const uint32_t a_row = (uint32_t)P.CA * 2u, b_row = (uint32_t)P.CB * 2u;
+    const uint32_t a_row = 128u, b_row = (uint32_t)P.CB * 2u;
     P.a_tx = 10u * (uint32_t)PW * a_row;
     P.a_slot_bytes = (P.a_tx + 1023u) & ~1023u;
     P.b_slot_bytes = 64u * b_row;                 // 8 KB (64 ch) / 4 KB (32 ch)
-    P.a_layout = P.CA == 64 ? 2u : 4u;            // SW128 / SW64
+    P.a_layout = 2u;                              // SW128
     P.b_layout = P.CB == 64 ? 2u : 4u;            // SW128 / SW64
     P.a_sbo = (uint32_t)PW * a_row;               // next 8-voxel group = next y row of the plane
     P.a_kstep = 2u * P.a_sbo;                     // K16 = two y rows
@@ -315,9 +291,6 @@ int igemm_wgrad_ns(const Plan& p, const amb_wgrad_args* a) {
     for (int nb = 1; nb <= 3; ++nb) P.idesc[nb - 1] = umma_idesc_bf16(128, nb * P.CB, 1, 1);
     P.oD = p.oD; P.Ty = p.oH / 8; P.Tx = p.oW / 8;
     P.dw = a->dw;
-    P.list = use_list ? a->active_list : nullptr;
-    P.count = use_list ? a->active_count : nullptr;
-    P.lgPv = p.lgPv; P.fd = p.fd; P.fh = p.fh; P.fw = p.fw;
 
     // in-plane taps sorted by window offset; sign = −1: the plane operand is dY (window shifted against the tap), +1: X
     const int sign = role == 1 ? -1 : 1;
@@ -333,42 +306,37 @@ int igemm_wgrad_ns(const Plan& p, const amb_wgrad_args* a) {
     // N block j of the (z−1, z, z+1) tile triple ↔ dz = j − 1 (role 1: X tile at z + dz) or 1 − j (role 2: dY tile at z − dz)
     auto dz_of_block = [&](int j) { return role == 1 ? j - 1 : 1 - j; };
     int nu = 0;
-    // a unit stacks `nat` windows i0, i0 + step, ... along M (equidistant: LBO = their distance); the other atoms are discarded
-    auto add_unit = [&](int i0, int nat, int step, int blk0, int nblk, int d_col) {
+    auto add_unit = [&](int i0, int i1, int blk0, int nblk, int d_col) {
         NsUnit& U = P.units[nu++];
         U.off = win_off(i0);
-        U.lbo = nat > 1 ? win_off(i0 + step) - win_off(i0) : (int)a_row;
+        U.lbo = i1 >= 0 ? win_off(i1) - win_off(i0) : (int)a_row;
         U.blk0 = (int16_t)blk0; U.nblk = (int16_t)nblk; U.d_col = (int16_t)d_col;
-        for (int at = 0; at < 4; ++at)
-            for (int b = 0; b < 3; ++b)
-                U.w[at][b] = (int16_t)((at < nat && b < nblk) ? slab(i0 + at * step, dz_of_block(blk0 + b)) : -1);
+        for (int at = 0; at < 2; ++at)
+            for (int b = 0; b < 3; ++b) {
+                const int i = at == 0 ? i0 : i1;
+                U.w[at][b] = (int16_t)((i >= 0 && b < nblk) ? slab(i, dz_of_block(blk0 + b)) : -1);
+            }
     };
     const int W3 = 3 * P.CB;
-    if (P.CA == 32) {                             // three sx windows per sy: 3 units of 96 columns, one CTA kind
-        P.n_batches = 1;
-        P.batch_begin[0] = 0;
-        for (int i = 0; i < 3; ++i) add_unit(3 * i, 3, 1, 0, 3, i * W3);
-        P.batch_count[0] = 3;
-    } else if (role == 1) {
+    if (role == 1) {
         P.n_batches = 2;
         P.batch_begin[0] = 0;
-        add_unit(0, 2, 1, 0, 3, 0); add_unit(2, 2, 1, 0, 3, W3); add_unit(4, 2, 1, 0, 2, 2 * W3);
+        add_unit(0, 1, 0, 3, 0); add_unit(2, 3, 0, 3, W3); add_unit(4, 5, 0, 2, 2 * W3);
         P.batch_count[0] = 3;
         P.batch_begin[1] = 3;
-        add_unit(6, 2, 1, 0, 3, 0); add_unit(8, 1, 1, 0, 3, W3); add_unit(4, 2, 1, 2, 1, 2 * W3);
+        add_unit(6, 7, 0, 3, 0); add_unit(8, -1, 0, 3, W3); add_unit(4, 5, 2, 1, 2 * W3);
         P.batch_count[1] = 3;
     } else {
         P.n_batches = 1;
         P.batch_begin[0] = 0;
-        for (int i = 0; i < 4; ++i) add_unit(2 * i, 2, 1, 0, 3, i * W3);
-        add_unit(8, 1, 1, 0, 3, 4 * W3);
+        for (int i = 0; i < 4; ++i) add_unit(2 * i, 2 * i + 1, 0, 3, i * W3);
+        add_unit(8, -1, 0, 3, 4 * W3);
         P.batch_count[0] = 5;
     }
-    int n_slabs_covered = 0;
     for (int u = 0; u < nu; ++u)
-        for (int at = 0; at < 4; ++at)
-            for (int b = 0; b < 3; ++b) n_slabs_covered += P.units[u].w[at][b] >= 0;
-    if (n_slabs_covered != 27) { set_error("wgrad ns: %d of 27 taps covered", n_slabs_covered); return -1; }
+        for (int at = 0; at < 2; ++at)
+            for (int b = 0; b < P.units[u].nblk; ++b)
+                if (P.units[u].w[at][b] < 0 && !(at == 1 && u == (role == 1 ? 4 : 4))) { set_error("wgrad ns: tap lookup failed"); return -1; }
 
     const int abox[4] = {1, 1, 10, PW}, bbox[4] = {1, 1, 8, 8};
     const void* a_t = role == 1 ? a->dy : a->x;
@@ -378,7 +346,7 @@ int igemm_wgrad_ns(const Plan& p, const amb_wgrad_args* a) {
     if (int e = encode_view_map(&P.a_map, a_t, av, P.CA, P.CA, abox)) return e;
     if (int e = encode_view_map(&P.b_map, b_t, bv, P.CB, P.CB, bbox)) return e;
 
-    const long steps = use_list ? ((long)p.oN * p.fd * p.fh * p.fw << (3 * p.lgPv - 6)) : (long)p.oN * P.Ty * P.Tx * p.oD;
+    const long steps = (long)p.oN * P.Ty * P.Tx * p.oD;
     if (steps >= (1L << 31)) return 0;
     P.n_steps = (uint32_t)steps;
     int ksplit = num_sms() / P.n_batches;

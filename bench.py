@@ -365,7 +365,21 @@ def run_ours(args):
             out['cpu_baseline'] = cpu_baseline_sample()
         print(json.dumps(out))
     if world > 1:
-        dist.destroy_process_group()
+        _hard_exit(dist, dev)
+
+
+def _hard_exit(dist, dev):
+    """Multi-rank teardown.  The step graph holds captured NCCL kernels; `destroy_process_group()` (and the interpreter's
+    own teardown of the communicator) was observed to block forever after the JSON line had been printed (round 2, 2 GPUs,
+    both bench.py and tests/dist_checks.py sat in it until the outer timeout).  All ranks meet at a barrier with their
+    streams drained — nothing is in flight any more — and then leave without running NCCL's destructors."""
+    torch.cuda.synchronize()
+    t = torch.zeros(1, device=dev)
+    dist.all_reduce(t)
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == '__main__':

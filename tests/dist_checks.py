@@ -143,9 +143,16 @@ def main():
         f'oracle grads: worst rel {worst4:.3e}; ok={ok4}')
     same4 = _same_on_all_ranks(torch.cat([p.detach().flatten() for p in params_req_grad]))
     say(f'RESULT script-level DDP step: params identical across ranks after optimizer.step()={same4}')
+    ok = bool(ok1 and ok2 and ok3 and ok4 and same4)
+    say(f'RESULT all ok={ok}')
+    # the step graphs hold captured NCCL kernels: destroy_process_group() blocks forever behind them (seen on 2 GPUs), so
+    # every rank drains its streams, meets the others once more and leaves without running NCCL's destructors
+    torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()
-    assert ok1 and ok2 and ok3 and ok4 and same4
+    torch.cuda.synchronize()
+    import os, sys
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(0 if ok else 1)
 
 
 def st_flat(eng, st):
