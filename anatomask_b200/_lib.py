@@ -71,6 +71,19 @@ _SIGNATURES = {
     'amb_ema_update': (i32, [vp, vp, i64, f64, vp]),
     'amb_sumsq': (i32, [vp, i64, vp, vp]),
     'amb_adamw_step': (i32, [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i32, vp, f64, f64, vp]),
+    'amb_voxel_norm_fwd': (i32, [C.POINTER(Geo), vp, vp, vp, i32, f32, vp, vp]),
+    'amb_voxel_norm_bwd': (i32, [C.POINTER(Geo), vp, vp, vp, i32, f32, vp, vp, vp, vp]),
+    'amb_pool3d_fwd': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
+    'amb_pool3d_bwd': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
+    'amb_masked_mean_fwd': (i32, [C.POINTER(Geo), vp, vp, vp]),
+    'amb_masked_mean_bwd': (i32, [C.POINTER(Geo), vp, vp, vp]),
+    'amb_dwconv3d': (i32, [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
+    'amb_dwconv3d_wgrad': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
+    'amb_gelu': (i32, [vp, vp, vp, i64, vp]),
+    'amb_layer_scale': (i32, [C.POINTER(Geo), vp, vp, vp, vp, vp, vp, vp]),
+    'amb_aug_spline_prefilter': (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp]),
+    'amb_aug_resample': (i32, [vp, i32, i32, i32, C.POINTER(f64), C.POINTER(i32), f32, vp, i32, i32, i32, vp]),
+    'amb_aug_crop_mirror': (i32, [vp, i32, i32, i32, i32, i32, i32, C.POINTER(i32), vp, i32, i32, i32, vp]),
 }
 
 EXPORTED = tuple(_SIGNATURES.keys())

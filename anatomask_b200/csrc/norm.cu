@@ -5,7 +5,7 @@
 
 namespace amb {
 
-static int make_geo(const amb_geo* a, Geo& g) {
+int make_geo(const amb_geo* a, Geo& g) {
     AMB_CHECK(a != nullptr, AMB_ERR_ARG, "geo is null");
     AMB_CHECK(a->C % 8 == 0 && a->C >= 8, AMB_ERR_ARG, "C=%d must be a multiple of 8", a->C);
     AMB_CHECK(a->fd > 0 && a->D % a->fd == 0 && a->H % a->fh == 0 && a->W % a->fw == 0, AMB_ERR_ARG,

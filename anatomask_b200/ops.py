@@ -722,3 +722,181 @@ def adamw_step_(p, g, m, v, lr, betas, eps, wd, step, max_norm: Optional[float],
     L.call('amb_adamw_step', _p(p), _p(g), _p(m), _p(v), p.numel(), lr, betas[0], betas[1], eps, wd, step, _p(gn),
            0.0 if max_norm is None else float(max_norm), float(gscale), _stream())
     return gn
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# remaining sparse-layer API: per-voxel group / layer norm, masked pooling, depthwise conv, GELU,
+# layer scale — the pieces of P/encoder3D.py:30-37,47-78,181-279 the MedNeXt / ConvNeXt heads use
+# ----------------------------------------------------------------------------------------------------------------
+class VoxelNormFn(torch.autograd.Function):
+    """SparseGroupNorm / SparseConvNeXtLayerNorm: every visible voxel normalised over each channel group
+    (P/encoder3D.py:61-68,205-225: nn.GroupNorm / nn.LayerNorm applied to the (N_active, C) matrix of visible voxels)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, m: MaskCtx):
+        require_cuda(x)
+        x = x.contiguous()
+        out = torch.zeros_like(x) if m is not None else torch.empty_like(x)
+        g = m.geo(x, True) if m is not None else dense_geo(x)
+        L.call('amb_voxel_norm_fwd', C.byref(g), _p(x), _p(gamma), _p(beta), groups, eps, _p(out), _stream())
+        ctx.save_for_backward(x, gamma)
+        ctx.cfg = (groups, eps, m)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, gamma = ctx.saved_tensors
+        groups, eps, m = ctx.cfg
+        dout = dout.contiguous()
+        dx = torch.zeros_like(x) if m is not None else torch.empty_like(x)
+        gb = torch.zeros(2 * x.shape[-1], dtype=torch.float32, device=x.device)
+        Cc = x.shape[-1]
+        g = m.geo(x, True) if m is not None else dense_geo(x)
+        L.call('amb_voxel_norm_bwd', C.byref(g), _p(dout), _p(x), _p(gamma), groups, eps, _p(dx), _p(gb[:Cc]), _p(gb[Cc:]),
+               _stream())
+        return dx, gb[:Cc], gb[Cc:], None, None, None
+
+
+class PoolFn(torch.autograd.Function):
+    """nn.MaxPool3d / nn.AvgPool3d followed by the mask multiply at the output resolution (P/encoder3D.py:12-15,31-36)."""
+
+    @staticmethod
+    def forward(ctx, x, k, s, p, mode, include_pad, divisor, m: Optional[MaskCtx]):
+        require_cuda(x)
+        x = x.contiguous()
+        N, D, H, W, Cc = x.shape
+        od, oh, ow = ((v + 2 * p - k) // s + 1 for v in (D, H, W))
+        y = torch.empty((N, od, oh, ow, Cc), dtype=bf16, device=x.device)
+        mk = (_p(m.active), m.fd, m.fh, m.fw) if m is not None else (C.c_void_p(0), 1, 1, 1)
+        L.call('amb_pool3d_fwd', _p(x), _p(y), N, D, H, W, Cc, k, s, p, mode, int(include_pad), int(divisor or 0), *mk, _stream())
+        ctx.save_for_backward(x)
+        ctx.cfg = (k, s, p, mode, include_pad, divisor, m)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        k, s, p, mode, include_pad, divisor, m = ctx.cfg
+        N, D, H, W, Cc = x.shape
+        dx = torch.empty_like(x)
+        mk = (_p(m.active), m.fd, m.fh, m.fw) if m is not None else (C.c_void_p(0), 1, 1, 1)
+        L.call('amb_pool3d_bwd', _p(x), _p(dy.contiguous()), _p(dx), N, D, H, W, Cc, k, s, p, mode, int(include_pad),
+               int(divisor or 0), *mk, _stream())
+        return dx, None, None, None, None, None, None, None
+
+
+class MaskedMeanFn(torch.autograd.Function):
+    """SparseAdaptiveAvgPooling(1): Σ x·mask / (Σ mask + 1e-6) → (N, C) fp32 (P/encoder3D.py:186-190)."""
+
+    @staticmethod
+    def forward(ctx, x, m: MaskCtx):
+        require_cuda(x)
+        x = x.contiguous()
+        mean = torch.empty((x.shape[0], x.shape[-1]), dtype=torch.float32, device=x.device)
+        L.call('amb_masked_mean_fwd', C.byref(m.geo(x, False)), _p(x), _p(mean), _stream())
+        ctx.m, ctx.shape = m, x.shape
+        return mean
+
+    @staticmethod
+    def backward(ctx, dmean):
+        dx = torch.empty(ctx.shape, dtype=bf16, device=dmean.device)
+        g = L.Geo(*ctx.shape, ctx.m.fd, ctx.m.fh, ctx.m.fw, ctx.m.active.data_ptr(), 0, 0)
+        L.call('amb_masked_mean_bwd', C.byref(g), _p(dmean.float().contiguous()), _p(dx), _stream())
+        return dx, None
+
+
+class DepthwiseConvFn(torch.autograd.Function):
+    """nn.Conv3d(C, C, k, stride, padding=k//2, groups=C) · mask — SparseConv3d on a depthwise layer
+    (SparseConvNeXtBlock.dwconv P/encoder3D.py:259; MedNeXtBlock.conv1 P/MedNeXt_head.py:255-262,339-346)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, k, stride, m: Optional[MaskCtx]):
+        require_cuda(x)
+        x = x.contiguous()
+        N, D, H, W, Cc = x.shape
+        y = torch.empty((N, D // stride, H // stride, W // stride, Cc), dtype=bf16, device=x.device)
+        mk = (_p(m.active), m.fd, m.fh, m.fw) if m is not None else (C.c_void_p(0), 1, 1, 1)
+        w = weight.detach().float().contiguous()
+        L.call('amb_dwconv3d', L.OP_CONV, _p(x), _p(w), _p(None if bias is None else bias.detach().float().contiguous()), _p(y),
+               N, D, H, W, Cc, k, stride, *mk, _stream())
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (k, stride, m, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        k, stride, m, has_bias = ctx.cfg
+        dy = dy.contiguous()
+        N, D, H, W, Cc = x.shape
+        mk = (_p(m.active), m.fd, m.fh, m.fw) if m is not None else (C.c_void_p(0), 1, 1, 1)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            L.call('amb_dwconv3d', L.OP_CONV_DGRAD, _p(dy), _p(w), C.c_void_p(0), _p(dx), N, D, H, W, Cc, k, stride, *mk, _stream())
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros_like(w)
+            L.call('amb_dwconv3d_wgrad', _p(x), _p(dy), _p(dw), N, D, H, W, Cc, k, stride, *mk, _stream())
+        if has_bias and ctx.needs_input_grad[2]:
+            db = column_sums(dy, m)          # Σ over visible outputs (the mask multiply's backward)
+        return dx, dw, db, None, None, None
+
+
+class GeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        require_cuda(x)
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        L.call('amb_gelu', _p(x), C.c_void_p(0), _p(out), x.numel(), _stream())
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        L.call('amb_gelu', _p(x), _p(dout.contiguous()), _p(dx), x.numel(), _stream())
+        return dx
+
+
+class LayerScaleFn(torch.autograd.Function):
+    """out = inp + mask·γ_c·x — the tail of SparseConvNeXtBlock (P/encoder3D.py:270-279); m None = no mask, gamma None = 1."""
+
+    @staticmethod
+    def forward(ctx, inp, x, gamma, m: Optional[MaskCtx]):
+        require_cuda(x)
+        inp, x = inp.contiguous(), x.contiguous()
+        out = torch.empty_like(x)
+        g = m.geo(x, False) if m is not None else dense_geo(x)
+        L.call('amb_layer_scale', C.byref(g), _p(inp), _p(x), _p(gamma), C.c_void_p(0), _p(out), C.c_void_p(0), _stream())
+        ctx.save_for_backward(x, gamma)
+        ctx.m = m
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, gamma = ctx.saved_tensors
+        m = ctx.m
+        dout = dout.contiguous()
+        dxb = torch.empty_like(x)
+        dg = torch.zeros(x.shape[-1], dtype=torch.float32, device=x.device) if gamma is not None else None
+        g = m.geo(x, False) if m is not None else dense_geo(x)
+        L.call('amb_layer_scale', C.byref(g), C.c_void_p(0), _p(x), _p(gamma), _p(dout), _p(dxb), _p(dg), _stream())
+        return dout, dxb, dg, None
+
+
+def voxel_norm(x, gamma, beta, groups, eps, m):
+    return VoxelNormFn.apply(x, gamma, beta, groups, eps, m)
+
+
+def pool3d(x, k, s, p, mode, m=None, include_pad=True, divisor=None):
+    return PoolFn.apply(x, k, s, p, mode, include_pad, divisor, m)
+
+
+def depthwise_conv3d(x, weight, bias, k, stride, m=None):
+    return DepthwiseConvFn.apply(x, weight, bias, k, stride, m)
+
+
+def gelu(x):
+    return GeluFn.apply(x)

@@ -229,6 +229,64 @@ int amb_adamw_step(float* p, const float* g, float* m, float* v, long n, double 
 int amb_step_dev(float* ema, const float* model, long n_ema, float* p, const float* g, float* m, float* v, long n_live,
                  const float* hyper, const double* gnorm_sq, int do_adamw, int do_ema, void* stream);
 
+/* ---- remaining sparse-layer API (the MedNeXt / ConvNeXt heads) -------------------------------------
+ * voxel norm: SparseGroupNorm / SparseConvNeXtLayerNorm — P/encoder3D.py:47-78,193-243.  The reference hands the visible
+ * voxels to nn.GroupNorm / nn.LayerNorm as an (N_active, C) matrix, so every voxel is normalised on its own over each of
+ * `groups` channel groups (LayerNorm: groups = 1; biased variance) followed by the per-channel affine.  With `active_list`
+ * only visible voxels are visited (caller zero-fills `out`); with `active` alone masked voxels are written as zero.
+ * Channels per group: 1, 2, 4 or a multiple of 8; C <= 1024.  bwd: dgamma / dbeta fp32[C] are ACCUMULATED into.          */
+int amb_voxel_norm_fwd(const amb_geo* g, const void* x, const float* gamma, const float* beta, int groups, float eps,
+                       void* out, void* stream);
+int amb_voxel_norm_bwd(const amb_geo* g, const void* dout, const void* x, const float* gamma, int groups, float eps,
+                       void* dx, float* dgamma, float* dbeta, void* stream);
+/* SparseMaxPooling / SparseAvgPooling — P/encoder3D.py:31-36: nn.MaxPool3d (mode 0) / nn.AvgPool3d (mode 1) with cubic
+ * kernel k, stride, pad (floor mode), then · mask at the OUTPUT resolution (`active` (N,fd,fh,fw), NULL = none).
+ * bwd is the gather form (deterministic); max routes to the first maximum in scan order like torch.                       */
+int amb_pool3d_fwd(const void* x, void* y, int N, int D, int H, int W, int C, int k, int stride, int pad, int mode,
+                   int count_include_pad, int divisor_override, const uint8_t* active, int fd, int fh, int fw, void* stream);
+int amb_pool3d_bwd(const void* x, const void* dy, void* dx, int N, int D, int H, int W, int C, int k, int stride, int pad,
+                   int mode, int count_include_pad, int divisor_override, const uint8_t* active, int fd, int fh, int fw,
+                   void* stream);
+/* SparseAdaptiveAvgPooling(1) — P/encoder3D.py:181-190: mean[n][c] = Σ x·mask / (Σ mask + 1e-6)                          */
+int amb_masked_mean_fwd(const amb_geo* g, const void* x, float* mean, void* stream);
+int amb_masked_mean_bwd(const amb_geo* g, const float* dmean, void* dx, void* stream);
+/* depthwise k³ convolution (groups = C; k in {3,5,7}, stride 1/2, pad k/2) — SparseConvNeXtBlock.dwconv P/encoder3D.py:259,
+ * MedNeXtBlock.conv1 P/MedNeXt_head.py:255-262,339-346.  w = the layer's fp32 weight (C,1,k,k,k).
+ *   op AMB_OP_CONV       x (N,D,H,W,C) → y (N,D/s,H/s,W/s,C) = (conv + bias) · mask(output resolution)
+ *   op AMB_OP_CONV_DGRAD x = dy (output resolution) → y = dx (N,D,H,W,C)
+ * wgrad: dw (C,1,k,k,k) fp32 accumulated into; outputs of masked patches are skipped (dy is zero there).                  */
+int amb_dwconv3d(int op, const void* x, const float* w, const float* bias, void* y, int N, int D, int H, int W, int C,
+                 int k, int stride, const uint8_t* active, int fd, int fh, int fw, void* stream);
+int amb_dwconv3d_wgrad(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int C, int k, int stride,
+                       const uint8_t* active, int fd, int fh, int fw, void* stream);
+/* exact GELU (nn.GELU()): dout == NULL → out = gelu(x); else out = dout · gelu'(x).  n bf16 elements, n % 8 == 0            */
+int amb_gelu(const void* x, const void* dout, void* out, long n, void* stream);
+/* ConvNeXt tail P/encoder3D.py:270-279: dout == NULL → out = inp + mask·γ_c·x; else out = mask·γ_c·dout (the branch
+ * gradient; the skip gradient is dout itself) and dgamma[c] += Σ mask·dout·x.  gamma NULL = 1.                             */
+int amb_layer_scale(const amb_geo* g, const void* inp, const void* x, const float* gamma, const void* dout, void* out,
+                    float* dgamma, void* stream);
+
+/* ---- device-side input pipeline ---------------------------------------------------------------------
+ * Replaces, per sample, nnUNetDataLoader3D.generate_train_batch's crop + zero padding (N/training/dataloading/
+ * data_loader_3d.py:22-49) and the transforms of P/pretrain_AntoMask.py:79-113 as the scripts configure them:
+ * batchgenerators SpatialTransform (rotation + isotropic scale about the patch centre, order-3 spline = scipy.ndimage.
+ * map_coordinates(order=3, mode='constant', cval=0), centre crop when nothing is drawn) and MirrorTransform.
+ * A case volume is a single-channel fp32 array (sD, sH, sW) resident in HBM; (lb_z, lb_y, lb_x) is the bounding box's lower
+ * corner in case coordinates (may be negative / reach beyond the case: zero padding).
+ *   amb_aug_spline_prefilter  cubic B-spline coefficients of the (pD,pH,pW) initial patch (mirror boundary at the patch
+ *                             edges, like scipy's spline_filter under mode='constant'); `scratch` is a second patch-sized buffer
+ *   amb_aug_resample          out[o] = spline(coef, (o − (O−1)/2)·M + (P/2 − ½)) or cval outside [0, P−1]; matrix9 (host, row-major
+ *                             M[i][j], batchgenerators' row-vector convention: rotation R = Rx·Ry·Rz times the scale);
+ *                             mirror3 (host) flips the written axis
+ *   amb_aug_crop_mirror       no rotation / scale drawn: out = case[lb + o] (zero padded), mirrored — `lb` here is the lower
+ *                             corner of the FINAL patch (bbox corner + (P − O) / 2, batchgenerators center_crop_aug)            */
+int amb_aug_spline_prefilter(const float* src, int sD, int sH, int sW, int lb_z, int lb_y, int lb_x, float* coef, float* scratch,
+                             int pD, int pH, int pW, void* stream);
+int amb_aug_resample(const float* coef, int pD, int pH, int pW, const double* matrix9, const int* mirror3, float cval, float* out,
+                     int oD, int oH, int oW, void* stream);
+int amb_aug_crop_mirror(const float* src, int sD, int sH, int sW, int lb_z, int lb_y, int lb_x, const int* mirror3, float* out,
+                        int oD, int oH, int oW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

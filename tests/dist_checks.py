@@ -150,7 +150,6 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
-    import os, sys
     sys.stdout.flush(); sys.stderr.flush()
     os._exit(0 if ok else 1)
 

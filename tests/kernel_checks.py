@@ -8,6 +8,7 @@ from __future__ import annotations
 import json
 import sys
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -454,3 +455,159 @@ if __name__ == '__main__':
     kwargs = json.loads(sys.argv[2]) if len(sys.argv) > 2 else {}
     out = CHECKS[name](**kwargs)
     print('RESULT', name, json.dumps(kwargs), json.dumps(out))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# remaining sparse-layer API: the CUDA modules against the oracle port on the seeded cases of
+# oracle/sparse_layers_port.py (whose reference results are committed in tests/golden/sparse_layers.pt)
+# ----------------------------------------------------------------------------------------------------------------
+def build_sparse_layer_module(name):
+    """Our module for a case, built the way a user of the reference would build it (incl. dense_model_to_sparse)."""
+    import torch.nn as nn
+    from anatomask_b200 import encoder3D as enc, MedNeXt_head as mh
+    from oracle import sparse_layers_port as sl
+    kind, opt = sl.CASES[name]
+    Cc = sl.CASE_C
+    if kind == 'group_norm':
+        return enc.SparseGroupNorm(opt['groups'], Cc, eps=1e-5)
+    if kind == 'layer_norm':
+        return enc.SparseConvNeXtLayerNorm(Cc, eps=1e-6, data_format=opt['fmt'], sparse=opt.get('sparse', True))
+    if kind == 'pool':
+        if opt['mode'] == 'max':
+            return enc.SparseMaxPooling(opt['k'], opt['s'], opt['p'])
+        return enc.SparseAvgPooling(opt['k'], opt['s'], opt['p'], count_include_pad=opt.get('include_pad', True))
+    if kind == 'adaptive_avg':
+        return enc.SparseEncoder.dense_model_to_sparse(nn.AdaptiveAvgPool3d(1))
+    if kind == 'dwconv':
+        return enc.SparseEncoder.dense_model_to_sparse(nn.Conv3d(Cc, Cc, opt['k'], opt['s'], opt['k'] // 2, groups=Cc))
+    if kind == 'convnext':
+        m = enc.SparseConvNeXtBlock(Cc, drop_path=0., layer_scale_init_value=0.5, sparse=True, ks=7)
+        return enc.SparseEncoder.dense_model_to_sparse(m) if opt['converted'] else m
+    if kind == 'mednext':
+        blk = mh.MedNeXtDownBlock(Cc, 2 * Cc, exp_r=2, kernel_size=3, do_res=True, norm_type='group') if opt['down'] else \
+            mh.MedNeXtBlock(Cc, Cc, exp_r=2, kernel_size=3, do_res=True, norm_type='group')
+        return enc.SparseEncoder.dense_model_to_sparse(blk)
+    raise KeyError(kind)
+
+
+def check_sparse_layer_case(name, tol=1.5e-2):
+    from anatomask_b200 import encoder3D as enc
+    from oracle import sparse_layers_port as sl
+    dev = _dev()
+    kind, opt = sl.CASES[name]
+    m = build_sparse_layer_module(name)
+    x, active, g = sl.case_inputs(name)
+    params = sl.case_params({k: tuple(v.shape) for k, v in m.named_parameters()}, g)
+    # oracle (CPU fp32) on the same bf16-exact inputs and parameters
+    xr = x.clone().requires_grad_(True)
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    yr = sl.run_case(name, pr, xr, active)
+    dy = sl.case_dy(yr.shape, name)
+    yr.backward(dy)
+    for k, p in m.named_parameters():
+        p.data.copy_(params[k])
+    m = m.to(dev).train()
+    enc._cur_active = active.to(dev)
+    xc = x.to(dev).requires_grad_(True)
+    y = m(xc)
+    y.backward(dy.to(dev).to(y.dtype))
+    torch.cuda.synchronize()
+    res = {'y': _rel(y.float().cpu(), yr.detach()), 'dx': _rel(xc.grad.float().cpu(), xr.grad)}
+    for k, p in m.named_parameters():
+        if pr[k].grad is not None:
+            assert p.grad is not None, f'{name}: no gradient for {k}'
+            res['d' + k] = _rel(p.grad.float().cpu(), pr[k].grad)
+    if kind in ('group_norm', 'layer_norm', 'dwconv', 'pool') and opt.get('sparse', True):
+        fmt_last = kind == 'layer_norm' and opt['fmt'] == 'channels_last'
+        yy = y.permute(0, 4, 1, 2, 3) if fmt_last else y
+        up = sl.expand_mask(active, yy.shape[2:]).to(dev)
+        assert float((yy.float().abs() * (~up)).max()) == 0.0, f'{name}: masked voxels must stay exactly zero'
+    bad = {k: v for k, v in res.items() if not (v < tol)}
+    assert not bad, f'sparse layer case {name}: {res}'
+    return res
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# device-side input pipeline (SURVEY §8f row 2) against the numpy / scipy restatement of the reference's CPU pipeline
+# ----------------------------------------------------------------------------------------------------------------
+def _synthetic_case(shape, seed):
+    """CT-like test volume: smooth structures + noise, fp32."""
+    g = np.random.RandomState(seed)
+    z, y, x = np.meshgrid(*[np.linspace(-1, 1, s) for s in shape], indexing='ij')
+    vol = np.sin(3.1 * x + 1.7 * y) * np.cos(2.3 * z - 0.4 * x) + 0.5 * np.exp(-4 * (x ** 2 + y ** 2 + z ** 2))
+    return (vol + 0.3 * g.standard_normal(shape)).astype(np.float32)
+
+
+def check_augment(patch=48, seed=0, tol=3e-4):
+    """Every branch of the pipeline on forced parameters (no draw, rotation, zoom in / out, both, all mirror flips, bounding
+    boxes reaching outside the case on both sides), then seeded random batches drawn in the reference's order."""
+    from anatomask_b200 import augment as A
+    from oracle import augment_port as O
+    dev = _dev()
+    aug = A.DeviceAugmenter(patch_size=(patch,) * 3, p_rot=0.5, p_scale=0.5)
+    P = aug.initial_patch_size
+    cases_np = [_synthetic_case((70, 96, 88), seed), _synthetic_case((P[0] - 9, 64, P[2] + 30), seed + 1)]
+    cases = [torch.from_numpy(c).to(dev) for c in cases_np]
+    R = A.rotation_matrix
+    forced = [
+        (0, (5, 7, 3), None, None, (False, False, False)),
+        (0, (-11, 20, -6), None, None, (True, False, True)),                       # bbox reaches outside the case: zero padding
+        (0, (2, 9, 4), (0.3, -0.2, 0.45), None, (False, True, False)),
+        (0, (-20, -15, 30), (0.5, 0.5, -0.5), None, (True, True, True)),
+        (1, (0, -12, 10), None, 0.75, (False, False, True)),                       # zoom in (scale < 1)
+        (1, (-4, 3, 40), None, 1.35, (False, False, False)),                       # zoom out: samples beyond the initial patch → 0
+        (1, (3, -8, 25), (-0.52, 0.1, 0.33), 1.2, (True, False, False)),
+    ]
+    worst = 0.0
+    for ci, lb, angles, sc, flips in forced:
+        mat = None
+        if angles is not None or sc is not None:
+            mat = (R(*angles) if angles is not None else np.eye(3)) * (sc if sc is not None else 1.0)
+        got = aug([cases[ci]], [A.SampleParams(lb, mat, flips)])[0, 0].cpu().numpy()
+        want = O.pipeline_sample(cases_np[ci], lb, P, aug.patch_size, angles, sc, flips)
+        err = float(np.abs(got - want).max()) / float(np.abs(want).max())
+        worst = max(worst, err)
+        assert err < tol, f'augment lb={lb} angles={angles} scale={sc} flips={flips}: rel max err {err:.3e}'
+        if mat is None:
+            assert np.array_equal(got, want), 'crop + mirror must be bit-exact'
+    for s in range(4):                                                             # random batches, reference draw order
+        r1, r2 = np.random.RandomState(100 + s), np.random.RandomState(100 + s)
+        inp, params = aug.sample(cases, r1)
+        ref = O.draw_batch(r2, [c.shape for c in cases_np], P, aug.patch_size, aug.angle, aug.scale, aug.p_rot, aug.p_scale)
+        for j, (lb, angles, sc, flips) in enumerate(ref):
+            want = O.pipeline_sample(cases_np[j], lb, P, aug.patch_size, angles, sc, flips)
+            err = float(np.abs(inp[j, 0].cpu().numpy() - want).max()) / max(float(np.abs(want).max()), 1e-6)
+            worst = max(worst, err)
+            assert err < tol, f'augment batch {s} sample {j}: {err:.3e}'
+    return {'worst_rel_max_err': worst}
+
+
+def check_augment_full_size(reps=3):
+    """BASELINE size (128³ out of a 205³ initial patch): size-independent properties + throughput.
+    (a) identity transform through the spline path reproduces the centre crop (a cubic spline interpolates its knots),
+    (b) a mirrored crop flipped back equals the crop bit-for-bit."""
+    import time
+    from anatomask_b200 import augment as A
+    dev = _dev()
+    aug = A.DeviceAugmenter()
+    P, Osz = aug.initial_patch_size, aug.patch_size
+    case = torch.from_numpy(_synthetic_case((230, 260, 240), 3)).to(dev)
+    lb = (10, 25, 17)
+    crop = aug([case], [A.SampleParams(lb, None, (False, False, False))])
+    ident = aug([case], [A.SampleParams(lb, np.eye(3), (False, False, False))])
+    err_a = float((crop - ident).abs().max() / crop.abs().max())
+    assert err_a < 2e-5, err_a
+    flipped = aug([case], [A.SampleParams(lb, None, (True, False, True))])
+    assert torch.equal(flipped.flip(2).flip(4), crop)
+    res = {'identity_vs_crop': err_a}
+    for name, mat in (('crop', None), ('spline', A.rotation_matrix(0.3, -0.2, 0.1) * 1.1)):
+        ps = [A.SampleParams(lb, mat, (True, False, False))] * 2
+        aug([case, case], ps)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(reps):
+            aug([case, case], ps)
+        torch.cuda.synchronize()
+        res[f'ms_per_volume_{name}'] = (time.time() - t0) / reps / 2 * 1e3
+    print('RESULT augment_full_size', res)
+    return res

@@ -404,3 +404,56 @@ if __name__ == '__main__':
     nm = sys.argv[1]
     kw = json.loads(sys.argv[2]) if len(sys.argv) > 2 else {}
     CHECKS[nm](**kw)
+
+
+def check_gradient_checkpointing(name='S64', batch=2, seed=5):
+    """P/GC.py: the activation-checkpointed STUNet / LightDecoder (anatomask_b200/GC.py) against the regular mirror on the same
+    weights, input and mask — same loss, same gradients up to the atomics' run-to-run noise, lower peak memory, and against
+    the oracle's loss."""
+    from anatomask_b200 import GC, spark3D
+    from anatomask_b200.encoder3D import SparseEncoder
+    cfg = rp.CONFIGS[name]
+    st = {k: v.cuda() for k, v in rp.make_state(cfg, seed).items()}
+    inp = rp.make_input(cfg, batch, seed).cuda()
+    active = rp.random_mask(cfg, batch, torch.Generator().manual_seed(seed + 1))
+    ref = rp.spark_loss_and_grads(rp.make_state(cfg, seed), cfg, inp.cpu(), active)
+    active = active.cuda()
+
+    def make(gc):
+        if not gc:
+            m = build(cfg, seed, anatomask=False)
+        else:
+            head = GC.STUNet(1, 1, depth=[cfg.depth] * 6, dims=[cfg.base * x for x in (1, 2, 4, 8, 16, 16)],
+                             pool_op_kernel_sizes=[[2, 2, 2]] * 4 + [[1, 1, 1]], conv_kernel_sizes=[[3, 3, 3]] * 6)
+            enc = SparseEncoder(head, input_size=cfg.input_size, sbn=False)
+            dec = GC.LightDecoder(enc.downsample_ratio, sbn=False, width=cfg.width, out_channel=1)
+            m = spark3D.SparK(enc, dec, mask_ratio=cfg.mask_ratio, densify_norm='in').cuda()
+            m.load_state_dict(st)
+        return m.train()
+
+    out = {}
+    for gc in (False, False, True):
+        m = make(gc)
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        loss = m(inp, active_b1ff=active)
+        loss.backward()
+        torch.cuda.synchronize()
+        key = 'gc' if gc else ('plain2' if 'plain' in out else 'plain')
+        out[key] = (float(loss), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None},
+                    torch.cuda.max_memory_allocated() - base)
+        del m, loss
+    keys = [k for k in out['plain'][1] if k.startswith(('dense_decoder.dec.3', 'dense_decoder.proj'))]
+    rel = lambda a, b: max(float((a[k] - b[k]).norm() / (b[k].norm() + 1e-12)) for k in keys)
+    noise, diff = rel(out['plain2'][1], out['plain'][1]), rel(out['gc'][1], out['plain'][1])
+    res = {'loss_plain': out['plain'][0], 'loss_gc': out['gc'][0], 'loss_oracle': float(ref['loss']), 'grad_noise': noise,
+           'grad_diff_gc': diff, 'peak_plain_MB': out['plain'][2] / 2 ** 20, 'peak_gc_MB': out['gc'][2] / 2 ** 20,
+           'n_grads': (len(out['plain'][1]), len(out['gc'][1]))}
+    print('RESULT gradient_checkpointing', name, json.dumps(res))
+    assert abs(out['gc'][0] - float(ref['loss'])) <= 1e-3 * abs(float(ref['loss'])), res
+    assert abs(out['gc'][0] - out['plain'][0]) <= 2e-4 * abs(out['plain'][0]), res
+    assert set(out['gc'][1]) == set(out['plain'][1]), 'checkpointed model must give every live parameter a gradient'
+    assert diff <= 2.0 * noise + 1e-2, res
+    assert out['gc'][2] < 0.8 * out['plain'][2], res
+    return res

@@ -171,3 +171,44 @@ def test_pack_plan_job_table():
     for (key, w), job in zip([rec[0], rec[1], rec[3]], tab):
         assert int(job['src']) == w.data_ptr() and int(job['dst']) == plan.cache[key].data_ptr()
         assert tuple(plan.cache[key].shape) == (key[1], key[2], key[3]) and plan.cache[key].dtype == torch.bfloat16
+
+
+def test_augmentation_draws_follow_the_reference_order():
+    """anatomask_b200.augment draws (bbox, rotation, scale, mirror) consume a seeded numpy stream exactly like the oracle's
+    restatement of the loader + batchgenerators transforms; the initial patch size is the reference's get_patch_size."""
+    import numpy as np
+    from anatomask_b200 import augment as A
+    from oracle import augment_port as O
+    aug = A.DeviceAugmenter()
+    assert aug.initial_patch_size == (205, 205, 205)            # 128·(cos30° + sin30°) / 0.85
+    assert A.DeviceAugmenter(patch_size=(64, 64, 64)).initial_patch_size == (102, 102, 102)
+    shapes = [(220, 310, 290), (150, 200, 180), (100, 512, 512)]
+    n_interp = 0
+    for seed in range(40):
+        r1, r2 = np.random.RandomState(seed), np.random.RandomState(seed)
+        mine = aug.draw(shapes, r1)
+        ref = O.draw_batch(r2, shapes, aug.initial_patch_size, aug.patch_size, aug.angle)
+        for a, (lb, angles, sc, flips) in zip(mine, ref):
+            assert a.bbox_lb == lb and a.mirror == flips
+            assert (a.matrix is None) == (angles is None and sc is None)
+            if a.matrix is not None:
+                n_interp += 1
+                coords = np.random.RandomState(1).standard_normal((3, 5))
+                want = O.rotate_coords_3d(coords.copy(), *angles) if angles is not None else coords.copy()
+                want = want * (sc if sc is not None else 1.0)
+                assert np.allclose((coords.T @ a.matrix).T, want, atol=1e-12)
+        assert np.array_equal(r1.get_state()[1], r2.get_state()[1])      # both consumed the stream identically
+    assert n_interp > 10
+
+
+def test_augmentation_bbox_bounds():
+    import numpy as np
+    from anatomask_b200 import augment as A
+    rng = np.random.RandomState(0)
+    for _ in range(200):
+        lb = A.draw_bbox((100, 300, 210), (205, 205, 205), (128, 128, 128), rng)
+        # need_to_pad = 77 (105 where the case is shorter than the patch): lower corner in [-need//2, shape + need//2 + need%2 - patch]
+        assert -53 <= lb[0] <= 100 + 52 + 1 - 205 and -39 <= lb[1] <= 300 + 38 + 1 - 205 and -39 <= lb[2] <= 210 + 38 + 1 - 205
+    locs = {1: np.array([[0, 50, 150, 100]]), 2: np.array([])}
+    lb = A.draw_bbox((100, 300, 210), (205, 205, 205), (128, 128, 128), rng, force_fg=True, class_locations=locs)
+    assert lb == (max(-53, 50 - 102), 150 - 102, max(-39, 100 - 102))

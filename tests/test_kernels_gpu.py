@@ -215,3 +215,49 @@ def test_full_size_properties_B128():
     m1 = encoder3D._cur_active
     up = m1.repeat_interleave(16, 2).repeat_interleave(16, 3).repeat_interleave(16, 4)
     assert float(feats[0].float().abs().mul((~up).float()).max()) == 0.0
+
+
+@pytest.mark.parametrize('name', sorted(__import__('oracle.sparse_layers_port', fromlist=['CASES']).CASES))
+def test_remaining_sparse_layers(name):
+    """SparseGroupNorm, SparseConvNeXtLayerNorm, SparseMax/AvgPooling, SparseAdaptiveAvgPooling, depthwise
+    SparseConv3d (k 3/5/7, stride 1/2), SparseConvNeXtBlock and converted MedNeXt blocks — the CUDA modules against the oracle
+    port (itself pinned to the unmodified reference classes by tests/golden/sparse_layers.pt)."""
+    kc.check_sparse_layer_case(name)
+
+
+def test_mednext_encoder_through_sparse_encoder():
+    """A small MedNeXt head (P/MedNeXt_head.py) converted by SparseEncoder runs forward/backward on the sm_100a kernels with
+    activation checkpointing outside the blocks (checkpoint_style='outside_block'), features zero on masked patches."""
+    from anatomask_b200 import encoder3D as enc, MedNeXt_head as mh
+    torch.manual_seed(0)
+    head = mh.MedNeXt(1, 16, 1, exp_r=2, kernel_size=3, do_res=True, do_res_up_down=True, checkpoint_style='outside_block',
+                      block_counts=[1] * 9)
+    se = enc.SparseEncoder(head, input_size=(32, 32, 32)).cuda()
+    assert se.downsample_ratio == 16 and se.enc_feat_map_chs == [16, 32, 64, 128, 256]
+    active = kc._rand_mask(2, 2, keep=0.5, seed=3).cuda()
+    enc._cur_active = active
+    inp = torch.randn(2, 1, 32, 32, 32, device='cuda') * kc._up(active, 32)
+    feats = se(inp)
+    assert [tuple(f.shape[1:]) for f in feats] == [(16, 32, 32, 32), (32, 16, 16, 16), (64, 8, 8, 8), (128, 4, 4, 4), (256, 2, 2, 2)]
+    sum(f.float().square().mean() for f in feats).backward()
+    torch.cuda.synchronize()
+    for f, s in zip(feats, (32, 16, 8, 4, 2)):
+        assert float(f.float().abs().mul((~kc._up(active, s)).float()).max()) == 0.0
+    for n, p in se.named_parameters():
+        if 'dummy_tensor' not in n:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+def test_gradient_checkpointed_variants():
+    """P/GC.py: checkpointed STUNet stages / decoder blocks — same loss and gradients as the regular mirror, less memory"""
+    mc.check_gradient_checkpointing()
+
+
+def test_device_side_input_pipeline():
+    """crop / pad + order-3 spline rotation / scaling + mirroring on the GPU against the numpy / scipy
+    restatement of the loader + batchgenerators transforms, forced branches and seeded random batches"""
+    kc.check_augment()
+
+
+def test_device_side_input_pipeline_full_size():
+    kc.check_augment_full_size()

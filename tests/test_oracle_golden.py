@@ -94,3 +94,27 @@ def test_hard_mask_schedule_lengths():
     assert rp.hard_mask_lengths(cfg, 500, 999)[0] == 76
     ll, easy = rp.hard_mask_lengths(cfg, 998, 999)
     assert ll + easy == 307 and ll == 153
+
+
+@pytest.mark.parametrize('name', sorted(__import__('oracle.sparse_layers_port', fromlist=['CASES']).CASES))
+def test_sparse_layer_port_matches_reference_fixture(golden_dir, name):
+    """oracle/sparse_layers_port.py against the results of the UNMODIFIED reference classes (P/encoder3D.py layers, converted
+    P/MedNeXt_head.py blocks) committed by oracle/make_golden_layers.py: outputs and input gradients through their digests
+    (norm, sum, 2048 strided samples), parameter gradients in full."""
+    from oracle import sparse_layers_port as sl
+    fx = _load(golden_dir, 'sparse_layers.pt')[name]
+    x, active, g = sl.case_inputs(name)
+    params = {k: v.requires_grad_(True) for k, v in sl.case_params(fx['param_shapes'], g).items()}
+    x.requires_grad_(True)
+    y = sl.run_case(name, params, x, active)
+    y.backward(sl.case_dy(y.shape, name))
+    for got, want in ((y.detach(), fx['y']), (x.grad, fx['dx'])):
+        assert tuple(got.shape) == want['shape']
+        flat = got.double().flatten()
+        scale = max(want['norm'] / flat.numel() ** 0.5, 1e-12)
+        assert abs(float(flat.norm()) - want['norm']) <= 1e-5 * want['norm'] + 1e-9
+        assert float((flat[want['idx']].float() - want['val']).abs().max()) <= 2e-5 * max(scale, float(want['val'].abs().max()))
+    for k, gref in fx['grads'].items():
+        got = params[k].grad
+        assert got is not None, k
+        assert float((got - gref).norm()) <= 2e-5 * float(gref.norm()) + 1e-7, k
