@@ -457,3 +457,68 @@ def check_gradient_checkpointing(name='S64', batch=2, seed=5):
     assert diff <= 2.0 * noise + 1e-2, res
     assert out['gc'][2] < 0.8 * out['plain'][2], res
     return res
+
+
+def check_checkpoint_resume(name='S64', batch=2, seed=7, tmp_dir='/tmp'):
+    """SURVEY §8f row 3 on the GPU: `_head_latest.pt` written mid-run by the engine, a fresh engine resumed from the file
+    continues with the SAME masks (device-RNG stream positions restored), the same Adam step count / moments and the same EMA
+    teacher; the file's encoder entries map onto a fine-tuning STUNet through the reference loader's key rule; a checkpoint
+    from a different model size is refused."""
+    import os
+    from anatomask_b200 import checkpoint
+    from anatomask_b200.trainer import PretrainEngine
+    cfg = rp.CONFIGS[name]
+    inps = [rp.make_input(cfg, batch, seed + i).cuda() for i in range(4)]
+
+    def engine():
+        return PretrainEngine(build(cfg, seed, anatomask=True), lr=1e-4, epochs=1000, anatomask=True, mask_rng='device')
+
+    a = engine()
+    for i in range(2):
+        a.device_step(inps[i], 500 + i)
+    path = os.path.join(tmp_dir, f'amb_ckpt_{os.getpid()}_head_latest.pt')
+    checkpoint.save_head_checkpoint(path, a.model, a, train_loss=1.0, val_loss=None, epoch=501)
+    tail_a = [a.device_step(inps[i], 500 + i) for i in (2, 3)]
+    torch.cuda.synchronize()
+    ck = torch.load(path, weights_only=False)
+    os.remove(path)
+    assert set(ck) >= {'network_weights', 'optimizer_state', 'grad_scaler_state', 'train_loss', 'val_loss', 'current_epoch'}
+    assert all(k.startswith('module.') for k in ck['network_weights'])                      # P/pretrain.py:450-463
+    b = engine()
+    checkpoint.resume(b, ck)
+    assert b.t == 2 and int(b.step_counter.item()) == int(ck['optimizer_state']['rng']['step_counter'])
+    tail_b = [b.device_step(inps[i], 500 + i) for i in (2, 3)]
+    c = engine()                          # a second resume of the same file: b-vs-c is the run-to-run noise of two steps
+    checkpoint.resume(c, ck)              # (fp32 atomics commit in a different order every run; Adam's m/sqrt(v) amplifies it)
+    for i in (2, 3):
+        c.device_step(inps[i], 500 + i)
+    torch.cuda.synchronize()
+    masks_equal = all(torch.equal(x[1], y[1]) for x, y in zip(tail_a, tail_b))
+    losses = [(float(x[0]), float(y[0])) for x, y in zip(tail_a, tail_b)]
+    ua = a.arena.flat[:a.arena.n_live]
+    ub = b.arena.flat[:b.arena.n_live]
+    uc = c.arena.flat[:c.arena.n_live]
+    sd0 = {k[len('module.'):]: v for k, v in ck['network_weights'].items()}
+    pdiff = float((ua - ub).norm() / ua.norm())
+    noise = float((ub - uc).norm() / ub.norm())
+    upd = float(torch.sqrt(sum(((p.detach().float() - sd0[k].to(p.device).float()) ** 2).sum()
+                               for k, p in b.model.named_parameters())) / ub.norm())
+    tdiff = float((a.tarena.flat - b.tarena.flat).norm() / a.tarena.flat.norm())
+    res = {'masks_equal': masks_equal, 'losses': losses, 'param_rel_diff': pdiff, 'rerun_noise': noise, 'update_size': upd,
+           'teacher_rel_diff': tdiff, 't': (a.t, b.t)}
+    print('RESULT checkpoint_resume', name, json.dumps(res))
+    assert masks_equal and a.t == b.t == 4
+    assert all(abs(x - y) <= 2e-3 * abs(x) for x, y in losses), res
+    # the uninterrupted run and the resumed run may differ by what two resumed runs differ by (run-to-run noise), and by a small
+    # fraction of what the two steps changed; a lost moment / step count / lr position shows up as O(update_size)
+    assert pdiff <= 3.0 * noise + 0.02 * upd and tdiff < 1e-5, res
+    enc = checkpoint.encoder_state_for_finetune(ck['network_weights'])
+    assert enc and all(k.startswith('conv_blocks_context.') for k in enc)                   # load_pretrained_weights.py:66-105
+    other = PretrainEngine(build(rp.CONFIGS['tiny'], seed, anatomask=True), epochs=1000, anatomask=True, mask_rng='device')
+    try:
+        checkpoint.resume(other, ck)
+    except RuntimeError:
+        pass
+    else:
+        raise AssertionError('resume() accepted a checkpoint of a different model size')
+    return res

@@ -261,3 +261,8 @@ def test_device_side_input_pipeline():
 
 def test_device_side_input_pipeline_full_size():
     kc.check_augment_full_size()
+
+
+def test_checkpoint_write_resume_roundtrip():
+    """`_head_latest.pt` writer + resume on the GPU — same masks, step count, moments and teacher after resume"""
+    mc.check_checkpoint_resume()
