@@ -45,25 +45,39 @@ class BasicResBlock(nn.Module):
         m = encoder3D._mask_ctx()
         c1, c2, c3 = self.conv1, self.conv2, self.conv3
         stride = c1.stride[0]
-        if c1.in_channels == 1:                 # stem: masked fp32 input → conv1 and shortcut in one kernel
+        stem = c1.in_channels == 1
+        # Engine mode (ops.LEAN_ZERO): which masked voxels of this block's sparse tensors have to be zero.  P = patch edge at the
+        # block's output resolution.  With P >= 8 every kernel that reads these tensors walks the active-patch list: the 3x3x3
+        # ones read one voxel beyond a visible patch ('shell'), norms / 1x1 convs / the stem weight gradient none at all
+        # ('none').  The block OUTPUT feeds the next stage's stride-2 convs, whose patch edge is P/2, hence P >= 16 there.
+        P = (x.shape[2] // stride) // m.fd
+        lean = ops.LEAN_ZERO and P >= 8 and x.shape[3] // stride // m.fh == P and x.shape[4] // stride // m.fw == P
+        z1 = ('shell', 'none' if stem else 'shell', 'full') if lean else ('full', 'full', 'full')
+        z2 = ('shell' if P >= 16 else 'full', 'shell', 'none') if lean else ('full', 'full', 'full')
+        zero_dx = not ops.LEAN_ZERO            # conv input gradients here are only ever read at visible voxels (norm backward)
+        if stem:                                # stem: masked fp32 input → conv1 and shortcut in one kernel
             if c3 is None or stride != 1:
                 raise NotImplementedError('in_channels=1 block needs stride 1 and a 1x1 shortcut')
             y, sc = ops.StemFn.apply(x, c1.weight, c1.bias, c3.weight, c3.bias, m, False)
+            s1 = None
         else:
             xi = ops.to_internal(x)
             # Σy / Σy² of the visible outputs come out of the conv epilogue (no separate statistics pass)
             s1 = ops.new_stats(c1.out_channels, xi.device) if ops.fused_stats_ok(c1.in_channels, c1.out_channels) else None
             # conv outputs feed pooled masked norms only (visible voxels), so their masked voxels may stay unwritten
-            y = ops.conv3d(xi, c1.weight, c1.bias, c1.kernel_size[0], stride, m, stats=s1, zero_inactive=False, zero_bias_grad=True)
-            sc = ops.conv3d(xi, c3.weight, c3.bias, 1, stride, m, zero_inactive=False) if c3 is not None else xi
-        if c1.in_channels == 1:
-            s1 = None
-        y = ops.masked_norm(y, self.norm1.weight, self.norm1.bias, self.norm1.eps, m, ACT_LRELU, sums=s1)
+            if c3 is not None and ops.LEAN_ZERO:
+                y, sc = ops.conv3d_pair(xi, c1.weight, c1.bias, c3.weight, c3.bias, c1.kernel_size[0], stride, m, stats=s1)
+            else:
+                y = ops.conv3d(xi, c1.weight, c1.bias, c1.kernel_size[0], stride, m, stats=s1, zero_inactive=False,
+                               zero_bias_grad=True, zero_dx=zero_dx)
+                sc = ops.conv3d(xi, c3.weight, c3.bias, 1, stride, m, zero_inactive=False) if c3 is not None else xi
+        y = ops.masked_norm(y, self.norm1.weight, self.norm1.bias, self.norm1.eps, m, ACT_LRELU, sums=s1, zero=z1)
         s2 = ops.new_stats(c2.out_channels, y.device) if ops.fused_stats_ok(c2.in_channels, c2.out_channels) else None
         # conv1 / conv2 feed SparseInstanceNorm only (batch statistics in train AND eval): their bias gradients are
         # identically zero, so no Σdy pass is run for them (ops.conv3d zero_bias_grad)
-        y = ops.conv3d(y, c2.weight, c2.bias, c2.kernel_size[0], 1, m, stats=s2, zero_inactive=False, zero_bias_grad=True)
-        y = ops.masked_norm(y, self.norm2.weight, self.norm2.bias, self.norm2.eps, m, ACT_LRELU, residual=sc, sums=s2)
+        y = ops.conv3d(y, c2.weight, c2.bias, c2.kernel_size[0], 1, m, stats=s2, zero_inactive=False, zero_bias_grad=True,
+                       zero_dx=zero_dx)
+        y = ops.masked_norm(y, self.norm2.weight, self.norm2.bias, self.norm2.eps, m, ACT_LRELU, residual=sc, sums=s2, zero=z2)
         return ops.to_external(y)
 
 

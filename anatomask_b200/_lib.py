@@ -64,6 +64,8 @@ _SIGNATURES = {
     'amb_norm_bwd_reduce': (i32, [C.POINTER(Geo), vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]),
     'amb_norm_bwd_apply': (i32, [C.POINTER(Geo), vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
     'amb_add': (i32, [vp, vp, vp, i64, vp]),
+    'amb_zero_shell': (i32, [C.POINTER(Geo), vp, vp]),
+    'amb_add_parity0': (i32, [C.POINTER(Geo), vp, vp, vp]),
     'amb_patch_loss_fwd': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
     'amb_patch_loss_bwd': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
     'amb_hard_mask': (i32, [vp, i32, i32, i32, i32, u64, u64, vp, vp, vp, vp, vp]),

@@ -293,10 +293,11 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
 // returns 1 when handled, 0 when the shape is outside this kernel's scope, <0 on error
 int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a) {
     if (getenv("AMB_DISABLE_WH")) return 0;
-    // sparse layers: this kernel can walk the active-patch list (a patch must hold whole 8x8 columns), parity-green, but
-    // opt-in (AMB_WH_LIST=1): measured no gain for the step (27.66 vs 27.54 ms) — the encoder weight gradients run on the
-    // side stream off the critical path and patch-deep columns pay 2 halo planes per 8-16 steps.  Default: per-tap kernel.
-    const bool use_list = a->active_list != nullptr && p.lgPv >= 3 && getenv("AMB_WH_LIST") != nullptr;
+    // sparse layers: the kernel walks the active-patch list (a patch must hold whole 8x8 columns: patch edge >= 8).  Round 1
+    // kept this opt-in (no step gain while the encoder weight gradients hid on the side stream); with the step's device time
+    // now back to back on both streams it is worth 0.27 ms of a 21 ms step (20.97 -> 20.70, same box), so it is the default.
+    // AMB_WH_NO_LIST=1 sends the sparse layers back to the per-tap kernel.
+    const bool use_list = a->active_list != nullptr && p.lgPv >= 3 && getenv("AMB_WH_NO_LIST") == nullptr;
     if (a->active_list != nullptr && !use_list) return 0;
     // a convolution (27 taps, one dY view) or a ConvTranspose k4 s2 (8 parity-class views of dY with 8 taps each)
     const bool is_conv = p.n_out_views == 1 && p.n_taps == 27;

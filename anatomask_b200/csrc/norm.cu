@@ -310,6 +310,296 @@ bwd_apply_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Row-group walk of the active-patch list (the sparse encoder's norms).  The per-chunk walk above decodes a patch id
+// (three 32-bit divisions) for every 16-byte item; here one warp iteration covers G = min(4, P) consecutive y-rows of one
+// patch at one z — a lane decodes once and then touches the same 16-byte column of G rows (G independent 128-bit loads in
+// flight per tensor).  A patch row is P·C/8 chunks; 32 of them per warp iteration (UPR iterations per row when it is longer).
+// Requires a power-of-two channel-group count; anything else takes the per-chunk kernels.
+// ------------------------------------------------------------------------------------------------------------
+struct RowWalk {
+    uint32_t unit, step, nunits;
+    int lgG, lgUPR, lgCG, G;
+    int cg;                  // channel group of this lane (constant over the walk)
+    bool lane_on;            // lane inside the row (rows shorter than 32 chunks leave lanes idle)
+    uint32_t vox;            // voxel of this lane inside the row
+    long row_stride;         // elements between consecutive y-rows
+};
+
+__device__ __forceinline__ int ilog2_dev(int v) { return 31 - __clz(v); }
+
+__device__ __forceinline__ RowWalk make_row_walk(const Geo& g) {
+    RowWalk w;
+    const int CG = g.C >> 3;
+    w.lgCG = ilog2_dev(CG);
+    const int R = g.P * CG;                                  // chunks per patch row
+    const int UPR = R > 32 ? (R >> 5) : 1;
+    w.lgUPR = ilog2_dev(UPR);
+    w.G = g.P < 4 ? g.P : 4;
+    w.lgG = ilog2_dev(w.G);
+    const uint32_t warp = ((uint32_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t nwarps = ((uint32_t)gridDim.x * blockDim.x) >> 5;
+    nwarps &= ~(uint32_t)(UPR - 1);                          // stride a multiple of UPR: `part` (and so cg) stays constant
+    const int lane = threadIdx.x & 31;
+    const uint32_t part = warp & (uint32_t)(UPR - 1);
+    const uint32_t c = part * 32u + (uint32_t)lane;
+    w.lane_on = c < (uint32_t)R;
+    w.cg = (int)(c & (uint32_t)(CG - 1));
+    w.vox = c >> w.lgCG;
+    w.unit = warp;
+    w.step = nwarps;
+    w.nunits = (nwarps == 0 || warp >= nwarps) ? 0u : ((uint32_t)(*g.count) << (g.lgP + (g.lgP - w.lgG) + w.lgUPR));
+    w.row_stride = (long)g.W * g.C;
+    return w;
+}
+
+// element offset of this lane's chunk in the first row of the group
+__device__ __forceinline__ long row_unit_offset(const Geo& g, const RowWalk& w, uint32_t u) {
+    uint32_t t = u >> w.lgUPR;
+    const uint32_t yg = t & (((uint32_t)g.P >> w.lgG) - 1u);
+    t >>= (g.lgP - w.lgG);
+    const uint32_t rz = t & ((uint32_t)g.P - 1u);
+    const uint32_t pid = (uint32_t)g.list[t >> g.lgP];
+    const uint32_t L = (uint32_t)(g.fd * g.fh * g.fw), hw = (uint32_t)(g.fh * g.fw);
+    const uint32_t n = pid / L, l = pid - n * L;
+    const uint32_t pz = l / hw, r2 = l - pz * hw;
+    const uint32_t py = r2 / (uint32_t)g.fw, px = r2 - py * (uint32_t)g.fw;
+    const long voxel = (((long)n * g.D + (pz << g.lgP) + rz) * g.H + (py << g.lgP) + (yg << w.lgG)) * g.W +
+                       ((long)px << g.lgP) + w.vox;
+    return voxel * g.C + (long)w.cg * 8;
+}
+
+// G (rows per group) is a template parameter: the G·(1..3) 128-bit loads of a group are issued back to back before any of
+// them is consumed (memory-level parallelism per thread instead of per-SM thread count).
+template <int MODE, int ACT, int G>
+__global__ void __launch_bounds__(256, 2) reduce_rows_kernel(Geo g, const bf16* __restrict__ x, const bf16* __restrict__ dout,
+                                                          const bf16* __restrict__ res, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, const float* __restrict__ saved,
+                                                          double* __restrict__ sums) {
+    extern __shared__ float sacc[];           // [2][C]
+    const int CG = g.C / 8;
+    for (int i = threadIdx.x; i < g.C * 2; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    float a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+    RowWalk w = make_row_walk(g);
+    const int cg = w.cg;
+    float sc[8], sh[8];
+    if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j]; }
+    }
+    if (w.lane_on) {
+        for (uint32_t u = w.unit; u < w.nunits; u += w.step) {
+            const long off0 = row_unit_offset(g, w, u);
+            uint4 vx[G], vd[G], vr[G];
+#pragma unroll
+            for (int r = 0; r < G; ++r) {
+                const long off = off0 + r * w.row_stride;
+                vx[r] = __ldg(reinterpret_cast<const uint4*>(x + off));
+                if (MODE == 1) {
+                    vd[r] = __ldg(reinterpret_cast<const uint4*>(dout + off));
+                    if (res) vr[r] = __ldg(reinterpret_cast<const uint4*>(res + off));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < G; ++r) {
+                float f[8];
+                unpack_u4(vx[r], f);
+                if (MODE == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { a0[j] += f[j]; a1[j] += f[j] * f[j]; }
+                } else {
+                    float d[8], rr[8];
+                    unpack_u4(vd[r], d);
+                    if (res) unpack_u4(vr[r], rr);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float uu = sc[j] * f[j] + sh[j] + (res ? rr[j] : 0.f);
+                        float gj = d[j] * act_grad(uu, ACT);
+                        a0[j] += gj;
+                        a1[j] += gj * f[j];
+                    }
+                }
+            }
+        }
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            a1[j] = saved[g.C + cg * 8 + j] * (a1[j] - saved[cg * 8 + j] * a0[j]);
+    }
+    if (CG < 32) {                            // lanes that share a channel group (lane % CG equal): shuffle first
+        for (int o = CG; o < 32; o <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], o);
+                a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], o);
+            }
+        }
+    }
+    if (CG >= 32 || (threadIdx.x & 31) < CG) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&sacc[cg * 8 + j], a0[j]);
+            atomicAdd(&sacc[g.C + cg * 8 + j], a1[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < g.C; i += blockDim.x) {
+        atomicAdd(&sums[i], (double)sacc[i]);
+        atomicAdd(&sums[g.C + i], (double)sacc[g.C + i]);
+    }
+}
+
+template <int ACT, int G>
+__global__ void __launch_bounds__(256, 3) apply_rows_kernel(Geo g, const bf16* __restrict__ x, const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, const bf16* __restrict__ res,
+                                                         bf16* __restrict__ out) {
+    RowWalk w = make_row_walk(g);
+    if (!w.lane_on) return;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[w.cg * 8 + j]; sh[j] = shift[w.cg * 8 + j]; }
+    for (uint32_t u = w.unit; u < w.nunits; u += w.step) {
+        const long off0 = row_unit_offset(g, w, u);
+        uint4 vx[G], vr[G];
+#pragma unroll
+        for (int r = 0; r < G; ++r) {
+            const long off = off0 + r * w.row_stride;
+            vx[r] = __ldg(reinterpret_cast<const uint4*>(x + off));
+            if (res) vr[r] = __ldg(reinterpret_cast<const uint4*>(res + off));
+        }
+#pragma unroll
+        for (int r = 0; r < G; ++r) {
+            float f[8], rr[8], o[8];
+            unpack_u4(vx[r], f);
+            if (res) unpack_u4(vr[r], rr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = act_fwd(sc[j] * f[j] + sh[j] + (res ? rr[j] : 0.f), ACT);
+            store8(out + off0 + r * w.row_stride, o);
+        }
+    }
+}
+
+template <int ACT, int G>
+__global__ void __launch_bounds__(256, 2)
+bwd_apply_rows_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ x, const bf16* __restrict__ res,
+                      const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ saved,
+                      const double* __restrict__ sums, bf16* __restrict__ dx, bf16* __restrict__ dres,
+                      float* __restrict__ dgamma, float* __restrict__ dbeta, const double* n_total) {
+    if (blockIdx.x == 0 && dgamma) {
+        for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+            dbeta[c] = (float)sums[c];
+            dgamma[c] = (float)sums[g.C + c];
+        }
+    }
+    RowWalk w = make_row_walk(g);
+    if (!w.lane_on) return;
+    const double n = n_total ? *n_total : (double)((long)(*g.count) << (3 * g.lgP));
+    float sc[8], sh[8], ca[8], cb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int c = w.cg * 8 + j;
+        sc[j] = scale[c]; sh[j] = shift[c];
+        const float mu = saved[c], rs = saved[g.C + c];
+        const float m1 = (float)(sums[c] / n), m2 = (float)(sums[g.C + c] / n);
+        ca[j] = -sc[j] * m2 * rs;
+        cb[j] = -sc[j] * m1 - ca[j] * mu;
+    }
+    for (uint32_t u = w.unit; u < w.nunits; u += w.step) {
+        const long off0 = row_unit_offset(g, w, u);
+        uint4 vx[G], vd[G], vr[G];
+#pragma unroll
+        for (int r = 0; r < G; ++r) {
+            const long off = off0 + r * w.row_stride;
+            vd[r] = __ldg(reinterpret_cast<const uint4*>(dout + off));
+            vx[r] = __ldg(reinterpret_cast<const uint4*>(x + off));
+            if (res) vr[r] = __ldg(reinterpret_cast<const uint4*>(res + off));
+        }
+#pragma unroll
+        for (int r = 0; r < G; ++r) {
+            const long off = off0 + r * w.row_stride;
+            float d[8], f[8], rr[8], o[8], gg[8];
+            unpack_u4(vd[r], d);
+            unpack_u4(vx[r], f);
+            if (res) unpack_u4(vr[r], rr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float uu = sc[j] * f[j] + sh[j] + (res ? rr[j] : 0.f);
+                gg[j] = d[j] * act_grad(uu, ACT);
+                o[j] = fmaf(sc[j], gg[j], fmaf(ca[j], f[j], cb[j]));
+            }
+            store8(dx + off, o);
+            if (dres) store8(dres + off, gg);
+        }
+    }
+}
+
+// Engine mode (ops.LEAN_ZERO): a sparse tensor whose consumers all walk the active-patch list is read at most ONE voxel beyond
+// a visible patch (3x3x3 halo), so instead of zero-filling the whole tensor only the 1-voxel shell of every visible patch that
+// lies inside masked patches is cleared.  One CTA per visible patch.
+__global__ void __launch_bounds__(256) zero_shell_kernel(Geo g, bf16* __restrict__ x) {
+    const int P = g.P, CG = g.C / 8;
+    const uint32_t L = (uint32_t)(g.fd * g.fh * g.fw), hw = (uint32_t)(g.fh * g.fw);
+    const int n_entries = *g.count;
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    for (int e = blockIdx.x; e < n_entries; e += gridDim.x) {
+        const uint32_t pid = (uint32_t)g.list[e];
+        const uint32_t n = pid / L, l = pid - n * L;
+        const int pz = (int)(l / hw), r2 = (int)(l - (uint32_t)pz * hw);
+        const int py = r2 / g.fw, px = r2 - py * g.fw;
+        // the shell splits into 26 slabs, one per neighbouring patch (face: P x P voxels, edge: P, corner: 1); a slab is
+        // cleared only when that neighbour exists and is masked — one uniform test per slab, shifts inside it
+        for (int dir = 0; dir < 27; ++dir) {
+            if (dir == 13) continue;
+            const int dz = dir / 9 - 1, dy = (dir / 3) % 3 - 1, dx = dir % 3 - 1;
+            const int qz = pz + dz, qy = py + dy, qx = px + dx;
+            if (qz < 0 || qz >= g.fd || qy < 0 || qy >= g.fh || qx < 0 || qx >= g.fw) continue;
+            if (g.active[((n * g.fd + qz) * g.fh + qy) * g.fw + qx]) continue;
+            const int lz = dz ? 0 : g.lgP, ly = dy ? 0 : g.lgP, lx = dx ? 0 : g.lgP;        // log2 extents of the slab
+            const int z0 = (pz << g.lgP) + (dz < 0 ? -1 : (dz > 0 ? P : 0));
+            const int y0 = (py << g.lgP) + (dy < 0 ? -1 : (dy > 0 ? P : 0));
+            const int x0 = (px << g.lgP) + (dx < 0 ? -1 : (dx > 0 ? P : 0));
+            const int items = CG << (lz + ly + lx);
+            for (int i = threadIdx.x; i < items; i += blockDim.x) {
+                const int cg = i % CG;
+                const int v = i / CG;
+                const int vx = v & ((1 << lx) - 1), vy = (v >> lx) & ((1 << ly) - 1), vz = v >> (lx + ly);
+                const long voxel = (((long)n * g.D + z0 + vz) * g.H + y0 + vy) * g.W + x0 + vx;
+                *reinterpret_cast<uint4*>(x + voxel * g.C + cg * 8) = z4;
+            }
+        }
+    }
+}
+
+// fine[n, 2z, 2y, 2x, :] += coarse[n, z, y, x, :] — the input gradient of a 1x1 stride-2 convolution lands on the even voxels
+// only; adding it in place replaces a zero-filled full-resolution tensor plus a full-resolution add (the residual shortcut,
+// P/STUNet_head.py:96-101).  `g` describes the COARSE tensor (walks its active-patch list when it has one).
+template <bool LIST>
+__global__ void __launch_bounds__(256) add_parity0_kernel(Geo g, const bf16* __restrict__ coarse, bf16* __restrict__ fine) {
+    const int CG = g.C / 8;
+    const int cg = threadIdx.x % CG;
+    Walk w = make_walk(g, CG);
+    for (; w.slot < w.nslots; w.slot += w.step) {
+        const long v = slot_voxel<LIST>(g, w.slot);
+        uint32_t t = (uint32_t)v;
+        const uint32_t xx = t % (uint32_t)g.W; t /= (uint32_t)g.W;
+        const uint32_t y = t % (uint32_t)g.H; t /= (uint32_t)g.H;
+        const uint32_t z = t % (uint32_t)g.D;
+        const uint32_t n = t / (uint32_t)g.D;
+        const long fv = (((long)n * (2 * g.D) + 2 * z) * (2 * g.H) + 2 * y) * (2 * g.W) + 2 * xx;
+        float a[8], b[8];
+        load8(coarse + v * g.C + cg * 8, a);
+        const uint4 old = *reinterpret_cast<const uint4*>(fine + fv * g.C + cg * 8);
+        unpack_u4(old, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += b[j];
+        store8(fine + fv * g.C + cg * 8, a);
+    }
+}
+
 __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, long n8) {
     const long stride = (long)gridDim.x * blockDim.x;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
@@ -396,6 +686,35 @@ static int grid_for(long work_items, int block) {
     return (int)b;
 }
 
+static bool rows_ok(const Geo& g) {
+    const int CG = g.C / 8;
+    return g.list != nullptr && (CG & (CG - 1)) == 0 && getenv("AMB_NORM_NO_ROWS") == nullptr;
+}
+// persistent grid of the row-group kernels: every resident CTA slot of the device once (a second, partial wave of a
+// bandwidth-bound kernel runs at a fraction of the occupancy), never more warps than row groups; with more than 32 channel
+// groups the warp count must cover at least one full row (UPR warps)
+template <typename K>
+static int rows_grid(const Geo& g, K kernel, size_t smem) {
+    const int CG = g.C / 8;
+    const long R = (long)g.P * CG, UPR = R > 32 ? R / 32 : 1;
+    const int G = g.P < 4 ? g.P : 4;
+    const long units = (long)g.N * g.fd * g.fh * g.fw * g.P * (g.P / G) * UPR;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem) != cudaSuccess || occ < 1) occ = 2;
+    long ctas = (units + 7) / 8;
+    const long cap = (long)num_sms() * occ;
+    if (ctas > cap) ctas = cap;
+    const long min_ctas = (UPR + 7) / 8;
+    if (ctas < min_ctas) ctas = min_ctas;
+    return (int)ctas;
+}
+#define AMB_ROWS_G(LAUNCH)                           \
+    do {                                             \
+        if (g.P >= 4) { LAUNCH(4); }                 \
+        else if (g.P == 2) { LAUNCH(2); }            \
+        else { LAUNCH(1); }                          \
+    } while (0)
+
 static long host_items_upper(const Geo& g) { return (long)g.N * g.D * g.H * g.W * (g.C / 8); }
 
 }  // namespace amb
@@ -432,7 +751,14 @@ extern "C" int amb_norm_stats(const amb_geo* a, const void* x, double* sums, voi
     if (int e = make_geo(a, g)) return e;
     int CG = g.C / 8, block = pick_block(CG);
     if (block < 0) return block;
-    if (g.list)
+    if (rows_ok(g)) {
+        const size_t sm = g.C * 2 * sizeof(float);
+#define AMB_STATS_ROWS(GG)                                                                                     \
+    reduce_rows_kernel<0, 0, GG><<<rows_grid(g, reduce_rows_kernel<0, 0, GG>, sm), 256, sm, (cudaStream_t)stream>>>( \
+        g, (const bf16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, sums)
+        AMB_ROWS_G(AMB_STATS_ROWS);
+#undef AMB_STATS_ROWS
+    } else if (g.list)
         reduce_kernel<0, 0, true, false><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>(
             g, (const bf16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, sums, nullptr);
     else
@@ -472,7 +798,21 @@ extern "C" int amb_norm_apply(const amb_geo* a, const void* x, const float* scal
     apply_kernel<A, LI, FI><<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(        \
         g, (const bf16*)x, scale, shift, (const bf16*)residual, token, act, (bf16*)out)
     if (token) { AMB_APPLY(0, false, true); }                       // densify fill: every voxel, no activation
-    else if (g.list) {
+    else if (rows_ok(g)) {
+#define AMB_APPLY_ROWS(A, GG)                                                                                 \
+    apply_rows_kernel<A, GG><<<rows_grid(g, apply_rows_kernel<A, GG>, 0), 256, 0, (cudaStream_t)stream>>>(        \
+        g, (const bf16*)x, scale, shift, (const bf16*)residual, (bf16*)out)
+#define AMB_APPLY_ROWS1(GG) AMB_APPLY_ROWS(1, GG)
+#define AMB_APPLY_ROWS2(GG) AMB_APPLY_ROWS(2, GG)
+#define AMB_APPLY_ROWS0(GG) AMB_APPLY_ROWS(0, GG)
+        if (act == AMB_ACT_LRELU) AMB_ROWS_G(AMB_APPLY_ROWS1);
+        else if (act == AMB_ACT_RELU6) AMB_ROWS_G(AMB_APPLY_ROWS2);
+        else AMB_ROWS_G(AMB_APPLY_ROWS0);
+#undef AMB_APPLY_ROWS
+#undef AMB_APPLY_ROWS0
+#undef AMB_APPLY_ROWS1
+#undef AMB_APPLY_ROWS2
+    } else if (g.list) {
         if (act == AMB_ACT_LRELU) AMB_APPLY(1, true, false);
         else if (act == AMB_ACT_RELU6) AMB_APPLY(2, true, false);
         else AMB_APPLY(0, true, false);
@@ -498,7 +838,22 @@ extern "C" int amb_norm_bwd_reduce(const amb_geo* a, const void* dout, const voi
     reduce_kernel<1, A, LI, FI><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>( \
         g, (const bf16*)x, (const bf16*)dout, (const bf16*)residual, scale, shift, saved, act, fill, sums, dtoken)
     if (fill) { AMB_RED(0, false, true); }
-    else if (g.list) {
+    else if (rows_ok(g)) {
+        const size_t sm = g.C * 2 * sizeof(float);
+#define AMB_RED_ROWS(A, GG)                                                                                     \
+    reduce_rows_kernel<1, A, GG><<<rows_grid(g, reduce_rows_kernel<1, A, GG>, sm), 256, sm, (cudaStream_t)stream>>>( \
+        g, (const bf16*)x, (const bf16*)dout, (const bf16*)residual, scale, shift, saved, sums)
+#define AMB_RED_ROWS1(GG) AMB_RED_ROWS(1, GG)
+#define AMB_RED_ROWS2(GG) AMB_RED_ROWS(2, GG)
+#define AMB_RED_ROWS0(GG) AMB_RED_ROWS(0, GG)
+        if (act == AMB_ACT_LRELU) AMB_ROWS_G(AMB_RED_ROWS1);
+        else if (act == AMB_ACT_RELU6) AMB_ROWS_G(AMB_RED_ROWS2);
+        else AMB_ROWS_G(AMB_RED_ROWS0);
+#undef AMB_RED_ROWS
+#undef AMB_RED_ROWS0
+#undef AMB_RED_ROWS1
+#undef AMB_RED_ROWS2
+    } else if (g.list) {
         if (act == AMB_ACT_LRELU) AMB_RED(1, true, false);
         else if (act == AMB_ACT_RELU6) AMB_RED(2, true, false);
         else AMB_RED(0, true, false);
@@ -525,7 +880,22 @@ extern "C" int amb_norm_bwd_apply(const amb_geo* a, const void* dout, const void
     bwd_apply_kernel<A, LI><<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(          \
         g, (const bf16*)dout, (const bf16*)x, (const bf16*)residual, scale, shift, saved, sums, act, fill, (bf16*)dx, \
         (bf16*)dres, dgamma, dbeta, n_total)
-    if (g.list) {
+    if (rows_ok(g)) {
+#define AMB_BWD_ROWS(A, GG)                                                                                    \
+    bwd_apply_rows_kernel<A, GG><<<rows_grid(g, bwd_apply_rows_kernel<A, GG>, 0), 256, 0, (cudaStream_t)stream>>>( \
+        g, (const bf16*)dout, (const bf16*)x, (const bf16*)residual, scale, shift, saved, sums, (bf16*)dx,      \
+        (bf16*)dres, dgamma, dbeta, n_total)
+#define AMB_BWD_ROWS1(GG) AMB_BWD_ROWS(1, GG)
+#define AMB_BWD_ROWS2(GG) AMB_BWD_ROWS(2, GG)
+#define AMB_BWD_ROWS0(GG) AMB_BWD_ROWS(0, GG)
+        if (act == AMB_ACT_LRELU) AMB_ROWS_G(AMB_BWD_ROWS1);
+        else if (act == AMB_ACT_RELU6) AMB_ROWS_G(AMB_BWD_ROWS2);
+        else AMB_ROWS_G(AMB_BWD_ROWS0);
+#undef AMB_BWD_ROWS
+#undef AMB_BWD_ROWS0
+#undef AMB_BWD_ROWS1
+#undef AMB_BWD_ROWS2
+    } else if (g.list) {
         if (act == AMB_ACT_LRELU) AMB_BWD(1, true);
         else if (act == AMB_ACT_RELU6) AMB_BWD(2, true);
         else AMB_BWD(0, true);
@@ -554,6 +924,31 @@ extern "C" int amb_count_voxels(const amb_geo* a, double* out, void* stream) {
 extern "C" int amb_add(const void* a, const void* b, void* out, long n, void* stream) {
     AMB_CHECK(n % 8 == 0, AMB_ERR_ARG, "amb_add: n must be a multiple of 8");
     add_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n / 8);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_zero_shell(const amb_geo* a, void* x, void* stream) {
+    Geo g;
+    if (int e = make_geo(a, g)) return e;
+    AMB_CHECK(g.list && g.active && x, AMB_ERR_ARG, "amb_zero_shell needs the active mask and its work-list");
+    int ctas = g.N * g.fd * g.fh * g.fw;
+    if (ctas > num_sms() * 8) ctas = num_sms() * 8;
+    zero_shell_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(g, (bf16*)x);
+    AMB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int amb_add_parity0(const amb_geo* a, const void* coarse, void* fine, void* stream) {
+    Geo g;
+    if (int e = make_geo(a, g)) return e;
+    AMB_CHECK(coarse && fine, AMB_ERR_ARG, "amb_add_parity0: null argument");
+    int CG = g.C / 8, block = pick_block(CG);
+    if (block < 0) return block;
+    if (g.list)
+        add_parity0_kernel<true><<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(g, (const bf16*)coarse, (bf16*)fine);
+    else
+        add_parity0_kernel<false><<<grid_for(host_items_upper(g), block), block, 0, (cudaStream_t)stream>>>(g, (const bf16*)coarse, (bf16*)fine);
     AMB_LAUNCH_CHECK();
     return 0;
 }

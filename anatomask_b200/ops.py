@@ -8,6 +8,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -193,6 +195,40 @@ def to_ncdhw_f32(xi: torch.Tensor) -> torch.Tensor:
 # out of one pool that the engine clears with a single memset at the start of the step, instead of ~100 fill launches.
 ZERO_POOL = None          # {'buf': uint8 tensor, 'off': int} while a step runs
 
+# Engine mode: masked encoder tensors are not zero-filled where nothing reads them.  Every consumer of a sparse tensor at a
+# resolution whose patch edge is >= 8 voxels walks the active-patch work-list and reads at most one voxel beyond a visible
+# patch, so clearing that 1-voxel shell (amb_zero_shell) — or nothing at all for tensors only ever read at visible voxels —
+# replaces the full-tensor fills (1.0 ms of a 22 ms STUNet-B step).  Off outside an engine step: the module API keeps the
+# reference's contract (masked voxels of every sparse layer's output are zero).  AMB_NO_LEAN_ZERO=1 disables it (A/B);
+# AMB_POISON=1 fills every such allocation with NaN first, so a consumer that does read beyond the shell shows up as a NaN loss.
+LEAN_ZERO = False
+POISON = bool(os.environ.get('AMB_POISON'))
+
+
+class lean_zero:
+    def __enter__(self):
+        global LEAN_ZERO
+        self.prev = LEAN_ZERO
+        LEAN_ZERO = not os.environ.get('AMB_NO_LEAN_ZERO')
+
+    def __exit__(self, *exc):
+        global LEAN_ZERO
+        LEAN_ZERO = self.prev
+
+
+def _sparse_alloc(like: torch.Tensor, mode: str) -> torch.Tensor:
+    """mode 'full': zero-filled; 'shell' / 'none': uninitialised (the caller clears the shell for 'shell')."""
+    if mode == 'full':
+        return torch.zeros_like(like)
+    t = torch.empty_like(like)
+    if POISON:
+        t.fill_(float('nan'))
+    return t
+
+
+def zero_shell(t: torch.Tensor, m: 'MaskCtx') -> None:
+    L.call('amb_zero_shell', C.byref(m.geo(t, True)), _p(t), _stream())
+
 
 def _zeros_small(numel: int, dtype, device) -> torch.Tensor:
     pool = ZERO_POOL
@@ -298,7 +334,8 @@ class ConvFn(torch.autograd.Function):
     2×8×8 tile fits a patch — masked tiles are never computed."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, k, stride, m, transposed, impl, stats=None, zero_inactive=True, zero_bias_grad=False):
+    def forward(ctx, x, weight, bias, k, stride, m, transposed, impl, stats=None, zero_inactive=True, zero_bias_grad=False,
+                zero_dx=True):
         require_cuda(x)
         x = x.contiguous()
         N, D, H, W, Cin = x.shape
@@ -329,6 +366,7 @@ class ConvFn(torch.autograd.Function):
         ctx.flops = flops
         ctx.cfg = (k, stride, m, transposed, impl, bias is not None)
         ctx.zero_bias_grad = zero_bias_grad
+        ctx.zero_dx = zero_dx
         return y
 
     @staticmethod
@@ -342,7 +380,7 @@ class ConvFn(torch.autograd.Function):
         dx = dw = db = None
         need_w = ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])
         main = torch.cuda.current_stream()
-        side = _side_stream(x.device) if (need_w and ctx.needs_input_grad[0]) else None
+        side = _side_stream(x.device) if (need_w and (ctx.needs_input_grad[0] or getattr(ctx, 'force_side', False))) else None
         if side is not None:
             side.wait_stream(main)
 
@@ -406,8 +444,11 @@ class ConvFn(torch.autograd.Function):
             else:
                 Cout = weight.shape[0]
                 wp = _pack(weight, k3, Cin, Cout, 1, k3, Cin * k3)
-                need_zero = m is not None or (k == 1 and stride == 2)
-                dx = torch.zeros_like(x) if need_zero else torch.empty_like(x)
+                # a masked input gradient is zero-filled unless the caller vouches that it is only read at visible voxels
+                # (zero_dx=False: list-walking kernels skip masked tiles, dense-walking ones write every voxel themselves);
+                # a 1x1 stride-2 conv only ever produces the even voxels
+                need_zero = (m is not None and ctx.zero_dx) or (k == 1 and stride == 2)
+                dx = torch.zeros_like(x) if need_zero else _sparse_alloc(x, 'none')
                 with _Timed('conv_dgrad', ctx.flops):
                     _conv_call(L.OP_CONV_DGRAD, impl, (N, D, H, W), Cin, Cout, k, stride, dy, dx, wp, None, m,
                                sparse=m is not None)
@@ -415,7 +456,72 @@ class ConvFn(torch.autograd.Function):
             main.wait_stream(side)
         elif side is None and need_w:
             dw, db = weight_branch()
-        return dx, dw, db, None, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None, None
+
+
+class _SubCtx:
+    """Stand-in for an autograd ctx so that ConvFn.forward / backward can serve as building blocks of ConvPairFn."""
+
+    def __init__(self):
+        self.saved_tensors = ()
+        self.needs_input_grad = (False,) * 12
+
+    def save_for_backward(self, *ts):
+        self.saved_tensors = ts
+
+
+class ConvPairFn(torch.autograd.Function):
+    """conv1 (k3) and the 1x1 shortcut conv3 of a residual block, both reading the block input with the same stride
+    (P/STUNet_head.py:79-80,96-101).  One autograd node, so that the input gradient is formed in place: dx = dgrad(conv1),
+    then the shortcut's contribution — which lands on the even voxels only at stride 2 — is added by amb_add_parity0 instead
+    of a zero-filled full-resolution tensor plus autograd's full-resolution add.  Engine mode only (ops.LEAN_ZERO)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w3, b3, k, stride, m, impl, stats):
+        c1, c3 = _SubCtx(), _SubCtx()
+        y = ConvFn.forward(c1, x, w1, b1, k, stride, m, False, impl, stats, False, True, False)
+        sc = ConvFn.forward(c3, x, w3, b3, 1, stride, m, False, impl, None, False, False, False)
+        x = c1.saved_tensors[0]
+        ctx.save_for_backward(x, w1, w3)
+        ctx.subs = (c1, c3)
+        return y, sc
+
+    @staticmethod
+    def backward(ctx, dy, dsc):
+        x, w1, w3 = ctx.saved_tensors
+        c1, c3 = ctx.subs
+        nig = ctx.needs_input_grad
+        c1.saved_tensors, c3.saved_tensors = (x, w1), (x, w3)
+        c1.needs_input_grad = (nig[0], nig[1], nig[2]) + (False,) * 9
+        c3.needs_input_grad = (False, nig[3], nig[4]) + (False,) * 9
+        c3.force_side = True
+        k, stride, m, _, impl, _ = c1.cfg
+        dx, dw1, db1 = ConvFn.backward(c1, dy)[:3]
+        dw3, db3 = ConvFn.backward(c3, dsc)[1:3]
+        if nig[0]:
+            dsc = dsc.contiguous()
+            N, D, H, W, Cin = x.shape
+            Cout = w3.shape[0]
+            wp = _pack(w3, 1, Cin, Cout, 1, 1, Cin)
+            if stride == 2:
+                # the shortcut is a per-voxel (Cout -> Cin) product on the coarse grid; its result belongs to the even voxels
+                coarse = torch.zeros((N, D // 2, H // 2, W // 2, Cin), dtype=bf16, device=x.device) if m is not None else \
+                    torch.empty((N, D // 2, H // 2, W // 2, Cin), dtype=bf16, device=x.device)
+                with _Timed('conv_dgrad', c3.flops):
+                    _conv_call(L.OP_CONV_DGRAD, impl, (N, D // 2, H // 2, W // 2), Cin, Cout, 1, 1, dsc, coarse, wp, None, m,
+                               sparse=m is not None)
+                g = m.geo(coarse, True) if m is not None else dense_geo(coarse)
+                L.call('amb_add_parity0', C.byref(g), _p(coarse), _p(dx), _stream())
+            else:
+                dx3 = torch.zeros_like(x) if m is not None else torch.empty_like(x)
+                with _Timed('conv_dgrad', c3.flops):
+                    _conv_call(L.OP_CONV_DGRAD, impl, (N, D, H, W), Cin, Cout, 1, 1, dsc, dx3, wp, None, m, sparse=m is not None)
+                L.call('amb_add', _p(dx), _p(dx3), _p(dx), dx.numel(), _stream())
+        return dx, dw1, db1, dw3, db3, None, None, None, None, None
+
+
+def conv3d_pair(x, w1, b1, w3, b3, k, stride, m, impl=L.IMPL_AUTO, stats=None):
+    return ConvPairFn.apply(x, w1, b1, w3, b3, k, stride, m, impl, stats)
 
 
 def fused_stats_ok(cin: int, cout: int) -> bool:
@@ -429,9 +535,10 @@ def new_stats(channels: int, device) -> torch.Tensor:
 
 
 def conv3d(x, weight, bias=None, k=3, stride=1, m: Optional[MaskCtx] = None, impl=L.IMPL_AUTO, stats=None,
-           zero_inactive=True, zero_bias_grad=False):
-    """zero_bias_grad: the caller guarantees the output goes ONLY into a norm that uses batch statistics (then ∂loss/∂bias ≡ 0)."""
-    return ConvFn.apply(x, weight, bias, k, stride, m, False, impl, stats, zero_inactive, zero_bias_grad)
+           zero_inactive=True, zero_bias_grad=False, zero_dx=True):
+    """zero_bias_grad: the caller guarantees the output goes ONLY into a norm that uses batch statistics (then ∂loss/∂bias ≡ 0).
+    zero_dx=False: the caller guarantees the input gradient is only read at visible voxels (see LEAN_ZERO)."""
+    return ConvFn.apply(x, weight, bias, k, stride, m, False, impl, stats, zero_inactive, zero_bias_grad, zero_dx)
 
 
 def conv_transpose3d(x, weight, bias=None, impl=L.IMPL_AUTO):
@@ -520,7 +627,8 @@ class NormFn(torch.autograd.Function):
     and one of (Σg, Σg·x̂) backward — SparseSyncBatchNorm3d / nn.SyncBatchNorm (P/encoder3D.py:43, P/decoder3D.py:42)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, token, eps, act, m, running, momentum, group=None, sums=None):
+    def forward(ctx, x, gamma, beta, residual, token, eps, act, m, running, momentum, group=None, sums=None,
+                zero=('full', 'full', 'full')):
         x = x.contiguous()
         Cc = x.shape[-1]
         dev = x.device
@@ -541,13 +649,18 @@ class NormFn(torch.autograd.Function):
         L.call('amb_norm_finalize', C.byref(g), _p(sums), _p(gamma), _p(beta), eps, _p(scale), _p(shift), _p(saved),
                _p(rm), _p(rv), _p(nbt), momentum, _p(ntot), _stream())
         fill = token is not None
-        out = torch.zeros_like(x) if (sparse and not fill) else torch.empty_like(x)
+        # zero = (output, dx, dresidual) treatment of the masked voxels of a sparse tensor: 'full' zero-fill (the reference's
+        # contract), 'shell' (1-voxel shell of the visible patches only) or 'none' — see LEAN_ZERO
+        out = _sparse_alloc(x, zero[0]) if (sparse and not fill) else torch.empty_like(x)
         tok = token.reshape(-1).contiguous() if fill else None
         if residual is not None:
             residual = residual.contiguous()
         L.call('amb_norm_apply', C.byref(g), _p(x), _p(scale), _p(shift), _p(residual), _p(tok), act, _p(out),
                _stream())
+        if sparse and not fill and zero[0] == 'shell':
+            zero_shell(out, m)
         ctx.save_for_backward(x, residual, ss, ntot)
+        ctx.zero = zero
         ctx.cfg = (act, m, fill, token.shape if fill else None, group)
         ctx.param_refs = (gamma, beta, token)
         return out
@@ -577,12 +690,15 @@ class NormFn(torch.autograd.Function):
             import torch.distributed as dist
             local_gb = sums[:2 * Cc].float()
             dist.all_reduce(sums[:2 * Cc], group=group)
-        dx = torch.zeros_like(x) if sparse else torch.empty_like(x)
+        zero = ctx.zero if not fill else ('full', 'full', 'full')
+        dx = _sparse_alloc(x, zero[1]) if sparse else torch.empty_like(x)
         dres = None
         if residual is not None:
-            dres = torch.zeros_like(x) if sparse else torch.empty_like(x)
+            dres = _sparse_alloc(x, zero[2]) if sparse else torch.empty_like(x)
         L.call('amb_norm_bwd_apply', C.byref(g), _p(dout), _p(x), _p(residual), _p(scale), _p(shift), _p(saved),
                _p(sums), act, int(fill), _p(dx), _p(dres), p_dgamma, p_dbeta, _p(ntot), _stream())
+        if sparse and zero[1] == 'shell':
+            zero_shell(dx, m)
         if local_gb is not None:
             dbeta, dgamma = local_gb[:Cc], local_gb[Cc:]
         elif direct:
@@ -595,12 +711,12 @@ class NormFn(torch.autograd.Function):
                 t_ref.grad.view(-1).copy_(sums[2 * Cc:])           # fp64 sums → fp32 .grad, one launch
             else:
                 dtoken = sums[2 * Cc:].float().view(tshape)
-        return dx, dgamma, dbeta, dres, dtoken, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, dres, dtoken, None, None, None, None, None, None, None, None
 
 
 def masked_norm(x, gamma, beta, eps, m: MaskCtx, act=L.ACT_NONE, residual=None, running=None, momentum=0.0,
-                group=None, sums=None):
-    return NormFn.apply(x, gamma, beta, residual, None, eps, act, m, running, momentum, group, sums)
+                group=None, sums=None, zero=('full', 'full', 'full')):
+    return NormFn.apply(x, gamma, beta, residual, None, eps, act, m, running, momentum, group, sums, zero)
 
 
 def densify_norm_fill(x, gamma, beta, token, eps, m: MaskCtx, running=None, momentum=0.0, group=None):

@@ -232,7 +232,7 @@ class PretrainEngine:
         zeros = torch.zeros(B, Lp, dtype=torch.float32, device=inp.device)
         _, mk = ops.hard_mask(zeros, 0, m.len_keep, seed=0xA11CE, offset=0, offset_dev=self.step_counter)
         mask1 = mk.bool().view(B, 1, m.fmap_h, m.fmap_w, m.fmap_d)
-        with torch.no_grad():
+        with torch.no_grad(), ops.lean_zero():
             rec1 = self.teacher.reconstruct(inp, mask1)
             recon = self.teacher.teacher_loss(inp, rec1, mask1)
         mask, _ = self.teacher.generate_mask(recon, guide=True, epoch=len_loss_epoch, total_epoch=self.epochs - 1)
@@ -269,11 +269,12 @@ class PretrainEngine:
             self.buckets.begin_step()
             ops.MARK_CALLBACK = lambda tag: self.buckets.start(group_of_mark[tag])
         try:
-            rec = m.reconstruct(inp, mask)
-            loss, _ = ops.PatchLossFn.apply(inp, rec, mask[:, 0].to(torch.uint8).contiguous(), True)
-            self.arena.zero_grad()
-            ops.DEFER_WGRAD = defer_wgrad          # wgrad chain → side stream, written straight into the arena views
-            loss.backward()
+            with ops.lean_zero():                  # masked voxels nothing reads are not zero-filled (ops.LEAN_ZERO)
+                rec = m.reconstruct(inp, mask)
+                loss, _ = ops.PatchLossFn.apply(inp, rec, mask[:, 0].to(torch.uint8).contiguous(), True)
+                self.arena.zero_grad()
+                ops.DEFER_WGRAD = defer_wgrad      # wgrad chain → side stream, written straight into the arena views
+                loss.backward()
         finally:
             ops.DEFER_WGRAD = False
             ops.MARK_CALLBACK = None
@@ -384,7 +385,7 @@ class PretrainEngine:
         B = inp.shape[0]
         if mask1 is None:
             mask1 = self.random_mask(B, inp.device)
-        with torch.no_grad():
+        with torch.no_grad(), ops.lean_zero():
             rec1 = self.teacher.reconstruct(inp, mask1)
             recon = self.teacher.teacher_loss(inp, rec1, mask1)
         mask, _ = self.teacher.generate_mask(recon, guide=True, epoch=epoch, total_epoch=self.epochs - 1)

@@ -196,6 +196,14 @@ int amb_norm_bwd_apply(const amb_geo* g, const void* dout, const void* x, const 
 int amb_count_voxels(const amb_geo* g, double* out, void* stream);
 /* plain elementwise add (decoder skip: x + to_dec[i], P/decoder3D.py:58): out = a + b, n bf16 elements */
 int amb_add(const void* a, const void* b, void* out, long n, void* stream);
+/* Engine-mode helpers for the masked encoder tensors (the `* mask` of P/encoder3D.py:12-15 without writing the zeros that
+ * nothing reads):
+ *   amb_zero_shell  : clears the 1-voxel shell around every visible patch where it lies inside masked patches — all a
+ *                     3x3x3 consumer that walks the active-patch list can read beyond the visible voxels
+ *   amb_add_parity0 : fine[n,2z,2y,2x,:] += coarse[n,z,y,x,:] — the input gradient of the residual block's 1x1 stride-2
+ *                     shortcut conv (P/STUNet_head.py:79-80,96-101) accumulated in place; `g` describes the COARSE tensor  */
+int amb_zero_shell(const amb_geo* g, void* x, void* stream);
+int amb_add_parity0(const amb_geo* g, const void* coarse, void* fine, void* stream);
 
 /* ---- patchify + per-patch (optionally mean/var-normalised) masked MSE — P/spark3D.py:130-138,
  *      P/AnatoMask.py:190-202, teacher score P/pretrain_AntoMask.py:423-425 ------------------------------------

@@ -625,3 +625,84 @@ def check_augment_full_size(reps=3, tol=3e-4):
         res[f'ms_per_volume_{name}'] = (time.time() - t0) / reps / 2 * 1e3
     print('RESULT augment_full_size', res)
     return res
+
+
+def check_zero_shell(Cc=32, S=32, N=2, f=2, seed=0):
+    """amb_zero_shell: exactly the masked voxels within one voxel (3x3x3 neighbourhood) of a visible patch of the same sample
+    become zero; every other voxel keeps its bits."""
+    from anatomask_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    mask = _rand_mask(N, f, seed=seed + 1)
+    x = (torch.randn(N, S, S, S, Cc, generator=g) + 3.0).to(bf16).to(dev)          # no zeros in the input
+    vis = _up(mask, S).float().to(dev)                                             # (N,1,S,S,S)
+    near = F.max_pool3d(vis, 3, 1, 1) > 0
+    shell = (near & (vis == 0))[:, 0].unsqueeze(-1)
+    want = torch.where(shell, torch.zeros_like(x), x)
+    got = x.clone()
+    ops.zero_shell(got, ops.MaskCtx(mask.to(dev)))
+    torch.cuda.synchronize()
+    assert torch.equal(got, want), f'zero_shell C={Cc} S={S} f={f}: {int((got != want).sum())} elements differ'
+    return {'shell_voxels': int(shell.sum()), 'of': int(vis.numel())}
+
+
+def check_add_parity0(Cc=32, S=32, N=2, f=2, masked=True, seed=0):
+    """amb_add_parity0: fine[:, 2z, 2y, 2x] += coarse[:, z, y, x] (visible patches only when masked), bf16 round-to-nearest."""
+    from anatomask_b200 import ops, _lib as L
+    import ctypes as C
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    fine = torch.randn(N, S, S, S, Cc, generator=g).to(bf16).to(dev)
+    coarse = torch.randn(N, S // 2, S // 2, S // 2, Cc, generator=g).to(bf16).to(dev)
+    want = fine.clone()
+    add = coarse.float()
+    m = None
+    if masked:
+        mask = _rand_mask(N, f, seed=seed + 1)
+        m = ops.MaskCtx(mask.to(dev))
+        add = add * _up(mask, S // 2)[:, 0].unsqueeze(-1).float().to(dev)
+    want[:, ::2, ::2, ::2] = (want[:, ::2, ::2, ::2].float() + add).to(bf16)
+    geo = m.geo(coarse, True) if m is not None else ops.dense_geo(coarse)
+    L.call('amb_add_parity0', C.byref(geo), ops._p(coarse), ops._p(fine), ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(fine, want), f'add_parity0: {int((fine != want).sum())} elements differ'
+    return {}
+
+
+def check_conv_pair(Cin=32, Cout=64, S=32, N=2, f=2, stride=2, seed=0, tol=1.5e-2):
+    """ConvPairFn (conv1 k3 + 1x1 shortcut on the same input, input gradient formed in place) against the two separate ConvFn
+    nodes + autograd's add, on visible voxels (the only ones the engine reads)."""
+    from anatomask_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(seed)
+    mask = _rand_mask(N, f, seed=seed + 1)
+    m = ops.MaskCtx(mask.to(dev))
+    vis = _up(mask, S)[:, 0].unsqueeze(-1).to(dev)
+    x = (torch.randn(N, S, S, S, Cin, generator=g).to(dev) * vis).to(bf16)
+    w1 = (torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5).to(dev)
+    w3 = (torch.randn(Cout, Cin, 1, 1, 1, generator=g) / Cin ** 0.5).to(dev)
+    b1, b3 = (0.1 * torch.randn(Cout, generator=g)).to(dev), (0.1 * torch.randn(Cout, generator=g)).to(dev)
+    So = S // stride
+    viso = _up(mask, So)[:, 0].unsqueeze(-1).to(dev)
+    dy = (torch.randn(N, So, So, So, Cout, generator=g).to(dev) * viso).to(bf16)
+    dsc = (torch.randn(N, So, So, So, Cout, generator=g).to(dev) * viso).to(bf16)
+    outs = []
+    for pair in (False, True):
+        xs = x.clone().requires_grad_(True)
+        ps = [t.clone().requires_grad_(True) for t in (w1, b1, w3, b3)]
+        if pair:
+            y, sc = ops.conv3d_pair(xs, ps[0], ps[1], ps[2], ps[3], 3, stride, m)
+        else:
+            y = ops.conv3d(xs, ps[0], ps[1], 3, stride, m)
+            sc = ops.conv3d(xs, ps[2], ps[3], 1, stride, m)
+        torch.autograd.backward([y, sc], [dy, dsc])
+        ops.join_side_stream(dev)
+        torch.cuda.synchronize()
+        keep = lambda t, v: torch.where(v.bool(), t.float(), torch.zeros((), device=dev))      # masked voxels may be unwritten
+        outs.append((keep(y, viso), keep(sc, viso), keep(xs.grad, vis), ps[0].grad, ps[2].grad, ps[3].grad))
+    names = ('y', 'sc', 'dx', 'dw1', 'dw3', 'db3')
+    res = {n: _rel(a, b) for n, a, b in zip(names, outs[1], outs[0])}
+    assert res['y'] < 1e-3 and res['sc'] < 1e-3, res           # same kernels; split-K layers commit fp32 atomics in any order
+    bad = {k: v for k, v in res.items() if not v < tol}
+    assert not bad, f'conv pair Cin={Cin} Cout={Cout} S={S} stride={stride}: {res}'
+    return res

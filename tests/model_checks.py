@@ -522,3 +522,49 @@ def check_checkpoint_resume(name='S64', batch=2, seed=7, tmp_dir='/tmp'):
     else:
         raise AssertionError('resume() accepted a checkpoint of a different model size')
     return res
+
+
+def check_lean_zero(name='S64', batch=2, seed=9):
+    """Engine mode leaves masked voxels that nothing reads unwritten (ops.LEAN_ZERO: 1-voxel shell zeroing, in-place shortcut
+    gradient).  The same teacher forward and student forward/backward with the mode OFF (full zero fills, the module API's
+    behaviour) and ON with every such allocation POISONED with NaN must agree: any kernel that reads beyond the cleared shell
+    turns the loss / gradients into NaN; the difference must stay within the run-to-run noise of the path's fp32 atomics."""
+    from anatomask_b200 import ops
+    from anatomask_b200.trainer import PretrainEngine
+    cfg = rp.CONFIGS[name]
+    inp = rp.make_input(cfg, batch, seed).cuda()
+    active = rp.random_mask(cfg, batch, torch.Generator().manual_seed(seed)).cuda()
+    eng = PretrainEngine(build(cfg, seed, anatomask=True), lr=1e-4, epochs=1000, anatomask=True, mask_rng='device')
+
+    def run(lean: bool, poison: bool):
+        if lean:
+            os.environ.pop('AMB_NO_LEAN_ZERO', None)
+        else:
+            os.environ['AMB_NO_LEAN_ZERO'] = '1'
+        ops.POISON = poison
+        try:
+            with torch.no_grad(), ops.lean_zero():
+                rec_t = eng.teacher.reconstruct(inp, active).float().clone()
+            loss = eng._student_fwd_bwd(inp, active, defer_wgrad=True)
+            ops.join_side_stream(inp.device)
+            torch.cuda.synchronize()
+            return rec_t, float(loss), eng.arena.grad.clone()
+        finally:
+            ops.POISON = False
+            os.environ.pop('AMB_NO_LEAN_ZERO', None)
+
+    rec0, loss0, g0 = run(False, False)
+    rec0b, loss0b, g0b = run(False, False)
+    rec1, loss1, g1 = run(True, True)
+    assert torch.isfinite(rec1).all() and np.isfinite(loss1) and torch.isfinite(g1).all(), 'a kernel read an unwritten (poisoned) voxel'
+    noise = float((g0 - g0b).norm() / g0.norm())
+    diff = float((g0 - g1).norm() / g0.norm())
+    rec_diff = float((rec0 - rec1).norm() / rec0.norm())
+    rec_noise = float((rec0 - rec0b).norm() / rec0.norm())      # split-K layers commit fp32 atomics in any order → bf16 rounding flips
+    res = {'loss_full': loss0, 'loss_lean': loss1, 'grad_rerun_noise': noise, 'grad_diff_lean_vs_full': diff,
+           'teacher_rec_diff': rec_diff, 'teacher_rec_rerun_noise': rec_noise}
+    print('RESULT lean_zero', name, json.dumps(res))
+    assert abs(loss0 - loss1) <= 1e-4 * abs(loss0) + abs(loss0 - loss0b), res
+    assert rec_diff <= 3.0 * rec_noise + 1e-3, res
+    assert diff <= 3.0 * noise + 2e-3, res
+    return res

@@ -35,7 +35,12 @@ def test_weight_repack_layouts():
 @pytest.mark.parametrize('kw', [
     dict(mode='sparse', act=1, residual=True), dict(mode='sparse', act=0, residual=False, Cc=32, S=32),
     dict(mode='dense', act=2, residual=False), dict(mode='dense', act=0, residual=False, Cc=512, S=8),
-    dict(mode='fill', act=0, residual=False)])
+    dict(mode='fill', act=0, residual=False),
+    # row-group walk of the active-patch list: rows of 64 / 32 / 4 chunks, 1 / 2 / 4 rows per group, > 32 channel groups;
+    # 96 channels (12 channel groups, not a power of two) stays on the per-chunk walk
+    dict(mode='sparse', act=1, residual=True, Cc=512, S=8, f=8), dict(mode='sparse', act=1, residual=True, Cc=16, S=32, f=2),
+    dict(mode='sparse', act=0, residual=False, Cc=8, S=16, f=4), dict(mode='sparse', act=1, residual=True, Cc=128, S=16, f=4),
+    dict(mode='sparse', act=2, residual=False, Cc=256, S=8, f=4), dict(mode='sparse', act=1, residual=True, Cc=96, S=16, f=2)])
 def test_norm_family(kw):
     kc.check_norm(**kw)
 
@@ -266,3 +271,25 @@ def test_device_side_input_pipeline_full_size():
 def test_checkpoint_write_resume_roundtrip():
     """`_head_latest.pt` writer + resume on the GPU — same masks, step count, moments and teacher after resume"""
     mc.check_checkpoint_resume()
+
+
+@pytest.mark.parametrize('name', ['S64', 'B64'])
+def test_engine_lean_zero_mode_with_poisoned_allocations(name):
+    """ops.LEAN_ZERO (shell zeroing + in-place shortcut gradient) against the full-zero-fill path, masked allocations poisoned with NaN"""
+    mc.check_lean_zero(name)
+
+
+@pytest.mark.parametrize('kw', [dict(Cc=32, S=32, f=2), dict(Cc=64, S=32, f=4), dict(Cc=16, S=16, f=4, N=3), dict(Cc=512, S=8, f=8)])
+def test_zero_shell_of_visible_patches(kw):
+    kc.check_zero_shell(**kw)
+
+
+@pytest.mark.parametrize('kw', [dict(Cc=32, S=32, f=2), dict(Cc=64, S=16, f=4), dict(Cc=128, S=16, masked=False), dict(Cc=24, S=16, f=2)])
+def test_add_parity0(kw):
+    kc.check_add_parity0(**kw)
+
+
+@pytest.mark.parametrize('kw', [dict(Cin=32, Cout=64, S=32, f=2), dict(Cin=64, Cout=128, S=32, f=4), dict(Cin=128, Cout=256, S=16, f=4),
+                                dict(Cin=32, Cout=32, S=32, f=2, stride=1)])
+def test_conv_pair_matches_separate_convs(kw):
+    kc.check_conv_pair(**kw)
