@@ -311,6 +311,189 @@ bwd_apply_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Dense walk with batched loads (the decoder's BatchNorm passes, 0.27 - 1.6 GB each): a thread owns chunk ids
+// tid + k·T (T = threads in the grid, a multiple of the channel-group count, so its channel group is fixed) and issues the
+// 128-bit loads of DB consecutive k before consuming any of them.
+// ------------------------------------------------------------------------------------------------------------
+#define DB 4
+template <int MODE, int ACT>
+__global__ void __launch_bounds__(512, 1) reduce_dense_kernel(Geo g, const bf16* __restrict__ x, const bf16* __restrict__ dout,
+                                                           const bf16* __restrict__ res, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, const float* __restrict__ saved,
+                                                           double* __restrict__ sums) {
+    extern __shared__ float sacc[];           // [2][C]
+    const int CG = g.C / 8;
+    for (int i = threadIdx.x; i < g.C * 2; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    float a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+    const int cg = threadIdx.x % CG;
+    float sc[8], sh[8];
+    if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j]; }
+    }
+    const long T = (long)gridDim.x * blockDim.x;
+    const long total = (long)g.N * g.D * g.H * g.W * CG;
+    for (long c0 = (long)blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += DB * T) {
+        uint4 vx[DB], vd[DB], vr[DB];
+#pragma unroll
+        for (int k = 0; k < DB; ++k) {
+            const long c = c0 + k * T;
+            if (c < total) {
+                vx[k] = __ldg(reinterpret_cast<const uint4*>(x) + c);
+                if (MODE == 1) {
+                    vd[k] = __ldg(reinterpret_cast<const uint4*>(dout) + c);
+                    if (res) vr[k] = __ldg(reinterpret_cast<const uint4*>(res) + c);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < DB; ++k) {
+            if (c0 + k * T >= total) break;
+            float f[8];
+            unpack_u4(vx[k], f);
+            if (MODE == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { a0[j] += f[j]; a1[j] += f[j] * f[j]; }
+            } else {
+                float d[8], rr[8];
+                unpack_u4(vd[k], d);
+                if (res) unpack_u4(vr[k], rr);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float uu = sc[j] * f[j] + sh[j] + (res ? rr[j] : 0.f);
+                    float gj = d[j] * act_grad(uu, ACT);
+                    a0[j] += gj;
+                    a1[j] += gj * f[j];
+                }
+            }
+        }
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            a1[j] = saved[g.C + cg * 8 + j] * (a1[j] - saved[cg * 8 + j] * a0[j]);
+    }
+    const bool shfl = CG < 32 && (CG & (CG - 1)) == 0 && (blockDim.x & 31) == 0;
+    if (shfl) {
+        for (int o = CG; o < 32; o <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], o);
+                a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], o);
+            }
+        }
+    }
+    if (!shfl || (threadIdx.x & 31) < CG) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&sacc[cg * 8 + j], a0[j]);
+            atomicAdd(&sacc[g.C + cg * 8 + j], a1[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < g.C; i += blockDim.x) {
+        atomicAdd(&sums[i], (double)sacc[i]);
+        atomicAdd(&sums[g.C + i], (double)sacc[g.C + i]);
+    }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(512, 1) apply_dense_kernel(Geo g, const bf16* __restrict__ x, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, const bf16* __restrict__ res,
+                                                          bf16* __restrict__ out) {
+    const int CG = g.C / 8;
+    const int cg = threadIdx.x % CG;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j]; }
+    const long T = (long)gridDim.x * blockDim.x;
+    const long total = (long)g.N * g.D * g.H * g.W * CG;
+    for (long c0 = (long)blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += DB * T) {
+        uint4 vx[DB], vr[DB];
+#pragma unroll
+        for (int k = 0; k < DB; ++k) {
+            const long c = c0 + k * T;
+            if (c < total) {
+                vx[k] = __ldg(reinterpret_cast<const uint4*>(x) + c);
+                if (res) vr[k] = __ldg(reinterpret_cast<const uint4*>(res) + c);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < DB; ++k) {
+            const long c = c0 + k * T;
+            if (c >= total) break;
+            float f[8], rr[8], o[8];
+            unpack_u4(vx[k], f);
+            if (res) unpack_u4(vr[k], rr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = act_fwd(sc[j] * f[j] + sh[j] + (res ? rr[j] : 0.f), ACT);
+            store8(out + c * 8, o);
+        }
+    }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(512, 1)
+bwd_apply_dense_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restrict__ x, const bf16* __restrict__ res,
+                       const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ saved,
+                       const double* __restrict__ sums, bf16* __restrict__ dx, bf16* __restrict__ dres,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, const double* n_total) {
+    const int CG = g.C / 8;
+    const int cg = threadIdx.x % CG;
+    const double n = n_total ? *n_total : (double)g.N * g.D * g.H * g.W;
+    float sc[8], sh[8], ca[8], cb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int c = cg * 8 + j;
+        sc[j] = scale[c]; sh[j] = shift[c];
+        const float mu = saved[c], rs = saved[g.C + c];
+        const float m1 = (float)(sums[c] / n), m2 = (float)(sums[g.C + c] / n);
+        ca[j] = -sc[j] * m2 * rs;
+        cb[j] = -sc[j] * m1 - ca[j] * mu;
+    }
+    if (blockIdx.x == 0 && dgamma) {
+        for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+            dbeta[c] = (float)sums[c];
+            dgamma[c] = (float)sums[g.C + c];
+        }
+    }
+    const long T = (long)gridDim.x * blockDim.x;
+    const long total = (long)g.N * g.D * g.H * g.W * CG;
+    for (long c0 = (long)blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += DB * T) {
+        uint4 vx[DB], vd[DB], vr[DB];
+#pragma unroll
+        for (int k = 0; k < DB; ++k) {
+            const long c = c0 + k * T;
+            if (c < total) {
+                vd[k] = __ldg(reinterpret_cast<const uint4*>(dout) + c);
+                vx[k] = __ldg(reinterpret_cast<const uint4*>(x) + c);
+                if (res) vr[k] = __ldg(reinterpret_cast<const uint4*>(res) + c);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < DB; ++k) {
+            const long c = c0 + k * T;
+            if (c >= total) break;
+            float d[8], f[8], rr[8], o[8], gg[8];
+            unpack_u4(vd[k], d);
+            unpack_u4(vx[k], f);
+            if (res) unpack_u4(vr[k], rr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float uu = sc[j] * f[j] + sh[j] + (res ? rr[j] : 0.f);
+                gg[j] = d[j] * act_grad(uu, ACT);
+                o[j] = fmaf(sc[j], gg[j], fmaf(ca[j], f[j], cb[j]));
+            }
+            store8(dx + c * 8, o);
+            if (dres) store8(dres + c * 8, gg);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Row-group walk of the active-patch list (the sparse encoder's norms).  The per-chunk walk above decodes a patch id
 // (three 32-bit divisions) for every 16-byte item; here one warp iteration covers G = min(4, P) consecutive y-rows of one
 // patch at one z — a lane decodes once and then touches the same 16-byte column of G rows (G independent 128-bit loads in
@@ -715,6 +898,32 @@ static int rows_grid(const Geo& g, K kernel, size_t smem) {
         else { LAUNCH(1); }                          \
     } while (0)
 
+// grid of the per-chunk reduce kernels.  Every CTA ends with 2·C fp64 atomics onto the same 2·C addresses, so a small tensor
+// spread over thousands of CTAs is bound by that tail (33 MB took 50 µs): at least 32 chunks per thread, and never more CTAs
+// than are resident at once.
+template <typename K>
+static int reduce_grid(long work_items, int block, K kernel, size_t smem) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem) != cudaSuccess || occ < 1) occ = 2;
+    long b = (work_items + (long)block * 32 - 1) / ((long)block * 32);
+    const long cap = (long)num_sms() * occ;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+template <typename K>
+static int dense_grid(long chunks, int block, K kernel, size_t smem) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem) != cudaSuccess || occ < 1) occ = 1;
+    long b = (chunks + (long)block * 8 - 1) / ((long)block * 8);
+    const long cap = (long)num_sms() * occ;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+static bool dense_batched_ok() { return getenv("AMB_NORM_NO_DENSE_BATCH") == nullptr; }
+
 static long host_items_upper(const Geo& g) { return (long)g.N * g.D * g.H * g.W * (g.C / 8); }
 
 }  // namespace amb
@@ -759,10 +968,14 @@ extern "C" int amb_norm_stats(const amb_geo* a, const void* x, double* sums, voi
         AMB_ROWS_G(AMB_STATS_ROWS);
 #undef AMB_STATS_ROWS
     } else if (g.list)
-        reduce_kernel<0, 0, true, false><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>(
+        reduce_kernel<0, 0, true, false><<<reduce_grid(host_items_upper(g), block, reduce_kernel<0, 0, true, false>, g.C * 3 * sizeof(float)), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>(
             g, (const bf16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, sums, nullptr);
-    else
-        reduce_kernel<0, 0, false, false><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>(
+    else if (dense_batched_ok()) {
+        const size_t sm = g.C * 2 * sizeof(float);
+        reduce_dense_kernel<0, 0><<<reduce_grid(host_items_upper(g), block, reduce_dense_kernel<0, 0>, sm), block, sm, (cudaStream_t)stream>>>(
+            g, (const bf16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, sums);
+    } else
+        reduce_kernel<0, 0, false, false><<<reduce_grid(host_items_upper(g), block, reduce_kernel<0, 0, false, false>, g.C * 3 * sizeof(float)), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>(
             g, (const bf16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, sums, nullptr);
     AMB_LAUNCH_CHECK();
     return 0;
@@ -816,6 +1029,14 @@ extern "C" int amb_norm_apply(const amb_geo* a, const void* x, const float* scal
         if (act == AMB_ACT_LRELU) AMB_APPLY(1, true, false);
         else if (act == AMB_ACT_RELU6) AMB_APPLY(2, true, false);
         else AMB_APPLY(0, true, false);
+    } else if (dense_batched_ok()) {
+#define AMB_APPLY_DENSE(A)                                                                                         \
+    apply_dense_kernel<A><<<dense_grid(host_items_upper(g), block, apply_dense_kernel<A>, 0), block, 0, (cudaStream_t)stream>>>( \
+        g, (const bf16*)x, scale, shift, (const bf16*)residual, (bf16*)out)
+        if (act == AMB_ACT_LRELU) AMB_APPLY_DENSE(1);
+        else if (act == AMB_ACT_RELU6) AMB_APPLY_DENSE(2);
+        else AMB_APPLY_DENSE(0);
+#undef AMB_APPLY_DENSE
     } else {
         if (act == AMB_ACT_LRELU) AMB_APPLY(1, false, false);
         else if (act == AMB_ACT_RELU6) AMB_APPLY(2, false, false);
@@ -835,7 +1056,7 @@ extern "C" int amb_norm_bwd_reduce(const amb_geo* a, const void* dout, const voi
     int CG = g.C / 8, block = pick_block(CG);
     if (block < 0) return block;
 #define AMB_RED(A, LI, FI)                                                                                                       \
-    reduce_kernel<1, A, LI, FI><<<grid_for(host_items_upper(g), block), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>( \
+    reduce_kernel<1, A, LI, FI><<<reduce_grid(host_items_upper(g), block, reduce_kernel<1, A, LI, FI>, g.C * 3 * sizeof(float)), block, g.C * 3 * sizeof(float), (cudaStream_t)stream>>>( \
         g, (const bf16*)x, (const bf16*)dout, (const bf16*)residual, scale, shift, saved, act, fill, sums, dtoken)
     if (fill) { AMB_RED(0, false, true); }
     else if (rows_ok(g)) {
@@ -857,6 +1078,15 @@ extern "C" int amb_norm_bwd_reduce(const amb_geo* a, const void* dout, const voi
         if (act == AMB_ACT_LRELU) AMB_RED(1, true, false);
         else if (act == AMB_ACT_RELU6) AMB_RED(2, true, false);
         else AMB_RED(0, true, false);
+    } else if (dense_batched_ok()) {
+        const size_t sm = g.C * 2 * sizeof(float);
+#define AMB_RED_DENSE(A)                                                                                          \
+    reduce_dense_kernel<1, A><<<reduce_grid(host_items_upper(g), block, reduce_dense_kernel<1, A>, sm), block, sm, (cudaStream_t)stream>>>( \
+        g, (const bf16*)x, (const bf16*)dout, (const bf16*)residual, scale, shift, saved, sums)
+        if (act == AMB_ACT_LRELU) AMB_RED_DENSE(1);
+        else if (act == AMB_ACT_RELU6) AMB_RED_DENSE(2);
+        else AMB_RED_DENSE(0);
+#undef AMB_RED_DENSE
     } else {
         if (act == AMB_ACT_LRELU) AMB_RED(1, false, false);
         else if (act == AMB_ACT_RELU6) AMB_RED(2, false, false);
@@ -899,6 +1129,15 @@ extern "C" int amb_norm_bwd_apply(const amb_geo* a, const void* dout, const void
         if (act == AMB_ACT_LRELU) AMB_BWD(1, true);
         else if (act == AMB_ACT_RELU6) AMB_BWD(2, true);
         else AMB_BWD(0, true);
+    } else if (dense_batched_ok()) {
+#define AMB_BWD_DENSE(A)                                                                                           \
+    bwd_apply_dense_kernel<A><<<dense_grid(host_items_upper(g), block, bwd_apply_dense_kernel<A>, 0), block, 0, (cudaStream_t)stream>>>( \
+        g, (const bf16*)dout, (const bf16*)x, (const bf16*)residual, scale, shift, saved, sums, (bf16*)dx,          \
+        (bf16*)dres, dgamma, dbeta, n_total)
+        if (act == AMB_ACT_LRELU) AMB_BWD_DENSE(1);
+        else if (act == AMB_ACT_RELU6) AMB_BWD_DENSE(2);
+        else AMB_BWD_DENSE(0);
+#undef AMB_BWD_DENSE
     } else {
         if (act == AMB_ACT_LRELU) AMB_BWD(1, false);
         else if (act == AMB_ACT_RELU6) AMB_BWD(2, false);

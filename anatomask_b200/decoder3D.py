@@ -43,8 +43,11 @@ class UNetBlock(nn.Module):
         )
 
     def forward_internal(self, x):
-        x = ops.conv_transpose3d(x, self.up_sample.weight, self.up_sample.bias)
         c0, c3 = self.conv[0], self.conv[3]
+        # the ConvTranspose's bias gradient (Σ over voxels of the gradient w.r.t. its output) rides on the input-gradient kernel
+        # of the conv that consumes that output (ops.GradSumTap)
+        tap = ops.GradSumTap() if (torch.is_grad_enabled() and self.up_sample.bias is not None) else None
+        x = ops.conv_transpose3d(x, self.up_sample.weight, self.up_sample.bias, bias_grad_from=tap)
         b1, b4 = self.conv[1], self.conv[4]
         if not torch.is_grad_enabled() and all(isinstance(b, (nn.BatchNorm3d, nn.SyncBatchNorm)) and not b.training
                                                and b.track_running_stats for b in (b1, b4)):
@@ -53,7 +56,7 @@ class UNetBlock(nn.Module):
             return ops.conv3d_bn_eval(x, c3.weight, b4.weight, b4.bias, b4.running_mean, b4.running_var, b4.eps, ACT_NONE)
         # training-mode BN statistics come out of the conv epilogue (Σy, Σy² per channel)
         s0 = ops.new_stats(c0.out_channels, x.device) if (self.conv[1].training and ops.fused_stats_ok(c0.in_channels, c0.out_channels)) else None
-        x = ops.conv3d(x, c0.weight, None, 3, 1, stats=s0)
+        x = ops.conv3d(x, c0.weight, None, 3, 1, stats=s0, dx_sum=tap)
         x = _bn(self.conv[1], x, ACT_RELU6, s0)
         s3 = ops.new_stats(c3.out_channels, x.device) if (self.conv[4].training and ops.fused_stats_ok(c3.in_channels, c3.out_channels)) else None
         x = ops.conv3d(x, c3.weight, None, 3, 1, stats=s3)

@@ -327,6 +327,16 @@ def column_sums(x: torch.Tensor, m: Optional[MaskCtx]) -> torch.Tensor:
     return sums[:Cc].float()
 
 
+class GradSumTap:
+    """Carries Σ_voxels dx (per channel) from the input-gradient kernel of one conv to the bias gradient of the layer that
+    produced its input.  ∂loss/∂bias of the decoder's ConvTranspose3d (P/decoder3D.py:17) is the per-channel sum of the
+    gradient w.r.t. its output — which is exactly what the following conv's dgrad kernel writes, so its Σ epilogue delivers
+    the sum without another 537 MB pass over that tensor."""
+
+    def __init__(self):
+        self.sums = None
+
+
 class ConvFn(torch.autograd.Function):
     """nn.Conv3d (k∈{1,3}, stride∈{1,2}, pad k//2) and nn.ConvTranspose3d (k4 s2 p1) on channels-last bf16.
 
@@ -335,7 +345,7 @@ class ConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, k, stride, m, transposed, impl, stats=None, zero_inactive=True, zero_bias_grad=False,
-                zero_dx=True):
+                zero_dx=True, tap=None):
         require_cuda(x)
         x = x.contiguous()
         N, D, H, W, Cin = x.shape
@@ -367,6 +377,7 @@ class ConvFn(torch.autograd.Function):
         ctx.cfg = (k, stride, m, transposed, impl, bias is not None)
         ctx.zero_bias_grad = zero_bias_grad
         ctx.zero_dx = zero_dx
+        ctx.tap = tap           # conv: publishes Σdx here; ConvTranspose: takes its bias gradient from it (GradSumTap)
         return y
 
     @staticmethod
@@ -409,7 +420,11 @@ class ConvFn(torch.autograd.Function):
                     dw_ = torch.empty_like(weight) if dst_w is None else dst_w
                     L.call('amb_unpack_wgrad', _p(dwp), _p(dw_), k3, Cout, Cin, 1, Cin * k3, k3, _stream())
             if has_bias and ctx.needs_input_grad[2]:
-                if ctx.zero_bias_grad:
+                tap = getattr(ctx, 'tap', None)
+                if transposed and tap is not None and tap.sums is not None:
+                    db_ = tap.sums[:dy.shape[-1]].float()          # Σ over voxels of dy, from the consumer's dgrad epilogue
+                    tap.sums = None
+                elif ctx.zero_bias_grad:
                     # the conv feeds a batch-statistics norm: dy is that norm's input gradient, whose per-channel sum over the
                     # pooled voxels is identically zero (the mean subtraction) — the reference's own value here is fp32
                     # rounding noise (~1e-9 relative to the weights' gradients).  No pass over dy.
@@ -449,14 +464,18 @@ class ConvFn(torch.autograd.Function):
                 # a 1x1 stride-2 conv only ever produces the even voxels
                 need_zero = (m is not None and ctx.zero_dx) or (k == 1 and stride == 2)
                 dx = torch.zeros_like(x) if need_zero else _sparse_alloc(x, 'none')
+                tap = getattr(ctx, 'tap', None)
+                dstats = None
+                if tap is not None and m is None and fused_stats_ok(Cin, Cout) and impl != L.IMPL_DIRECT:
+                    dstats = tap.sums = _zeros_small(2 * Cin + 1, torch.float64, x.device)
                 with _Timed('conv_dgrad', ctx.flops):
                     _conv_call(L.OP_CONV_DGRAD, impl, (N, D, H, W), Cin, Cout, k, stride, dy, dx, wp, None, m,
-                               sparse=m is not None)
+                               sparse=m is not None, stats=dstats)
         if side is not None and not deferred:
             main.wait_stream(side)
         elif side is None and need_w:
             dw, db = weight_branch()
-        return dx, dw, db, None, None, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None, None, None
 
 
 class _SubCtx:
@@ -464,7 +483,8 @@ class _SubCtx:
 
     def __init__(self):
         self.saved_tensors = ()
-        self.needs_input_grad = (False,) * 12
+        self.needs_input_grad = (False,) * 13
+        self.tap = None
 
     def save_for_backward(self, *ts):
         self.saved_tensors = ts
@@ -535,14 +555,14 @@ def new_stats(channels: int, device) -> torch.Tensor:
 
 
 def conv3d(x, weight, bias=None, k=3, stride=1, m: Optional[MaskCtx] = None, impl=L.IMPL_AUTO, stats=None,
-           zero_inactive=True, zero_bias_grad=False, zero_dx=True):
+           zero_inactive=True, zero_bias_grad=False, zero_dx=True, dx_sum: Optional[GradSumTap] = None):
     """zero_bias_grad: the caller guarantees the output goes ONLY into a norm that uses batch statistics (then ∂loss/∂bias ≡ 0).
     zero_dx=False: the caller guarantees the input gradient is only read at visible voxels (see LEAN_ZERO)."""
-    return ConvFn.apply(x, weight, bias, k, stride, m, False, impl, stats, zero_inactive, zero_bias_grad, zero_dx)
+    return ConvFn.apply(x, weight, bias, k, stride, m, False, impl, stats, zero_inactive, zero_bias_grad, zero_dx, dx_sum)
 
 
-def conv_transpose3d(x, weight, bias=None, impl=L.IMPL_AUTO):
-    return ConvFn.apply(x, weight, bias, 4, 2, None, True, impl)
+def conv_transpose3d(x, weight, bias=None, impl=L.IMPL_AUTO, bias_grad_from: Optional[GradSumTap] = None):
+    return ConvFn.apply(x, weight, bias, 4, 2, None, True, impl, None, True, False, True, bias_grad_from)
 
 
 class StemFn(torch.autograd.Function):

@@ -10,9 +10,10 @@ A step = teacher forward (eval) â†’ per-patch teacher loss â†’ hard-mask top-k â
 the batch coming from pinned host memory every step (a different host batch each step) and the loss read back to the host.
 
   --model L --sbn      BASELINE config 4: STUNet-L, decoder SyncBN (P/pretrain_DDP.py:224-225), batch-sharded over N GPUs
-  --gpu-reference      also times the oracle port on the SAME GPU through torch + cuDNN under bf16 autocast (SURVEY Â§8d:
-                       "the real kernel-to-beat"); reported as `gpu_reference`, separate from `cpu_baseline`
-  --sweep              also times the step at epochs 0 / 998 (len_loss 0 / 153; the headline epoch 500 has len_loss 76)
+  At N=1 the line also carries (unless --no-extras):
+  gpu_reference        the oracle port on the SAME GPU through torch + cuDNN under bf16 autocast (SURVEY Â§8d: "the real
+                       kernel-to-beat"), separate from `cpu_baseline`
+  len_loss_sweep       the step at epochs 0 / 998 (len_loss 0 / 153; the headline epoch 500 has len_loss 76)
 """
 from __future__ import annotations
 
@@ -326,7 +327,7 @@ def run_ours(args):
            'd2h_bytes_per_step': 4 * world, 'ms_per_step': ms_e2e, 'last_loss': lv}
     # ---- easyâ†’hard schedule: the same step at the first and last epochs (len_loss 0 and 153 hard patches) ----------
     sweep = None
-    if args.sweep and use_graph:
+    if use_graph and (args.sweep or (world == 1 and not args.no_extras)):
         sweep = {'76': value}
         for ep, ll in ((0, '0'), (998, '153')):
             for _ in range(3):
@@ -357,10 +358,13 @@ def run_ours(args):
         out['len_loss_sweep'] = {'unit': UNIT, 'by_len_loss': sweep,
                                  'note': 'epochs 0 / 500 / 998 of 1000 â†’ 0 / 76 / 153 hard patches of 307 masked (SURVEY Â§8d C3)'}
     if rank == 0:
-        if world == 1 and args.gpu_reference:
+        if world == 1 and args.model == 'B' and S == 128 and (args.gpu_reference or not args.no_extras):
             del eng, model
             torch.cuda.empty_cache()
-            out['gpu_reference'] = gpu_reference_sample(dev, B)
+            try:
+                out['gpu_reference'] = gpu_reference_sample(dev, B)
+            except Exception as e:                                   # noqa: BLE001 â€” context only, never fails the bench line
+                out['gpu_reference'] = {'unavailable': f'{type(e).__name__}: {e}'[:200]}
         if world == 1 and not args.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline_sample()
         print(json.dumps(out))
@@ -394,7 +398,8 @@ if __name__ == '__main__':
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--sbn', action='store_true', help='decoder nn.SyncBatchNorm (BASELINE config 4)')
-    ap.add_argument('--sweep', action='store_true', help='also time epochs 0 and 998 (len_loss 0 / 153)')
+    ap.add_argument('--sweep', action='store_true', help='also time epochs 0 and 998 (len_loss 0 / 153); default at N=1')
+    ap.add_argument('--no-extras', action='store_true', help='N=1: skip the len_loss sweep and the same-GPU torch+cuDNN reference')
     ap.add_argument('--gpu-reference', action='store_true', help='also time the oracle port on this GPU (torch+cuDNN, bf16 autocast)')
     a = ap.parse_args()
     if a.impl == 'reference':
