@@ -723,35 +723,54 @@ bwd_apply_rows_kernel(Geo g, const bf16* __restrict__ dout, const bf16* __restri
 // Engine mode (ops.LEAN_ZERO): a sparse tensor whose consumers all walk the active-patch list is read at most ONE voxel beyond
 // a visible patch (3x3x3 halo), so instead of zero-filling the whole tensor only the 1-voxel shell of every visible patch that
 // lies inside masked patches is cleared.  One CTA per visible patch.
-__global__ void __launch_bounds__(256) zero_shell_kernel(Geo g, bf16* __restrict__ x) {
+__device__ __forceinline__ void zero_slab(const Geo& g, bf16* __restrict__ x, uint32_t n, int pz, int py, int px, int dir,
+                                          int first, int stride) {
     const int P = g.P, CG = g.C / 8;
+    const int dz = dir / 9 - 1, dy = (dir / 3) % 3 - 1, dx = dir % 3 - 1;
+    const int lz = dz ? 0 : g.lgP, ly = dy ? 0 : g.lgP, lx = dx ? 0 : g.lgP;        // log2 extents of the slab
+    const int z0 = (pz << g.lgP) + (dz < 0 ? -1 : (dz > 0 ? P : 0));
+    const int y0 = (py << g.lgP) + (dy < 0 ? -1 : (dy > 0 ? P : 0));
+    const int x0 = (px << g.lgP) + (dx < 0 ? -1 : (dx > 0 ? P : 0));
+    const int items = CG << (lz + ly + lx);
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = first; i < items; i += stride) {
+        const int cg = i % CG;
+        const int v = i / CG;
+        const int vx = v & ((1 << lx) - 1), vy = (v >> lx) & ((1 << ly) - 1), vz = v >> (lx + ly);
+        const long voxel = (((long)n * g.D + z0 + vz) * g.H + y0 + vy) * g.W + x0 + vx;
+        *reinterpret_cast<uint4*>(x + voxel * g.C + cg * 8) = z4;
+    }
+}
+
+__global__ void __launch_bounds__(256) zero_shell_kernel(Geo g, bf16* __restrict__ x) {
     const uint32_t L = (uint32_t)(g.fd * g.fh * g.fw), hw = (uint32_t)(g.fh * g.fw);
     const int n_entries = *g.count;
-    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    // the shell splits into 26 slabs, one per neighbouring patch (face: P x P voxels, edge: P, corner: 1); a slab is cleared
+    // only when that neighbour exists and is masked.  The 26 visibility bytes are fetched by 26 threads at once (26 slab loops
+    // each behind its own load were latency-bound); the 6 faces are then cleared by the whole block, the 20 edges / corners by
+    // one warp each.
+    __shared__ unsigned char s_flag[27];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int e = blockIdx.x; e < n_entries; e += gridDim.x) {
         const uint32_t pid = (uint32_t)g.list[e];
         const uint32_t n = pid / L, l = pid - n * L;
         const int pz = (int)(l / hw), r2 = (int)(l - (uint32_t)pz * hw);
         const int py = r2 / g.fw, px = r2 - py * g.fw;
-        // the shell splits into 26 slabs, one per neighbouring patch (face: P x P voxels, edge: P, corner: 1); a slab is
-        // cleared only when that neighbour exists and is masked — one uniform test per slab, shifts inside it
+        __syncthreads();
+        if (threadIdx.x < 27) {
+            const int dir = threadIdx.x;
+            const int qz = pz + dir / 9 - 1, qy = py + (dir / 3) % 3 - 1, qx = px + dir % 3 - 1;
+            s_flag[dir] = dir != 13 && qz >= 0 && qz < g.fd && qy >= 0 && qy < g.fh && qx >= 0 && qx < g.fw &&
+                          !g.active[((n * g.fd + qz) * g.fh + qy) * g.fw + qx];
+        }
+        __syncthreads();
+        int k = 0;
         for (int dir = 0; dir < 27; ++dir) {
-            if (dir == 13) continue;
-            const int dz = dir / 9 - 1, dy = (dir / 3) % 3 - 1, dx = dir % 3 - 1;
-            const int qz = pz + dz, qy = py + dy, qx = px + dx;
-            if (qz < 0 || qz >= g.fd || qy < 0 || qy >= g.fh || qx < 0 || qx >= g.fw) continue;
-            if (g.active[((n * g.fd + qz) * g.fh + qy) * g.fw + qx]) continue;
-            const int lz = dz ? 0 : g.lgP, ly = dy ? 0 : g.lgP, lx = dx ? 0 : g.lgP;        // log2 extents of the slab
-            const int z0 = (pz << g.lgP) + (dz < 0 ? -1 : (dz > 0 ? P : 0));
-            const int y0 = (py << g.lgP) + (dy < 0 ? -1 : (dy > 0 ? P : 0));
-            const int x0 = (px << g.lgP) + (dx < 0 ? -1 : (dx > 0 ? P : 0));
-            const int items = CG << (lz + ly + lx);
-            for (int i = threadIdx.x; i < items; i += blockDim.x) {
-                const int cg = i % CG;
-                const int v = i / CG;
-                const int vx = v & ((1 << lx) - 1), vy = (v >> lx) & ((1 << ly) - 1), vz = v >> (lx + ly);
-                const long voxel = (((long)n * g.D + z0 + vz) * g.H + y0 + vy) * g.W + x0 + vx;
-                *reinterpret_cast<uint4*>(x + voxel * g.C + cg * 8) = z4;
+            const int nz = (dir / 9 != 1) + ((dir / 3) % 3 != 1) + (dir % 3 != 1);      // 1 = face, 2 = edge, 3 = corner
+            if (nz == 1) {
+                if (s_flag[dir]) zero_slab(g, x, n, pz, py, px, dir, threadIdx.x, blockDim.x);
+            } else if (nz >= 2) {
+                if ((k++ & 7) == warp && s_flag[dir]) zero_slab(g, x, n, pz, py, px, dir, lane, 32);
             }
         }
     }

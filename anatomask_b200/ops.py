@@ -263,12 +263,14 @@ def _pack(w: torch.Tensor, T: int, A: int, B: int, st: int, sa: int, sb: int) ->
 
 class PackPlan:
     """One-launch packing of every conv weight a step uses (amb_pack_weights_batched).  Built from the (key, weight)
-    pairs recorded during one eager step; the weights are views of the parameter arenas, so their addresses are stable."""
+    pairs recorded during one eager step; the weights are views of the parameter arenas, so their addresses are stable.
+    `group_of(weight)` splits the jobs into separately launched groups (the engine packs the teacher's weights on the main
+    stream and the student's — not needed before the student forward, a teacher forward later — on the side stream)."""
 
-    def __init__(self, record):
+    def __init__(self, record, group_of=None):
         import numpy as np
-        seen, jobs, self.cache, self._keep = set(), [], {}, []
-        tile = 0
+        seen, self.cache, self._keep = set(), {}, []
+        jobs, tiles = {}, {}
         for key, w in record:
             if key in seen:
                 continue
@@ -280,25 +282,32 @@ class PackPlan:
             else:
                 continue                                   # layout outside the tiled kernel: stays a per-call pack
             seen.add(key)
+            grp = 0 if group_of is None else int(group_of(w))
             ta, tb = (4, 64) if b_fast else (16, 16)
             tiles_a, tiles_b, tchunks = -(-A // ta), -(-B // tb), -(-T // 32)
             out = torch.empty((T, A, B), dtype=bf16, device=w.device)
-            jobs.append((ptr, out.data_ptr(), T, A, B, b_fast, tile, tiles_b, tchunks, 0))
-            tile += tiles_a * tiles_b * tchunks
+            tile = tiles.get(grp, 0)
+            jobs.setdefault(grp, []).append((ptr, out.data_ptr(), T, A, B, b_fast, tile, tiles_b, tchunks, 0))
+            tiles[grp] = tile + tiles_a * tiles_b * tchunks
             self.cache[key] = out
             self._keep.append(w)
-        self.n_jobs, self.total_tiles = len(jobs), tile
         dt = np.dtype([('src', np.uint64), ('dst', np.uint64), ('T', np.int32), ('A', np.int32), ('B', np.int32),
                        ('b_fast', np.int32), ('tile_begin', np.int32), ('tiles_b', np.int32), ('tchunks', np.int32),
                        ('pad', np.int32)])
         assert dt.itemsize == 48
-        table = np.array(jobs, dtype=dt)
         dev = record[0][1].device if record else 'cuda'
-        self.table = torch.from_numpy(table.view(np.uint8).copy()).to(dev) if jobs else None
+        self.groups = {}
+        for grp, js in jobs.items():
+            table = torch.from_numpy(np.array(js, dtype=dt).view(np.uint8).copy()).to(dev)
+            self.groups[grp] = (table, len(js), tiles[grp])
+        self.n_jobs = sum(v[1] for v in self.groups.values())
+        self.total_tiles = sum(v[2] for v in self.groups.values())
+        self.table = self.groups[0][0] if (len(self.groups) == 1 and 0 in self.groups) else None
 
-    def run(self):
-        if self.table is not None:
-            L.call('amb_pack_weights_batched', _p(self.table), self.n_jobs, self.total_tiles, _stream())
+    def run(self, group=None):
+        for grp, (table, n_jobs, total_tiles) in self.groups.items():
+            if group is None or grp == group:
+                L.call('amb_pack_weights_batched', _p(table), n_jobs, total_tiles, _stream())
 
 
 def _conv_call(op, impl, dims, Cin, Cout, k, stride, x, y, w, bias=None, m: Optional[MaskCtx] = None, sparse=False,

@@ -212,7 +212,16 @@ class PretrainEngine:
         if plan is None:
             ops.PACK_RECORD = []
         else:
-            plan.run()
+            # teacher operands on this stream (the teacher forward is next); the student's — two thirds of the bytes, first
+            # read a whole teacher forward later — on the side stream, next to the teacher's small latency-bound layers
+            plan.run(0)
+            side = ops._side_stream(inp.device) if 1 in plan.groups else None
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    plan.run(1)
+            elif 1 in plan.groups:
+                plan.run(1)
             ops.PACK_CACHE = plan.cache
         if getattr(self, '_zero_pool', None) is None:
             self._zero_pool = torch.empty(4 << 20, dtype=torch.uint8, device=inp.device)
@@ -223,7 +232,8 @@ class PretrainEngine:
         finally:
             ops.ZERO_POOL = None
             if plan is None and ops.PACK_RECORD:
-                self._pack_plan = ops.PackPlan(ops.PACK_RECORD)
+                lo, hi = self.arena.flat.data_ptr(), self.arena.flat.data_ptr() + self.arena.flat.numel() * 4
+                self._pack_plan = ops.PackPlan(ops.PACK_RECORD, group_of=lambda w: 1 if lo <= w.data_ptr() < hi else 0)
             ops.PACK_RECORD = None
             ops.PACK_CACHE = None
 
@@ -236,6 +246,7 @@ class PretrainEngine:
             rec1 = self.teacher.reconstruct(inp, mask1)
             recon = self.teacher.teacher_loss(inp, rec1, mask1)
         mask, _ = self.teacher.generate_mask(recon, guide=True, epoch=len_loss_epoch, total_epoch=self.epochs - 1)
+        ops.join_side_stream(inp.device)           # the student's packed weights (side stream) are complete
         loss = self._student_fwd_bwd(inp, mask, defer_wgrad=True)
         ops.join_side_stream(inp.device)
         return loss, mask, recon

@@ -1,6 +1,7 @@
 # round-2 final evidence (1 GPU): launch list of one step (time + DRAM bytes + tensor-pipe %), section captures of the HBM-bound
 # kernels, final bench line (with sweep + GPU reference + CPU baseline), mask-ratio sweep
 cd $GRAFT_REPO_ROOT
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "lean_zero or zero_shell or stem" 2>&1 | tail -2
 echo "=== ncu launch list (one eager step)"
 timeout 1500 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
     --clock-control none --csv --log-file gpurun_out/r2f_launches.csv python tests/ncu_target_step.py > gpurun_out/ncu_e.log 2>&1

@@ -171,6 +171,15 @@ def test_pack_plan_job_table():
     for (key, w), job in zip([rec[0], rec[1], rec[3]], tab):
         assert int(job['src']) == w.data_ptr() and int(job['dst']) == plan.cache[key].data_ptr()
         assert tuple(plan.cache[key].shape) == (key[1], key[2], key[3]) and plan.cache[key].dtype == torch.bfloat16
+    # groups (the engine: teacher weights on the main stream, student weights on the side stream): every group is a job table
+    # of its own whose tile ranges start at 0, and together they cover the same jobs
+    split = ops.PackPlan(rec, group_of=lambda w: 1 if w is w2 else 0)
+    assert sorted(split.groups) == [0, 1] and split.n_jobs == 3 and split.total_tiles == sum(tiles) and split.table is None
+    t0, n0, tiles0 = split.groups[0]
+    t1, n1, tiles1 = split.groups[1]
+    assert (n0, tiles0, n1, tiles1) == (2, tiles[0] + tiles[1], 1, tiles[2])
+    assert list(t0.numpy().view(dt)['tile_begin']) == [0, tiles[0]] and list(t1.numpy().view(dt)['tile_begin']) == [0]
+    assert int(t1.numpy().view(dt)['src'][0]) == w2.data_ptr()
 
 
 def test_augmentation_draws_follow_the_reference_order():
