@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libanatomask_b200.so')
-SOURCES = ['misc.cu', 'norm.cu', 'conv_direct.cu', 'conv_igemm.cu', 'conv_igemm3.cu', 'conv_igemm4.cu', 'conv_wgrad_tc.cu',
+SOURCES = ['misc.cu', 'norm.cu', 'conv_direct.cu', 'conv_igemm.cu', 'conv_igemm3.cu', 'conv_igemm4.cu', 'conv_igemm4t.cu', 'conv_wgrad_tc.cu',
            'conv_wgrad_halo.cu', 'conv_wgrad_ns.cu', 'sparse_layers.cu', 'augment.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '-Wno-deprecated-gpu-targets']

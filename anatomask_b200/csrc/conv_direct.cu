@@ -211,6 +211,11 @@ extern "C" int amb_conv(const amb_conv_args* a) {
             if (r3 < 0) return r3;
             if (r3 == 1) return 0;
         }
+        if (a->op == AMB_OP_CONVT && a->impl != AMB_IMPL_TCGEN05_V1) {
+            int rt = igemm4t_conv(p, a);         // ConvTranspose forward, Cout <= 64: kz taps stacked along N over halo planes
+            if (rt < 0) return rt;
+            if (rt == 1) return 0;
+        }
         int r = igemm_conv(p, a);
         if (r < 0) return r;
         if (r == 1) return 0;

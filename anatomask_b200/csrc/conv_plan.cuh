@@ -187,6 +187,7 @@ int igemm_conv(const Plan& p, const amb_conv_args* a);
 long igemm_workspace_bytes(const Plan& p, bool sparse_list);
 int igemm3_conv(const Plan& p, const amb_conv_args* a);
 int igemm4_conv(const Plan& p, const amb_conv_args* a);
+int igemm4t_conv(const Plan& p, const amb_conv_args* a);
 int igemm_wgrad(const Plan& p, const amb_wgrad_args* a);
 int igemm_wgrad_halo(const Plan& p, const amb_wgrad_args* a);
 int igemm_wgrad_ns(const Plan& p, const amb_wgrad_args* a);

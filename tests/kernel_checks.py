@@ -88,8 +88,8 @@ def check_conv(Cin=64, Cout=64, k=3, stride=1, S=16, N=2, impl=2, masked=False, 
     return res
 
 
-def check_convT(Cin=64, Cout=64, S=8, N=2, impl=2, seed=0, tol=1.5e-2):
-    from anatomask_b200 import ops
+def check_convT(Cin=64, Cout=64, S=8, N=2, impl=2, seed=0, tol=1.5e-2, fwd_kernel=None):
+    from anatomask_b200 import ops, _lib as L
     dev = _dev()
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(N, Cin, S, S, S, generator=g).to(bf16)
@@ -105,6 +105,9 @@ def check_convT(Cin=64, Cout=64, S=8, N=2, impl=2, seed=0, tol=1.5e-2):
     wp = w.to(dev).requires_grad_(True)
     bp = b.to(dev).requires_grad_(True)
     y = ops.conv_transpose3d(xi, wp, bp, impl)
+    if fwd_kernel is not None:          # the dispatcher must have picked this kernel for the forward pass
+        got = (L.load().amb_last_conv_kernel() or b'').decode()
+        assert got == fwd_kernel, f'convT Cin={Cin} Cout={Cout} S={S}: forward ran on {got}, expected {fwd_kernel}'
     y.backward(gy.to(dev).permute(0, 2, 3, 4, 1).contiguous())
     torch.cuda.synchronize()
     res = {'fwd': _rel(y.permute(0, 4, 1, 2, 3), yr.detach()), 'dgrad': _rel(xi.grad.permute(0, 4, 1, 2, 3), xr.grad),

@@ -72,9 +72,14 @@ def test_conv_fwd_dgrad_wgrad(kw):
 
 @pytest.mark.parametrize('kw', [dict(Cin=16, Cout=8, S=4, impl=D), dict(Cin=64, Cout=64, S=8, impl=T),
                                 dict(Cin=512, Cout=512, S=4, impl=T), dict(Cin=32, Cout=32, S=8, impl=T),
-                                # halo-plane kernel, 8 parity classes as output groups (input edge >= 16, Cout <= 64)
                                 dict(Cin=64, Cout=64, S=16, impl=T), dict(Cin=64, Cout=32, S=16, N=1, impl=T),
-                                dict(Cin=128, Cout=64, S=16, N=1, impl=T), dict(Cin=32, Cout=16, S=20, N=1, impl=T)])
+                                dict(Cin=128, Cout=64, S=16, N=1, impl=T), dict(Cin=32, Cout=16, S=20, N=1, impl=T),
+                                # kz-stacked halo-plane forward (conv_igemm4t.cu: Cout <= 64, at least one unit per SM),
+                                # incl. ragged extents (partial y / x tiles, odd depth)
+                                dict(Cin=64, Cout=64, S=32, impl=T, fwd_kernel='igemm4t_kernel'),
+                                dict(Cin=32, Cout=16, S=36, N=1, impl=T, fwd_kernel='igemm4t_kernel'),
+                                dict(Cin=64, Cout=32, S=27, N=2, impl=T, fwd_kernel='igemm4t_kernel'),
+                                dict(Cin=128, Cout=32, S=26, N=2, impl=T, fwd_kernel='igemm4t_kernel')])
 def test_conv_transpose(kw):
     kc.check_convT(**kw)
 
