@@ -112,8 +112,15 @@ class STUNet(nn.Module):
         return self.dims[:5]
 
     def forward(self, x, hierarchical=False):
+        from .parallel import ENCODER_DEEP_FROM_STAGE
         feats = []
-        for blocks in self.conv_blocks_context:
-            x = blocks(x)
+        for s, blocks in enumerate(self.conv_blocks_context):
+            if s == ENCODER_DEEP_FROM_STAGE:
+                # backward reaches this point when the deep stages — most of the encoder's parameters — have their
+                # gradients: their all-reduce overlaps the shallow stages' backward pass (parallel.GradBuckets)
+                xin, = ops.backward_mark('encoder_deep_done', x)
+            else:
+                xin = x
+            x = blocks(xin)
             feats.append(x)
         return feats if hierarchical else x

@@ -6,8 +6,9 @@ One process per GPU, batch sharded across ranks, the only data-path collectives 
   shard_batch         the per-rank slice of a global batch, as the DDP scripts compute it
   clip_scale          the factor the fused AdamW kernel applies to a SUM-all-reduced gradient (1/world and the global-norm
                       clip folded together) — host mirror of `adamw_dev_kernel`'s arithmetic
-  GradBuckets         the gradient arena split into the three parameter groups in the order the backward pass finishes
-                      them (decoder → densify → encoder); each group's all-reduce is started from a backward mark
+  GradBuckets         the gradient arena split into parameter groups in the order the backward pass finishes them
+                      (decoder → densify → deep encoder stages → shallow encoder stages); each group's all-reduce is
+                      started from a backward mark
                       (ops.backward_mark) so it overlaps the remaining backward work, and joined before the optimiser
 """
 from __future__ import annotations
@@ -40,11 +41,16 @@ def clip_scale(sumsq_of_summed_grads: float, world: int, max_norm: Optional[floa
 
 
 # parameter groups in backward-completion order (autograd runs later-created nodes first: the decoder's nodes all precede
-# the densify nodes, which precede the encoder's)
+# the densify nodes, which precede the encoder's; inside the encoder the deep stages — which hold 94 % of its parameters —
+# finish first, so they travel as their own bucket while the shallow, large-extent stages are still in their backward pass).
+# A name belongs to the FIRST group whose prefix it matches.
+ENCODER_DEEP_FROM_STAGE = 3                   # STUNet conv_blocks_context.{3,4}: 13.4 M of STUNet-B's 14.3 M encoder parameters
 GROUP_PREFIXES = (('decoder', ('dense_decoder.',)),
                   ('densify', ('densify_norms.', 'densify_projs.', 'mask_tokens.')),
+                  ('encoder_deep', tuple(f'sparse_encoder.sp_cnn.conv_blocks_context.{s}.' for s in range(ENCODER_DEEP_FROM_STAGE, 8))),
                   ('encoder', ('sparse_encoder.',)))
-MARK_OF_GROUP = {'decoder': 'decoder_done', 'densify': 'densify_done'}      # the encoder group is complete when backward returns
+# the last group is complete when backward returns
+MARK_OF_GROUP = {'decoder': 'decoder_done', 'densify': 'densify_done', 'encoder_deep': 'encoder_deep_done'}
 
 
 def bucket_ranges(offsets: Dict[str, Tuple[int, int]], n_live: int) -> List[Tuple[str, int, int]]:
@@ -53,8 +59,11 @@ def bucket_ranges(offsets: Dict[str, Tuple[int, int]], n_live: int) -> List[Tupl
     (dead parameters, buffers) are ignored.  Raises if a group is not contiguous or the groups do not tile [0, n_used)."""
     out = []
     covered = 0
+    claimed = set()
     for group, prefixes in GROUP_PREFIXES:
-        spans = sorted((o, o + k) for n, (o, k) in offsets.items() if n.startswith(prefixes) and o < n_live)
+        names = [n for n, (o, _) in offsets.items() if n.startswith(prefixes) and o < n_live and n not in claimed]
+        claimed.update(names)
+        spans = sorted((offsets[n][0], offsets[n][0] + offsets[n][1]) for n in names)
         if not spans:
             continue
         lo, hi = spans[0][0], spans[-1][1]

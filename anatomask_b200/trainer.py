@@ -152,6 +152,8 @@ class PretrainEngine:
         self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self._graphs = {}
         self._static_inp = None
+        self._stage = None                   # (copy stream, device buffer) of stage_input()
+        self._stage_ready = self._stage_consumed = None
         self._static_out = None
 
     # ---- pieces ---------------------------------------------------------------------------------------------
@@ -324,7 +326,7 @@ class PretrainEngine:
         if self._static_inp is None or self._static_inp.shape != inp.shape:
             self._static_inp = torch.empty_like(inp)
             self._graphs.clear()
-        self._static_inp.copy_(inp, non_blocking=True)
+        self._consume_input(inp)
         self._set_hyper(epoch)
         # world > 1: the NCCL collectives (bucketed gradient all-reduce started from the backward pass, SyncBN statistics)
         # are captured INTO the step graph, so a step stays one graph launch and the exchange overlaps the backward pass.
@@ -377,6 +379,36 @@ class PretrainEngine:
             graphs[0].replay()
         self.t += 1
         return out
+
+    # ---- input staging ------------------------------------------------------------------------------------
+    def stage_input(self, host: torch.Tensor) -> torch.Tensor:
+        """Starts the host → device copy of the NEXT batch on a copy stream while the current step runs (what the scripts'
+        pinned DataLoader + `.to(device, non_blocking=True)` do, P/pretrain_AntoMask.py:312-345, 419).  Returns the device
+        buffer; hand it to graph_step(), which waits for the copy and frees the buffer for the following stage_input()
+        as soon as it has taken the batch over.  One buffer: stage, step, stage, step, ..."""
+        dev = self.arena.flat.device
+        if self._stage is None or self._stage[1].shape != host.shape:
+            self._stage = (torch.cuda.Stream(dev), torch.empty(host.shape, dtype=torch.float32, device=dev))
+            self._stage_consumed = None
+        cs, buf = self._stage
+        if self._stage_consumed is not None:
+            cs.wait_event(self._stage_consumed)          # the previous batch has been copied out of the buffer
+        else:
+            cs.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cs):
+            buf.copy_(host, non_blocking=True)
+            self._stage_ready = torch.cuda.Event()
+            self._stage_ready.record(cs)
+        return buf
+
+    def _consume_input(self, inp: torch.Tensor):
+        staged = self._stage is not None and inp is self._stage[1]
+        if staged:
+            torch.cuda.current_stream().wait_event(self._stage_ready)
+        self._static_inp.copy_(inp, non_blocking=True)
+        if staged:
+            self._stage_consumed = torch.cuda.Event()
+            self._stage_consumed.record()
 
     # ---- steps ----------------------------------------------------------------------------------------------
     def spark_step(self, inp: torch.Tensor, active: Optional[torch.Tensor] = None, epoch: int = 0) -> torch.Tensor:

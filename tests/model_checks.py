@@ -348,6 +348,36 @@ def check_device_step(name='S64', batch=2, seed=1, steps=4):
     return {'losses': losses}
 
 
+def check_staged_input(name='S64', batch=2, seed=1, steps=5):
+    """PretrainEngine.stage_input: the next batch's host → device copy runs on a copy stream during the current step.  Each
+    step must train on ITS batch (the static graph input equals the host batch the step was given, also while the following
+    copy is already in flight) and the losses must equal those of the same batches fed through a plain `.to(device)`."""
+    from anatomask_b200.trainer import PretrainEngine
+    cfg = rp.CONFIGS[name]
+    hosts = [rp.make_input(cfg, batch, seed + i).pin_memory() for i in range(3)]
+    out = {}
+    for mode in ('plain', 'staged'):
+        eng = PretrainEngine(build(cfg, seed, anatomask=True), lr=1e-4, epochs=1000, anatomask=True, mask_rng='device')
+        losses, same = [], []
+        nxt = eng.stage_input(hosts[0]) if mode == 'staged' else None
+        for i in range(steps):
+            if mode == 'staged':
+                loss, _, _ = eng.graph_step(nxt, 500)
+                seen = eng._static_inp.clone()                       # enqueued before the next copy can land
+                nxt = eng.stage_input(hosts[(i + 1) % 3])
+            else:
+                loss, _, _ = eng.graph_step(hosts[i % 3].cuda(non_blocking=True), 500)
+                seen = eng._static_inp.clone()
+            same.append(bool(torch.equal(seen.cpu(), hosts[i % 3])))
+            losses.append(float(loss))
+        out[mode] = (losses, same)
+    d = max(abs(a - b) / abs(b) for a, b in zip(out['staged'][0], out['plain'][0]))
+    print('RESULT staged_input', name, json.dumps({'plain': out['plain'][0], 'staged': out['staged'][0], 'rel': d}))
+    assert all(out['plain'][1]) and all(out['staged'][1]), out
+    assert d < 5e-3, d
+    return out
+
+
 def check_graph_matches_eager(name='S64', batch=2, seed=1, steps=4):
     """The CUDA-graph replay (side-stream weight-gradient chain written straight into the arena, device-side scalars)
     against the same device-RNG step launched eagerly.  No host synchronisation between steps in either mode (losses are

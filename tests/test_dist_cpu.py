@@ -22,7 +22,10 @@ def _free_port():
 
 
 # a miniature of ParamArena.offsets: named_parameters order = encoder, decoder, densify norms / projs / tokens
-OFFSETS = {'sparse_encoder.sp_cnn.conv.weight': (0, 300), 'sparse_encoder.sp_cnn.conv.bias': (300, 20),
+OFFSETS = {'sparse_encoder.sp_cnn.conv_blocks_context.0.0.conv1.weight': (0, 100),
+           'sparse_encoder.sp_cnn.conv_blocks_context.2.0.conv1.weight': (100, 60),
+           'sparse_encoder.sp_cnn.conv_blocks_context.3.0.conv1.weight': (160, 140),
+           'sparse_encoder.sp_cnn.conv_blocks_context.4.0.conv2.bias': (300, 20),
            'dense_decoder.dec.0.up_sample.weight': (320, 500), 'dense_decoder.proj.bias': (820, 4),
            'densify_norms.0.weight': (824, 16), 'densify_projs.1.weight': (840, 100), 'mask_tokens.0': (940, 24),
            'densify_norms.4.weight': (1000, 8),                       # dead parameter: beyond n_live
@@ -41,7 +44,9 @@ def test_shard_batch_like_the_ddp_scripts():
 
 def test_bucket_ranges_follow_backward_completion_order():
     r = bucket_ranges(OFFSETS, N_LIVE)
-    assert r == [('decoder', 320, 824), ('densify', 824, 964), ('encoder', 0, 320)]
+    assert r == [('decoder', 320, 824), ('densify', 824, 964), ('encoder_deep', 160, 320), ('encoder', 0, 160)]
+    flat = {n.replace('conv_blocks_context', 'stages'): v for n, v in OFFSETS.items()}      # an encoder without STUNet's stage names
+    assert bucket_ranges(flat, N_LIVE) == [('decoder', 320, 824), ('densify', 824, 964), ('encoder', 0, 320)]
     broken = dict(OFFSETS)
     broken['sparse_encoder.late.weight'] = (900, 10)                  # an encoder tensor in the middle of another group
     with pytest.raises(RuntimeError):
@@ -73,12 +78,13 @@ def _worker(rank, world, port, ret):
         dist.all_gather(gathered, local)
         want = torch.stack(gathered).sum(0)
         b = GradBuckets(grad, OFFSETS, N_LIVE, dist.group.WORLD)
-        ok = b.order == ['decoder', 'densify', 'encoder']
-        # a step: the decoder mark fires, then densify; the encoder group is only started by finish()
+        ok = b.order == ['decoder', 'densify', 'encoder_deep', 'encoder']
+        # a step: the decoder mark fires, then densify, then the deep encoder stages; the shallow group is started by finish()
         b.begin_step()
         b.start('decoder')
         b.start('decoder')                                            # idempotent within a step
         b.start('densify')
+        b.start('encoder_deep')
         b.finish()
         ok = ok and torch.allclose(grad, want, atol=1e-6)
         # next step: no mark fires at all (eager path without marks) → finish() exchanges everything, exactly once

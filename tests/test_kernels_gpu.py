@@ -192,6 +192,10 @@ def test_device_rng_step_runs_without_host_sync():
     mc.check_device_step()
 
 
+def test_staged_input_copy_overlaps_the_step_and_feeds_the_right_batch():
+    mc.check_staged_input()
+
+
 def test_graph_replay_matches_eager_launches():
     mc.check_graph_matches_eager()
 
