@@ -15,18 +15,21 @@ import torch
 
 
 def head_checkpoint(model: torch.nn.Module, engine=None, train_loss=None, val_loss=None, epoch: int = 0) -> Dict:
-    sd = OrderedDict(('module.' + k, v.detach().clone()) for k, v in model.state_dict().items())
+    # .contiguous(): engine parameters may be strided views of taps-major arena storage; the file holds the reference's layout
+    sd = OrderedDict(('module.' + k, v.detach().clone().contiguous()) for k, v in model.state_dict().items())
     ckpt = {'network_weights': sd, 'optimizer_state': None, 'grad_scaler_state': None, 'train_loss': train_loss,
             'val_loss': val_loss, 'current_epoch': epoch}
     if engine is not None:
         from . import AnatoMask as _am
-        ckpt['optimizer_state'] = {'exp_avg': engine.m.clone(), 'exp_avg_sq': engine.v.clone(), 'step': engine.t,
+        # Adam moments per parameter, in the parameter's own shape and element order (independent of the arena's storage order)
+        moments = lambda flat: OrderedDict((n, v.detach().clone().contiguous()) for n, v in engine.arena.views(flat).items())
+        ckpt['optimizer_state'] = {'exp_avg': moments(engine.m), 'exp_avg_sq': moments(engine.v), 'step': engine.t,
                                    'layout': dict(engine.arena.offsets), 'n_live': engine.arena.n_live,
                                    # device-RNG stream positions: without them a resumed run replays the masks of step 0
                                    'rng': {'step_counter': int(engine.step_counter.item()), 'rng_calls': engine._rng_calls,
                                            'mask_rng_offset': _am.SparK._rng_offset}}
         if engine.teacher is not None:
-            ckpt['ema_weights'] = OrderedDict((k, v.detach().clone()) for k, v in engine.teacher.state_dict().items())
+            ckpt['ema_weights'] = OrderedDict((k, v.detach().clone().contiguous()) for k, v in engine.teacher.state_dict().items())
     return ckpt
 
 
@@ -60,6 +63,16 @@ def resume(engine, ckpt: Dict) -> None:
             engine.step_counter.fill_(int(rng['step_counter']))
             engine._rng_calls = int(rng['rng_calls'])
             _am.SparK._rng_offset = int(rng['mask_rng_offset'])
-        engine.m.copy_(opt['exp_avg'])
-        engine.v.copy_(opt['exp_avg_sq'])
+        for flat, saved in ((engine.m, opt['exp_avg']), (engine.v, opt['exp_avg_sq'])):
+            if isinstance(saved, dict):
+                views = engine.arena.views(flat)
+                if set(views) != set(saved):
+                    raise RuntimeError('resume: the checkpoint\'s Adam moments name other parameters than this engine\'s')
+                for n, v in saved.items():
+                    views[n].copy_(v)
+            else:                                  # flat moments of an older checkpoint: only valid for the same storage order
+                if getattr(engine.arena, 'taps_major', None):
+                    raise RuntimeError('resume: flat Adam moments were saved in stock parameter order; this engine stores '
+                                       'conv weights taps-major — rebuild it with PretrainEngine(..., taps_major=False)')
+                flat.copy_(saved)
         engine.t = int(opt['step'])

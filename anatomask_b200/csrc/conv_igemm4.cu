@@ -47,6 +47,8 @@ struct Igemm4Params {
     uint32_t idesc[3];                   // N = NT, 2·NT, 3·NT
     uint16_t row_off[9];                 // (dy·PW + dx)·64: window start inside a plane
     int16_t tap_w[3][9];                 // [plane offset dz][in-plane tap] → weight slab index
+    int dbg_skip;                        // diagnostic (AMB_V4_SKIP, with AMB_V4_DBG): 1 = no weight-slab loads, 2 = no plane loads (wrong results)
+    long long* dbg;                      // AMB_V4_DBG=1: per-CTA cycle counts of the MMA issuer {total, tempty, b_full, a_full, issue, units}
 };
 
 struct Unit4 {
@@ -147,13 +149,14 @@ __global__ void __launch_bounds__(256, 1) igemm4_kernel(const __grid_constant__ 
                 const uint32_t set = cc & 1u, ph = (cc >> 1) & 1u;
                 mbar_wait_u32(a_empty0 + set * 8u, ph ^ 1u, 41);
                 if (elect_one()) {
+                    // ONE barrier per plane set: the issuer polls once per chunk instead of once per plane
+                    const uint32_t bar = a_full0 + set * 8u;
+                    mbar_expect_tx_u32(bar, (P.dbg_skip & 2) ? 0u : (uint32_t)NP * P.plane_tx);
 #pragma unroll
-                    for (int pl = 0; pl < NP; ++pl) {
-                        const uint32_t bar = a_full0 + (set * NP + (uint32_t)pl) * 8u;
-                        mbar_expect_tx_u32(bar, P.plane_tx);
+                    for (int pl = 0; pl < NP; ++pl)
+                        if (!(P.dbg_skip & 2))
                         tma_load_5d_u32(a_ring_u32 + (set * NP + (uint32_t)pl) * V4_SLOT, &P.a_map, bar, (int)(kc * 32),
                                         c.x0 - 1, c.y0 - 1, c.z0 - 1 + pl, c.n);
-                    }
                 }
                 __syncwarp();
             }
@@ -168,9 +171,10 @@ __global__ void __launch_bounds__(256, 1) igemm4_kernel(const __grid_constant__ 
                     mbar_wait_u32(b_empty0 + slot * 8u, phase ^ 1u, 42);
                     if (elect_one()) {
                         const uint32_t bar = b_full0 + slot * 8u;
-                        mbar_expect_tx_u32(bar, 3u * P.blk_bytes);
+                        mbar_expect_tx_u32(bar, (P.dbg_skip & 1) ? 0u : 3u * P.blk_bytes);
 #pragma unroll
                         for (int j = 0; j < 3; ++j)
+                            if (!(P.dbg_skip & 1))
                             tma_load_3d_u32(b_ring_u32 + slot * b_bytes + (uint32_t)j * P.blk_bytes, &P.w_map, bar,
                                             (int)(kc * 32), 0, P.tap_w[2 - j][t9]);
                     }
@@ -188,23 +192,41 @@ __global__ void __launch_bounds__(256, 1) igemm4_kernel(const __grid_constant__ 
         const uint32_t id1 = P.idesc[0], id2 = P.idesc[1], id3 = P.idesc[2];
         const uint32_t blk16 = P.blk_bytes >> 4;
         uint32_t cc = 0, b_slot = 0, b_phase = 0, iter = 0;
+        const bool dbg = P.dbg != nullptr;
+        long long t_start = 0, w_te = 0, w_b = 0, w_a = 0, w_i = 0, tq = 0;
+        if (dbg) t_start = clock64();
+        // the tensor pipe queues only a few MMAs behind the issuing thread, so every cycle this thread spends polling a barrier
+        // between two taps is a cycle the pipe idles: the NEXT tap's weight slab (and at the end of a chunk the next plane set)
+        // is polled non-blockingly before the current tap's MMAs are issued; the blocking wait remains as the fallback
+        uint32_t b_ready = 0, a_ready = 0;
         for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x, ++iter) {
             const uint32_t acc = iter & 1u;
+            if (dbg) tq = clock64();
             mbar_wait_u32(smem_u32(&tempty[acc]), ((iter >> 1) & 1u) ^ 1u, 43);
+            if (dbg) w_te += clock64() - tq;
             tc_fence_after();
             const uint32_t d_base = tmem_base + acc * T * NT;
+            uint32_t d_tile[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) d_tile[t] = d_base + (uint32_t)t * NT;
             for (uint32_t kc = 0; kc < kchunks; ++kc, ++cc) {
                 const uint32_t set = cc & 1u, aph = (cc >> 1) & 1u;
                 const uint32_t a_set = a_ring_u32 + set * NP * V4_SLOT;
-#pragma unroll 1
-                for (int t9 = 0; t9 < 9; ++t9) {
-                    mbar_wait_u32(b_full0 + b_slot * 8u, b_phase, 45);
-                    if (t9 == 0) {
 #pragma unroll
-                        for (int pl = 0; pl < NP; ++pl) mbar_wait_u32(a_full0 + (set * NP + (uint32_t)pl) * 8u, aph, 44);
-                    }
+                for (int t9 = 0; t9 < 9; ++t9) {
+                    if (dbg) tq = clock64();
+                    if (!b_ready) mbar_wait_u32(b_full0 + b_slot * 8u, b_phase, 45);
+                    if (dbg) { const long long t = clock64(); w_b += t - tq; tq = t; }
+                    if (t9 == 0 && !a_ready) mbar_wait_u32(a_full0 + set * 8u, aph, 44);
+                    if (dbg) { const long long t = clock64(); w_a += t - tq; tq = t; }
                     tc_fence_after();
-                    const uint32_t a_lo = lo_const | (((a_set + (uint32_t)P.row_off[t9]) & 0x3FFFFu) >> 4);
+                    {
+                        const uint32_t nslot = b_slot + 1 == B_SLOTS ? 0u : b_slot + 1;
+                        b_ready = mbar_test_wait_u32(b_full0 + nslot * 8u, b_slot + 1 == B_SLOTS ? b_phase ^ 1u : b_phase);
+                        if (t9 == 8) a_ready = mbar_test_wait_u32(a_full0 + ((cc + 1) & 1u) * 8u, ((cc + 1) >> 1) & 1u);
+                    }
+                    // window start inside a plane: (dy·PW + dx)·64 B with PW = 10 — a compile-time constant once t9 is unrolled
+                    const uint32_t a_lo = lo_const | (((a_set + (uint32_t)(((t9 / 3) * 10 + t9 % 3) * 64)) & 0x3FFFFu) >> 4);
                     const uint32_t b_lo = lo_const | (((b_ring_u32 + b_slot * b_bytes) & 0x3FFFFu) >> 4);
                     const bool first = (kc | (uint32_t)t9) == 0u;
                     if (elect_one()) {
@@ -230,12 +252,24 @@ __global__ void __launch_bounds__(256, 1) igemm4_kernel(const __grid_constant__ 
                                 issue(pl, 1, lo, hi, true);
                             }
                         } else if (P.order == 0) {
+                            // running descriptors: A walks plane by plane (+ one slot), B only moves over the first planes
+                            // (slab block 2, 1, 0, 0, ...), the accumulator addresses are four values per unit
+                            uint64_t ad = a_hi | (uint64_t)a_lo;
+                            uint64_t bd = b_hi | (uint64_t)(b_lo + 2u * blk16);
 #pragma unroll
                             for (int k = 0; k < 2; ++k) {
 #pragma unroll
                                 for (int pl = 0; pl < NP; ++pl) {
                                     const int lo = pl - 2 < 0 ? 0 : pl - 2, hi = pl > T - 1 ? T - 1 : pl;
-                                    issue(pl, k, lo, hi, true);
+                                    const int cnt = hi - lo + 1;
+                                    mma_bf16(d_tile[lo], ad, bd, cnt == 1 ? id1 : (cnt == 2 ? id2 : id3), true);
+                                    if (pl + 1 < NP) {
+                                        desc_advance(ad, (int32_t)(V4_SLOT >> 4));
+                                        if (pl < 2) desc_advance(bd, -(int32_t)blk16);
+                                    } else if (k == 0) {
+                                        desc_advance(ad, 2 - (int32_t)((NP - 1) * (V4_SLOT >> 4)));
+                                        desc_advance(bd, 2 + (int32_t)((NP - 1 < 2 ? NP - 1 : 2) * blk16));
+                                    }
                                 }
                             }
                         } else {
@@ -250,11 +284,16 @@ __global__ void __launch_bounds__(256, 1) igemm4_kernel(const __grid_constant__ 
                         if (t9 == 8) mma_commit_u32(a_empty0 + set * 8u);      // the whole plane set is free again
                     }
                     __syncwarp();
+                    if (dbg) w_i += clock64() - tq;
                     if (++b_slot == B_SLOTS) { b_slot = 0; b_phase ^= 1u; }
                 }
             }
             if (elect_one()) mma_commit_u32(smem_u32(&tfull[acc]));
             __syncwarp();
+        }
+        if (dbg && lane == 0) {
+            long long* o = P.dbg + (size_t)blockIdx.x * 8;
+            o[0] = clock64() - t_start; o[1] = w_te; o[2] = w_b; o[3] = w_a; o[4] = w_i; o[5] = iter;
         }
     } else if (warp >= 4) {
         // =============================== epilogue ===============================
@@ -399,12 +438,10 @@ int igemm4_conv(const Plan& p, const amb_conv_args* a) {
     P.tmem_cols = 32;
     while (P.tmem_cols < (uint32_t)(2 * T * NT)) P.tmem_cols <<= 1;
     for (int c = 1; c <= 3; ++c) P.idesc[c - 1] = c * NT <= 256 ? umma_idesc_bf16(128, c * NT, 0, 0) : 0u;   // (c <= T)
-    // in-plane taps in the order of the dz = -1 taps of the plan; the same (dy,dx) is then looked up for dz = 0, +1
-    int n9 = 0;
+    // in-plane taps in raster order (dy, dx) = (t9 / 3 - 1, t9 % 3 - 1) — the kernel's unrolled tap loop has the window offsets
+    // as immediates; the weight slab of every (dz, dy, dx) is looked up in the plan (forward and input-gradient plans differ)
     int8_t t_dy[9], t_dx[9];
-    for (int t = 0; t < 27; ++t)
-        if (p.taps[t].dz == -1 && n9 < 9) { t_dy[n9] = p.taps[t].dy; t_dx[n9] = p.taps[t].dx; ++n9; }
-    if (n9 != 9) return 0;
+    for (int t9 = 0; t9 < 9; ++t9) { t_dy[t9] = (int8_t)(t9 / 3 - 1); t_dx[t9] = (int8_t)(t9 % 3 - 1); }
     for (int t9 = 0; t9 < 9; ++t9) {
         P.row_off[t9] = (uint16_t)(((t_dy[t9] + 1) * PW + (t_dx[t9] + 1)) * 64);
         for (int dz = 0; dz < 3; ++dz) {
@@ -453,6 +490,14 @@ int igemm4_conv(const Plan& p, const amb_conv_args* a) {
     const size_t smem = fixed + (size_t)b_slots * P.b_bytes;
     long units = use_list ? ((long)p.oN * p.fd * p.fh * p.fw << (3 * p.lgPv - 9)) : (long)p.oN * P.Ty * P.Tx * P.Tzg;
     int grid = (int)(units < (long)num_sms() ? units : (long)num_sms());
+    static long long* dbg_buf = nullptr;
+    const bool dbg = getenv("AMB_V4_DBG") != nullptr;                    // issuer cycle accounting (diagnostic; synchronises)
+    if (dbg) {
+        if (!dbg_buf) AMB_CUDA(cudaMalloc(&dbg_buf, 8 * sizeof(long long) * 1024));
+        AMB_CUDA(cudaMemsetAsync(dbg_buf, 0, 8 * sizeof(long long) * 1024, (cudaStream_t)a->stream));
+        P.dbg = dbg_buf;
+        P.dbg_skip = env_int("AMB_V4_SKIP", 0);
+    }
     if (T == 6) {
         AMB_CUDA(cudaFuncSetAttribute(igemm4_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         igemm4_kernel<6><<<grid, 256, smem, (cudaStream_t)a->stream>>>(P);
@@ -467,6 +512,16 @@ int igemm4_conv(const Plan& p, const amb_conv_args* a) {
         igemm4_kernel<4><<<grid, 256, smem, (cudaStream_t)a->stream>>>(P);
     }
     AMB_LAUNCH_CHECK();
+    if (dbg) {
+        static long long host[8 * 1024];
+        AMB_CUDA(cudaStreamSynchronize((cudaStream_t)a->stream));
+        AMB_CUDA(cudaMemcpy(host, dbg_buf, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost));
+        double s[6] = {0, 0, 0, 0, 0, 0}, mx = 0;
+        for (int b = 0; b < grid; ++b) { for (int j = 0; j < 6; ++j) s[j] += (double)host[b * 8 + j]; if (host[b * 8] > mx) mx = (double)host[b * 8]; }
+        fprintf(stderr, "V4DBG T=%d NT=%d Cx=%d grid=%d units/CTA=%.1f | issuer cycles/CTA: total %.0f (max %.0f)  tempty %.1f%%  b_full %.1f%%  "
+                        "a_full %.1f%%  issue %.1f%%  | per (chunk, tap): %.0f cycles\n", T, NT, p.Cx, grid, s[5] / grid, s[0] / grid, mx,
+                100 * s[1] / s[0], 100 * s[2] / s[0], 100 * s[3] / s[0], 100 * s[4] / s[0], s[0] / (s[5] * P.kchunks * 9));
+    }
     g_last_conv_kernel = "igemm4_kernel";
     return 1;
 }

@@ -1016,6 +1016,47 @@ __global__ void __launch_bounds__(256) repack_tiled_kernel(const float* __restri
     repack_tile<PACK, BFAST>(tile, src, dst, T, A, B, tiles_b, tchunks, blockIdx.x);
 }
 
+// Taps-major master weights (the engine's parameter arena keeps conv weights as fp32 [tap][Cout][Cin], trainer.ParamArena):
+// the forward operand is a plain fp32 → bf16 conversion, the input-gradient operand [tap][Cin][Cout] a per-tap transpose.
+//   linear    : block = 2048 consecutive elements, a thread converts 8 (two 128-bit loads, one 128-bit store)
+__device__ __forceinline__ void pack_linear_tile(const float* __restrict__ src, bf16* __restrict__ dst, long total, uint32_t blk) {
+    const long i = ((long)blk * 256 + threadIdx.x) * 8;
+    if (i >= total) return;
+    if (i + 8 <= total && (((uintptr_t)(src + i)) & 15) == 0) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src + i) + 1);
+        uint4 o;
+        o.x = pack2(a.x, a.y); o.y = pack2(a.z, a.w); o.z = pack2(b.x, b.y); o.w = pack2(b.z, b.w);
+        *reinterpret_cast<uint4*>(dst + i) = o;
+    } else {
+        for (long j = i; j < total && j < i + 8; ++j) dst[j] = __float2bfloat16(__ldg(src + j));
+    }
+}
+
+//   transpose : src [t][B][A] (a fastest) → dst [t][A][B] (b fastest); block = 32 a x 64 b of one tap through shared memory,
+//               128-byte runs on both sides
+__device__ __forceinline__ void pack_transpose_tile(float (*tile)[33], const float* __restrict__ src, bf16* __restrict__ dst,
+                                                    int A, int B, int tiles_b, int tiles_a, uint32_t blk) {
+    const int tb = (int)(blk % (uint32_t)tiles_b); blk /= (uint32_t)tiles_b;
+    const int ta = (int)(blk % (uint32_t)tiles_a);
+    const long t = (long)(blk / (uint32_t)tiles_a);
+    const int a0 = ta * 32, b0 = tb * 64;
+    const float* s = src + t * A * B;
+    bf16* d = dst + t * A * B;
+    for (uint32_t e = threadIdx.x; e < 2048u; e += 256u) {
+        const uint32_t la = e & 31u, lb = e >> 5;
+        float v = 0.f;
+        if (a0 + (int)la < A && b0 + (int)lb < B) v = __ldg(s + (long)(b0 + (int)lb) * A + a0 + (int)la);
+        tile[lb][la] = v;
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < 1024u; e += 256u) {
+        const uint32_t lb = (e & 31u) * 2u, la = e >> 5;
+        if (a0 + (int)la < A && b0 + (int)lb < B)                   // B is even (channel counts are multiples of 8)
+            *reinterpret_cast<uint32_t*>(d + (long)(a0 + (int)la) * B + b0 + (int)lb) = pack2(tile[lb][la], tile[lb + 1][la]);
+    }
+}
+
 // every conv weight of a step packed by ONE launch: block → job by binary search over the jobs' first tile
 __global__ void __launch_bounds__(256) repack_batched_kernel(const amb_pack_job* __restrict__ jobs, int n_jobs) {
     __shared__ float tile[256][33];
@@ -1031,12 +1072,29 @@ __global__ void __launch_bounds__(256) repack_batched_kernel(const amb_pack_job*
     __syncthreads();
     const amb_pack_job J = jobs[s_job];
     const uint32_t blk = blockIdx.x - (uint32_t)J.tile_begin;
-    if (J.b_fast) repack_tile<true, true>(tile, J.src, J.dst, J.T, J.A, J.B, J.tiles_b, J.tchunks, blk);
+    if (J.b_fast == 2) pack_linear_tile(J.src, (bf16*)J.dst, (long)J.T * J.A * J.B, blk);
+    else if (J.b_fast == 3) pack_transpose_tile(tile, J.src, (bf16*)J.dst, J.A, J.B, J.tiles_b, J.tchunks, blk);
+    else if (J.b_fast) repack_tile<true, true>(tile, J.src, J.dst, J.T, J.A, J.B, J.tiles_b, J.tchunks, blk);
     else repack_tile<true, false>(tile, J.src, J.dst, J.T, J.A, J.B, J.tiles_b, J.tchunks, blk);
 }
 
-// 1: b is the fast parameter axis, 0: a is, −1: layout not covered by the tiled kernel
-static int repack_case(int T, int A, int B, long st, long sa, long sb) {
+__global__ void __launch_bounds__(256) pack_linear_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long total) {
+    pack_linear_tile(src, dst, total, blockIdx.x);
+}
+
+__global__ void __launch_bounds__(256) pack_transpose_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int A, int B,
+                                                             int tiles_b, int tiles_a) {
+    __shared__ float tile[64][33];
+    pack_transpose_tile(tile, src, dst, A, B, tiles_b, tiles_a, blockIdx.x);
+}
+
+// 1: b is the fast parameter axis, 0: a is; 2 / 3: taps-major source, dst order / per-tap transposed (pack only);
+// −1: layout not covered by a tiled kernel
+static int repack_case(int T, int A, int B, long st, long sa, long sb, bool pack = false) {
+    if (pack && !(B & 1) && (T == 1 || st == (long)A * B)) {
+        if (sa == B && sb == 1) return 2;
+        if (sa == 1 && sb == A) return 3;
+    }
     if (st != 1 || (B & 1)) return -1;
     if (sb == T && sa == (long)B * T) return 1;
     if (sa == T && sb == (long)A * T) return 0;
@@ -1055,8 +1113,15 @@ static void launch_repack(const float* src, void* dst, int T, int A, int B, int 
 
 extern "C" int amb_pack_weight(const float* src, void* dst, int T, int A, int B, long st, long sa, long sb,
                                void* stream) {
-    const int c = repack_case(T, A, B, st, sa, sb);
-    if (c >= 0)
+    const int c = repack_case(T, A, B, st, sa, sb, true);
+    if (c == 2) {
+        const long total = (long)T * A * B;
+        pack_linear_kernel<<<(unsigned)((total + 2047) / 2048), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, total);
+    } else if (c == 3) {
+        const int tiles_b = (B + 63) / 64, tiles_a = (A + 31) / 32;
+        pack_transpose_kernel<<<(unsigned)((long)T * tiles_a * tiles_b), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, A, B,
+                                                                                                        tiles_b, tiles_a);
+    } else if (c >= 0)
         launch_repack<true>(src, dst, T, A, B, c, (cudaStream_t)stream);
     else
         pack_weight_kernel<<<grid_cap((long)T * A * B, 256, 8), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, T, A, B,

@@ -70,6 +70,19 @@ __device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// non-blocking poll (try_wait may suspend the thread up to a time limit): an MMA issuer looks one pipeline stage ahead
+// BEFORE it issues the current stage's MMAs and consumes the answer afterwards, so the poll's latency hides behind the issue
+__device__ __forceinline__ uint32_t mbar_test_wait_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity, int tag) {
     if (mbar_try_wait_u32(bar, parity)) return;
     const long long t0 = clock64();
@@ -139,6 +152,18 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64
         : "memory");
 }
 // arrives (count 1) on the mbarrier when all previously issued MMAs of this thread have completed
+// in-place add on the LOW word of a shared-memory matrix descriptor (start address field, 16-byte units): the issuing thread
+// walks its operands with one uniform add per MMA instead of re-assembling (lo, hi) pairs — the instructions between two
+// tcgen05.mma of the issuing thread are what a narrow MMA costs (tests/probes/mma_ts_probe.cu)
+__device__ __forceinline__ void desc_advance(uint64_t& desc, int32_t delta16) {
+    asm volatile(
+        "{\n\t.reg .b32 lo, hi;\n\t"
+        "mov.b64 {lo, hi}, %0;\n\t"
+        "add.s32 lo, lo, %1;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t}"
+        : "+l"(desc)
+        : "r"(delta16));
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

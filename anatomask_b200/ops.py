@@ -249,15 +249,62 @@ PACK_RECORD = None
 
 
 def _pack(w: torch.Tensor, T: int, A: int, B: int, st: int, sa: int, sb: int) -> torch.Tensor:
-    key = (w.data_ptr(), T, A, B, sa, sb)
+    key = (w.data_ptr(), T, A, B, sa, sb, st)
     if PACK_CACHE is not None:
         hit = PACK_CACHE.get(key)
         if hit is not None:
             return hit
     out = torch.empty((T, A, B), dtype=bf16, device=w.device)
     L.call('amb_pack_weight', _p(w), _p(out), T, A, B, st, sa, sb, _stream())
-    if PACK_RECORD is not None and st == 1:
+    if PACK_RECORD is not None:
         PACK_RECORD.append((key, w))
+    return out
+
+
+def _pack_conv(weight: torch.Tensor, transposed: bool, dgrad: bool) -> torch.Tensor:
+    """bf16 operand of a conv weight: forward form [tap][Cout][Cin] or input-gradient form [tap][Cin][Cout].  The strides
+    come from the tensor itself: a stock parameter is (Cout, Cin, k, k, k)-contiguous (ConvTranspose3d: (Cin, Cout, 4, 4, 4)),
+    an engine parameter is a view of the taps-major arena storage [tap][Cout][Cin] (trainer.ParamArena) — then the forward
+    form is a plain dtype conversion and the weight gradient needs no re-layout at all (packed_alias)."""
+    if weight.dim() == 2:                      # nn.Linear used as a per-voxel (1x1x1) conv: (Cout, Cin)
+        s0, s1 = weight.stride()
+        if dgrad:
+            return _pack(weight, 1, weight.shape[1], weight.shape[0], 1, s1, s0)
+        return _pack(weight, 1, weight.shape[0], weight.shape[1], 1, s0, s1)
+    s = weight.stride()
+    T = weight.shape[2] * weight.shape[3] * weight.shape[4]
+    if T > 1 and not (s[2] == weight.shape[3] * s[3] and s[3] == weight.shape[4] * s[4]):
+        weight = weight.contiguous()
+        s = weight.stride()
+    co, ci = (1, 0) if transposed else (0, 1)
+    if dgrad:
+        return _pack(weight, T, weight.shape[ci], weight.shape[co], s[4], s[ci], s[co])
+    return _pack(weight, T, weight.shape[co], weight.shape[ci], s[4], s[co], s[ci])
+
+
+def packed_alias(t: Optional[torch.Tensor], transposed: bool) -> Optional[torch.Tensor]:
+    """The [tap][Cout][Cin]-contiguous tensor that shares memory with conv weight (or weight gradient) `t`, if `t` is stored
+    taps-major (engine arena; any 1×1×1 weight qualifies trivially) — the layout the weight-gradient kernels produce."""
+    if t is None or t.dim() != 5:
+        return None
+    v = t.permute(2, 3, 4, 1, 0) if transposed else t.permute(2, 3, 4, 0, 1)
+    if not v.is_contiguous():
+        return None
+    return v.reshape(-1, v.shape[3], v.shape[4])
+
+
+def _from_packed(dwp: torch.Tensor, like: torch.Tensor, transposed: bool) -> torch.Tensor:
+    """[tap][Cout][Cin] gradient → a tensor of `like`'s shape: zero-copy view when `like` is stored taps-major, else the
+    re-layout kernel into the parameter's (contiguous) layout."""
+    T, Cout, Cin = dwp.shape
+    if packed_alias(like, transposed) is not None:
+        v = dwp.view(*like.shape[2:], Cout, Cin)
+        return v.permute(4, 3, 0, 1, 2) if transposed else v.permute(3, 4, 0, 1, 2)
+    out = torch.empty(like.shape, dtype=torch.float32, device=dwp.device)
+    if transposed:
+        L.call('amb_unpack_wgrad', _p(dwp), _p(out), T, Cout, Cin, 1, T, Cout * T, _stream())
+    else:
+        L.call('amb_unpack_wgrad', _p(dwp), _p(out), T, Cout, Cin, 1, Cin * T, T, _stream())
     return out
 
 
@@ -274,21 +321,28 @@ class PackPlan:
         for key, w in record:
             if key in seen:
                 continue
-            ptr, T, A, B, sa, sb = key
-            if sb == T and sa == B * T:
-                b_fast = 1
-            elif sa == T and sb == A * T:
-                b_fast = 0
+            ptr, T, A, B, sa, sb, st = key
+            # job kinds (amb_pack_job.b_fast): 2 / 3 = taps-major source (engine arena) → plain conversion / per-tap transpose;
+            # 1 / 0 = taps innermost (stock parameter layout), b or a the faster channel axis
+            if B % 2 == 0 and (T == 1 or st == A * B) and sa == B and sb == 1:
+                b_fast, tiles_b, tchunks = 2, 0, 0
+                n_tiles = -(-(T * A * B) // 2048)
+            elif B % 2 == 0 and (T == 1 or st == A * B) and sa == 1 and sb == A:
+                b_fast, tiles_b, tchunks = 3, -(-B // 64), -(-A // 32)
+                n_tiles = T * tiles_b * tchunks
+            elif st == 1 and B % 2 == 0 and (sb == T and sa == B * T or sa == T and sb == A * T):
+                b_fast = 1 if (sb == T and sa == B * T) else 0
+                ta, tb = (4, 64) if b_fast else (16, 16)
+                tiles_a, tiles_b, tchunks = -(-A // ta), -(-B // tb), -(-T // 32)
+                n_tiles = tiles_a * tiles_b * tchunks
             else:
-                continue                                   # layout outside the tiled kernel: stays a per-call pack
+                continue                                   # layout outside the tiled kernels: stays a per-call pack
             seen.add(key)
             grp = 0 if group_of is None else int(group_of(w))
-            ta, tb = (4, 64) if b_fast else (16, 16)
-            tiles_a, tiles_b, tchunks = -(-A // ta), -(-B // tb), -(-T // 32)
             out = torch.empty((T, A, B), dtype=bf16, device=w.device)
             tile = tiles.get(grp, 0)
             jobs.setdefault(grp, []).append((ptr, out.data_ptr(), T, A, B, b_fast, tile, tiles_b, tchunks, 0))
-            tiles[grp] = tile + tiles_a * tiles_b * tchunks
+            tiles[grp] = tile + n_tiles
             self.cache[key] = out
             self._keep.append(w)
         dt = np.dtype([('src', np.uint64), ('dst', np.uint64), ('T', np.int32), ('A', np.int32), ('B', np.int32),
@@ -361,14 +415,14 @@ class ConvFn(torch.autograd.Function):
         k3 = k * k * k
         if transposed:
             Cout = weight.shape[1]
-            wp = _pack(weight, 64, Cout, Cin, 1, 64, Cout * 64)
+            wp = _pack_conv(weight, True, False)
             y = torch.empty((N, 2 * D, 2 * H, 2 * W, Cout), dtype=bf16, device=x.device)
             flops = 2.0 * N * D * H * W * 64 * Cin * Cout
             with _Timed('convT_fwd', flops):
                 _conv_call(L.OP_CONVT, impl, (N, D, H, W), Cin, Cout, 4, 2, x, y, wp, bias, stats=stats)
         else:
             Cout = weight.shape[0]
-            wp = _pack(weight, k3, Cout, Cin, 1, Cin * k3, k3)
+            wp = _pack_conv(weight, False, False)
             shape = (N, D // stride, H // stride, W // stride, Cout)
             # masked voxels are never written where the work-list skips whole tiles: zero-fill unless the only consumer
             # (a pooled masked norm) visits visible voxels exclusively
@@ -405,29 +459,33 @@ class ConvFn(torch.autograd.Function):
             side.wait_stream(main)
 
         def weight_branch(dst_w=None):
+            # dst_w: the parameter's .grad view in the engine's (pre-zeroed) gradient arena.  Stored taps-major it IS the
+            # [tap][Cout][Cin] buffer the kernels accumulate into (no staging buffer, no fill, no re-layout pass); a
+            # contiguous destination goes through a staging buffer and amb_unpack_wgrad.
             dw_ = db_ = None
-            if transposed:
-                Cout = weight.shape[1]
-                if ctx.needs_input_grad[1]:
-                    dwp = torch.zeros((64, Cout, Cin), dtype=torch.float32, device=x.device)
+            Cout = weight.shape[1] if transposed else weight.shape[0]
+            T = 64 if transposed else k3
+            if ctx.needs_input_grad[1]:
+                direct = packed_alias(dst_w, transposed)
+                dwp = direct if direct is not None else torch.zeros((T, Cout, Cin), dtype=torch.float32, device=x.device)
+                if transposed:
                     a = L.WgradArgs(L.OP_CONVT, impl, N, D, H, W, Cin, Cout, 4, 2, x.data_ptr(), dy.data_ptr(),
                                     dwp.data_ptr(), 1, 1, 1, 0, 0, torch.cuda.current_stream().cuda_stream)
-                    with _Timed('convT_wgrad', ctx.flops):
-                        L.call('amb_conv_wgrad', C.byref(a))
-                    dw_ = torch.empty_like(weight) if dst_w is None else dst_w
-                    L.call('amb_unpack_wgrad', _p(dwp), _p(dw_), 64, Cout, Cin, 1, 64, Cout * 64, _stream())
-            else:
-                Cout = weight.shape[0]
-                if ctx.needs_input_grad[1]:
-                    dwp = torch.zeros((k3, Cout, Cin), dtype=torch.float32, device=x.device)
+                else:
                     a = L.WgradArgs(L.OP_CONV, impl, N, D, H, W, Cin, Cout, k, stride, x.data_ptr(), dy.data_ptr(),
                                     dwp.data_ptr(), 1 if m is None else m.fd, 1 if m is None else m.fh,
                                     1 if m is None else m.fw, 0 if m is None else m.list.data_ptr(),
                                     0 if m is None else m.count.data_ptr(), torch.cuda.current_stream().cuda_stream)
-                    with _Timed('conv_wgrad', ctx.flops):
-                        L.call('amb_conv_wgrad', C.byref(a))
-                    dw_ = torch.empty_like(weight) if dst_w is None else dst_w
-                    L.call('amb_unpack_wgrad', _p(dwp), _p(dw_), k3, Cout, Cin, 1, Cin * k3, k3, _stream())
+                with _Timed('convT_wgrad' if transposed else 'conv_wgrad', ctx.flops):
+                    L.call('amb_conv_wgrad', C.byref(a))
+                if direct is not None:
+                    dw_ = dst_w
+                elif dst_w is not None:
+                    L.call('amb_unpack_wgrad', _p(dwp), _p(dst_w), T, Cout, Cin, 1, *((T, Cout * T) if transposed else (Cin * T, T)),
+                           _stream())
+                    dw_ = dst_w
+                else:
+                    dw_ = _from_packed(dwp, weight, transposed)
             if has_bias and ctx.needs_input_grad[2]:
                 tap = getattr(ctx, 'tap', None)
                 if transposed and tap is not None and tap.sums is not None:
@@ -445,7 +503,8 @@ class ConvFn(torch.autograd.Function):
         deferred = False
         if side is not None:
             wref = ctx.weight_ref
-            can_defer = DEFER_WGRAD and wref.grad is not None and wref.grad.is_contiguous() and \
+            can_defer = DEFER_WGRAD and wref.grad is not None and \
+                (wref.grad.is_contiguous() or packed_alias(wref.grad, transposed) is not None) and \
                 (bias_ref is None or not has_bias or bias_ref.grad is not None)
             with torch.cuda.stream(side):
                 dw, db = weight_branch(wref.grad if can_defer else None)
@@ -461,13 +520,13 @@ class ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if transposed:
                 Cout = weight.shape[1]
-                wp = _pack(weight, 64, Cin, Cout, 1, Cout * 64, 64)
+                wp = _pack_conv(weight, True, True)
                 dx = torch.empty_like(x)
                 with _Timed('convT_dgrad', ctx.flops):
                     _conv_call(L.OP_CONVT_DGRAD, impl, (N, D, H, W), Cin, Cout, 4, 2, dy, dx, wp)
             else:
                 Cout = weight.shape[0]
-                wp = _pack(weight, k3, Cin, Cout, 1, k3, Cin * k3)
+                wp = _pack_conv(weight, False, True)
                 # a masked input gradient is zero-filled unless the caller vouches that it is only read at visible voxels
                 # (zero_dx=False: list-walking kernels skip masked tiles, dense-walking ones write every voxel themselves);
                 # a 1x1 stride-2 conv only ever produces the even voxels
@@ -531,7 +590,7 @@ class ConvPairFn(torch.autograd.Function):
             dsc = dsc.contiguous()
             N, D, H, W, Cin = x.shape
             Cout = w3.shape[0]
-            wp = _pack(w3, 1, Cin, Cout, 1, 1, Cin)
+            wp = _pack_conv(w3, False, True)
             if stride == 2:
                 # the shortcut is a per-voxel (Cout -> Cin) product on the coarse grid; its result belongs to the even voxels
                 coarse = torch.zeros((N, D // 2, H // 2, W // 2, Cin), dtype=bf16, device=x.device) if m is not None else \
@@ -783,7 +842,7 @@ def conv3d_bn_eval(x, weight, gamma, beta, rm, rv, eps, act, k=3, impl=L.IMPL_AU
     Cout = weight.shape[0]
     ss = torch.empty(2 * Cout, dtype=torch.float32, device=x.device)
     L.call('amb_norm_eval', _p(gamma), _p(beta), _p(rm), _p(rv), eps, _p(ss[:Cout]), _p(ss[Cout:]), Cout, _stream())
-    wp = _pack(weight, k ** 3, Cout, Cin, 1, Cin * k ** 3, k ** 3)
+    wp = _pack_conv(weight, False, False)
     y = torch.empty((N, D, H, W, Cout), dtype=bf16, device=x.device)
     with _Timed('conv_fwd', 2.0 * N * D * H * W * k ** 3 * Cin * Cout):
         _conv_call(L.OP_CONV, impl, (N, D, H, W), Cin, Cout, k, 1, x, y, wp, ss[Cout:], ep_scale=ss[:Cout], ep_act=act)

@@ -54,26 +54,26 @@ MARK_OF_GROUP = {'decoder': 'decoder_done', 'densify': 'densify_done', 'encoder_
 
 
 def bucket_ranges(offsets: Dict[str, Tuple[int, int]], n_live: int) -> List[Tuple[str, int, int]]:
-    """[(group, lo, hi)] — contiguous element ranges of the live-gradient arena, one per parameter group, in
-    backward-completion order.  `offsets` is ParamArena.offsets (name -> (offset, numel)); entries at or beyond n_live
-    (dead parameters, buffers) are ignored.  Raises if a group is not contiguous or the groups do not tile [0, n_used)."""
+    """[(group, lo, hi)] — element ranges of the live-gradient arena, one per parameter group, in backward-completion order.
+    `offsets` is ParamArena.offsets (name -> (offset, numel)); entries at or beyond n_live (dead parameters, buffers) are
+    ignored.  A range may contain the arena's alignment padding (zeros) but no tensor of another group; raises if the groups'
+    ranges overlap or a live tensor belongs to no group."""
     out = []
-    covered = 0
     claimed = set()
     for group, prefixes in GROUP_PREFIXES:
         names = [n for n, (o, _) in offsets.items() if n.startswith(prefixes) and o < n_live and n not in claimed]
         claimed.update(names)
-        spans = sorted((offsets[n][0], offsets[n][0] + offsets[n][1]) for n in names)
-        if not spans:
+        if not names:
             continue
-        lo, hi = spans[0][0], spans[-1][1]
-        if sum(b - a for a, b in spans) != hi - lo:
-            raise RuntimeError(f'gradient arena: parameter group {group} is not contiguous')
+        lo = min(offsets[n][0] for n in names)
+        hi = max(offsets[n][0] + offsets[n][1] for n in names)
+        for n, (o, k) in offsets.items():
+            if o < n_live and n not in names and o < hi and o + k > lo:
+                raise RuntimeError(f'gradient arena: parameter group {group} is not contiguous ({n} lies inside it)')
         out.append((group, lo, hi))
-        covered += hi - lo
-    used = max((o + k for o, k in offsets.values() if o < n_live), default=0)
-    if covered != used:
-        raise RuntimeError(f'gradient arena: groups cover {covered} of {used} live elements')
+    missing = [n for n, (o, _) in offsets.items() if o < n_live and n not in claimed]
+    if missing:
+        raise RuntimeError(f'gradient arena: {len(missing)} live tensors belong to no parameter group (e.g. {missing[0]})')
     return out
 
 

@@ -47,10 +47,42 @@ def dead_parameter_names(model: spark3D.SparK) -> List[str]:
     return [n for n, _ in model.named_parameters() if n.startswith(pre)]
 
 
-class ParamArena:
-    """Re-homes a module's float parameters/buffers into one contiguous fp32 buffer (views keep their names/shapes)."""
+def taps_major_weight_names(module: nn.Module) -> set:
+    """Names of the conv weights the arena stores taps-major, fp32 [tap][Cout][Cin]: every ungrouped Conv3d / ConvTranspose3d
+    whose channel counts the implicit-GEMM kernels take (multiples of 8) — exactly the weights that reach the kernels through
+    ops.ConvFn.  The stem (Cin = 1), the 1-channel projection and depthwise convs are read through raw pointers by their own
+    kernels and keep the stock layout."""
+    out = set()
+    for mn, mod in module.named_modules():
+        if isinstance(mod, (nn.Conv3d, nn.ConvTranspose3d)) and getattr(mod, 'groups', 1) == 1 and mod.weight is not None \
+                and mod.weight.dim() == 5 and mod.in_channels % 8 == 0 and mod.out_channels % 8 == 0:
+            out.add((mn + '.' if mn else '') + 'weight')
+    return out
 
-    def __init__(self, module: nn.Module, dead: List[str], with_grads: bool):
+
+def _taps_major_view(flat_slice: torch.Tensor, shape, transposed: bool) -> torch.Tensor:
+    """A tensor of the parameter's shape — (Cout, Cin, k, k, k), ConvTranspose3d (Cin, Cout, 4, 4, 4) — over storage laid out
+    [tap][Cout][Cin]."""
+    c0, c1 = shape[0], shape[1]
+    T = shape[2] * shape[3] * shape[4]
+    if transposed:
+        return flat_slice.view(T, c1, c0).permute(2, 1, 0).unflatten(-1, tuple(shape[2:]))
+    return flat_slice.view(T, c0, c1).permute(1, 2, 0).unflatten(-1, tuple(shape[2:]))
+
+
+class ParamArena:
+    """Re-homes a module's float parameters/buffers into one contiguous fp32 buffer (views keep their names/shapes).
+
+    Every tensor starts on a 16-byte boundary.  With `taps_major` (the engine's default) the conv weights the implicit-GEMM
+    kernels consume are STORED as [tap][Cout][Cin] — the order of their bf16 operand copies and of the weight-gradient
+    kernels' output — and the module's `weight` is a strided view with the reference's shape: packing a step's operands is
+    then a dtype conversion (forward form) or a per-tap transpose (input-gradient form) instead of a gather with the taps
+    innermost, and the weight gradients are accumulated by the kernels straight into the gradient arena (no staging
+    buffer, no fill, no re-layout pass: 0.8 ms of a 20 ms STUNet-B step).  AdamW, EMA, the global-norm clip and the gradient
+    all-reduce are element-wise over the flat buffers, so they never see the difference; state_dict() / load_state_dict()
+    go through the strided views."""
+
+    def __init__(self, module: nn.Module, dead: List[str], with_grads: bool, taps_major: bool = True):
         dev = next(module.parameters()).device
         named_p = list(module.named_parameters())
         live = [(n, p) for n, p in named_p if n not in dead]
@@ -58,25 +90,33 @@ class ParamArena:
         fbuf = [(n, b) for n, b in module.named_buffers() if b.is_floating_point()]
         self.int_buffers = [(n, b) for n, b in module.named_buffers() if not b.is_floating_point()]
         pad = lambda k: (k + 3) // 4 * 4
-        self.n_live = pad(sum(p.numel() for _, p in live))
-        total = self.n_live + pad(sum(p.numel() for _, p in deadp)) + pad(sum(b.numel() for _, b in fbuf))
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.taps_major = taps_major_weight_names(module) if taps_major else set()
+        transposed = {(mn + '.' if mn else '') + 'weight' for mn, mod in module.named_modules()
+                      if isinstance(mod, nn.ConvTranspose3d)}
+        self.n_live = sum(pad(p.numel()) for _, p in live)
+        n_dead, n_buf = sum(pad(p.numel()) for _, p in deadp), sum(pad(b.numel()) for _, b in fbuf)
+        self.flat = torch.zeros(self.n_live + n_dead + n_buf, dtype=torch.float32, device=dev)
         self.offsets: Dict[str, Tuple[int, int]] = {}
-        starts = (0, self.n_live, self.n_live + pad(sum(p.numel() for _, p in deadp)))
+        self._view_of = {}                       # name -> function(flat buffer) -> view with the parameter's shape
+        starts = (0, self.n_live, self.n_live + n_dead)
         for group, off in zip((live, deadp, fbuf), starts):
             for n, t in group:
                 k = t.numel()
-                view = self.flat[off:off + k].view(t.shape)
+                if n in self.taps_major:
+                    make = (lambda f, o=off, k=k, sh=tuple(t.shape), tr=(n in transposed): _taps_major_view(f[o:o + k], sh, tr))
+                else:
+                    make = (lambda f, o=off, k=k, sh=tuple(t.shape): f[o:o + k].view(sh))
+                view = make(self.flat)
                 view.copy_(t.data)
                 t.data = view
                 self.offsets[n] = (off, k)
-                off += k
+                self._view_of[n] = make
+                off += pad(k)
         self.grad = None
         if with_grads:
             self.grad = torch.zeros(self.n_live, dtype=torch.float32, device=dev)
             for n, p in live:
-                o, k = self.offsets[n]
-                p.grad = self.grad[o:o + k].view(p.shape)
+                p.grad = self._view_of[n](self.grad)
         if self.int_buffers:
             self.iflat = torch.zeros(len(self.int_buffers), dtype=torch.int64, device=dev)
             for i, (_, b) in enumerate(self.int_buffers):
@@ -84,6 +124,12 @@ class ParamArena:
                 b.data = self.iflat[i]
         else:
             self.iflat = None
+
+    def views(self, flat_like: torch.Tensor, names=None) -> Dict[str, torch.Tensor]:
+        """name -> view of another flat buffer laid out like this arena (Adam moments, a gradient snapshot) with the
+        parameter's shape and element order — what a checkpoint stores, independent of the arena's storage order."""
+        names = [n for n, (o, _) in self.offsets.items() if o < flat_like.numel()] if names is None else names
+        return {n: self._view_of[n](flat_like) for n in names}
 
     def zero_grad(self):
         self.grad.zero_()
@@ -109,7 +155,10 @@ class PretrainEngine:
 
     def __init__(self, model: spark3D.SparK, lr: float = 1e-4, weight_decay: float = 1e-5, clip: float = 12.0,
                  betas=(0.9, 0.999), eps: float = 1e-8, epochs: int = 1000, anatomask: bool = True,
-                 mask_rng: str = 'device', process_group=None):
+                 mask_rng: str = 'device', process_group=None, taps_major: bool = True):
+        import os
+        if os.environ.get('AMB_NO_TAPS_MAJOR') == '1':       # A/B switch: stock parameter layout in the arena
+            taps_major = False
         self.model = model
         self.lr, self.wd, self.clip, self.betas, self.eps, self.epochs = lr, weight_decay, clip, betas, eps, epochs
         self.dead = dead_parameter_names(model)
@@ -120,8 +169,8 @@ class PretrainEngine:
             for p in self.teacher.parameters():
                 p.requires_grad_(False)
             self.teacher.mask_rng = mask_rng
-            self.tarena = ParamArena(self.teacher, self.dead, with_grads=False)
-        self.arena = ParamArena(model, self.dead, with_grads=True)
+            self.tarena = ParamArena(self.teacher, self.dead, with_grads=False, taps_major=taps_major)
+        self.arena = ParamArena(model, self.dead, with_grads=True, taps_major=taps_major)
         self.m = torch.zeros_like(self.arena.grad)
         self.v = torch.zeros_like(self.arena.grad)
         self.t = 0
@@ -350,6 +399,14 @@ class PretrainEngine:
             if self.world > 1:
                 torch.cuda.synchronize()                 # nothing of the warm-up may still be polled by NCCL's watchdog
             mode = {'capture_error_mode': 'thread_local'} if self.world > 1 else {}
+            # The main chain (forward passes, input gradients, norms — every kernel waits for the one before it) is captured
+            # on a HIGH-priority stream, the deferred weight-gradient branch stays on the default-priority side stream: kernel
+            # nodes keep their stream's priority, so whenever SMs free up the block scheduler hands them to the critical path
+            # first and the weight gradients fill in behind (both are persistent one-CTA-per-SM kernels: without priorities
+            # whichever was launched first holds the machine, and a weight gradient ahead of its layer's input gradient
+            # delays everything downstream).  AMB_NO_PRIORITY=1: capture on a default-priority stream (A/B).
+            if os.environ.get('AMB_NO_PRIORITY') != '1':
+                mode['stream'] = torch.cuda.Stream(priority=-1)
             if split:
                 g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                 keep, self.buckets = self.buckets, None  # no collective may be issued while capturing

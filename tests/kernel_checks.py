@@ -258,6 +258,40 @@ def check_repack(seed=0):
         L.call('amb_unpack_wgrad', ops._p(dwp), ops._p(dwt), T, co, ci, 1, T, co * T, ops._stream())
         assert torch.equal(dwt, dwp.permute(2, 1, 0)), ('unpack convT', co, ci, T)
         out[f'{co}x{ci}x{T}'] = 'exact'
+    # taps-major master weights (trainer.ParamArena): the module-shaped strided view packs to the same operands as the stock
+    # tensor — forward form by plain conversion, input-gradient form by the per-tap transpose kernel; through the per-call
+    # entry point and through the batched job table; a misaligned (odd-offset) source takes the scalar path
+    from anatomask_b200.trainer import _taps_major_view
+    for (co, ci, k, tr) in [(64, 64, 3, False), (24, 40, 3, False), (136, 72, 3, False), (32, 64, 1, False), (64, 32, 4, True),
+                            (8, 8, 3, False), (512, 256, 3, False), (40, 24, 4, True)]:
+        T = k ** 3
+        shape = (ci, co, k, k, k) if tr else (co, ci, k, k, k)
+        stock = torch.randn(*shape, generator=g).to(dev)
+        for misalign in (0, 1):
+            store = torch.zeros(stock.numel() + 4, device=dev)
+            wv = _taps_major_view(store[misalign:misalign + stock.numel()], shape, tr)
+            wv.copy_(stock)
+            al = ops.packed_alias(wv, tr)
+            assert al is not None and al.data_ptr() == store.data_ptr() + 4 * misalign
+            ops.PACK_RECORD = rec = []
+            try:
+                fwd, dgr = ops._pack_conv(wv, tr, False), ops._pack_conv(wv, tr, True)
+            finally:
+                ops.PACK_RECORD = None
+            want_f, want_d = ops._pack_conv(stock, tr, False), ops._pack_conv(stock, tr, True)
+            assert torch.equal(fwd, want_f) and torch.equal(dgr, want_d), ('taps-major', co, ci, k, tr, misalign)
+            assert torch.equal(fwd, al.to(bf16)) and torch.equal(dgr, al.transpose(1, 2).to(bf16))
+            plan = ops.PackPlan(rec)
+            assert plan.n_jobs == 2, (plan.n_jobs, co, ci, k)
+            plan.run()
+            got = list(plan.cache.values())
+            assert torch.equal(got[0], want_f) and torch.equal(got[1], want_d), ('taps-major batched', co, ci, k, tr, misalign)
+            # gradient: a [tap][Cout][Cin] buffer viewed in the parameter's shape without a copy
+            dwp = torch.randn(T, co, ci, generator=g).to(dev)
+            back = ops._from_packed(dwp, wv, tr)
+            assert back.data_ptr() == dwp.data_ptr() and tuple(back.shape) == shape
+            assert torch.equal(back.contiguous(), ops._from_packed(dwp, stock, tr))
+        out[f'taps-major {co}x{ci}x{k}{"T" if tr else ""}'] = 'exact'
     torch.cuda.synchronize()
     return out
 

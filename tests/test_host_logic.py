@@ -150,8 +150,8 @@ def test_pack_plan_job_table():
     w2 = torch.zeros(16, 24, 64)          # ConvTranspose (Cin, Cout, taps)
     w3 = torch.zeros(8, 8, 27)
     rec = []
-    def ask(w, T, A, B, sa, sb):
-        rec.append(((w.data_ptr(), T, A, B, sa, sb), w))
+    def ask(w, T, A, B, sa, sb, st=1):
+        rec.append(((w.data_ptr(), T, A, B, sa, sb, st), w))
     ask(w1, 27, 64, 32, 32 * 27, 27)      # forward form  [t][co][ci]: b (= ci) is the fast parameter axis
     ask(w1, 27, 32, 64, 27, 32 * 27)      # dgrad form    [t][ci][co]: a (= ci) is the fast axis
     ask(w1, 27, 64, 32, 32 * 27, 27)      # asked again by the next step: same key
@@ -180,6 +180,75 @@ def test_pack_plan_job_table():
     assert (n0, tiles0, n1, tiles1) == (2, tiles[0] + tiles[1], 1, tiles[2])
     assert list(t0.numpy().view(dt)['tile_begin']) == [0, tiles[0]] and list(t1.numpy().view(dt)['tile_begin']) == [0]
     assert int(t1.numpy().view(dt)['src'][0]) == w2.data_ptr()
+    # taps-major master weights (the engine arena, fp32 [tap][Cout][Cin]): forward form = plain conversion (kind 2, blocks of
+    # 2048 elements), input-gradient form = per-tap transpose (kind 3, 32 a x 64 b tiles); a 1x1x1 weight in the stock
+    # layout is the same memory order and takes the same two kinds
+    w4 = torch.zeros(27, 64, 40)          # [tap][Cout][Cin]
+    w5 = torch.zeros(48, 16)              # 1x1x1 conv, stock layout (Cout, Cin)
+    rec2 = []
+    def ask2(w, T, A, B, sa, sb, st):
+        rec2.append(((w.data_ptr(), T, A, B, sa, sb, st), w))
+    ask2(w4, 27, 64, 40, 40, 1, 64 * 40)  # forward: A = Cout, B = Cin
+    ask2(w4, 27, 40, 64, 1, 40, 64 * 40)  # dgrad:   A = Cin,  B = Cout
+    ask2(w5, 1, 48, 16, 16, 1, 1)
+    ask2(w5, 1, 16, 48, 1, 16, 1)
+    plan2 = ops.PackPlan(rec2)
+    tab2 = plan2.table.numpy().view(dt)
+    assert list(tab2['b_fast']) == [2, 3, 2, 3]
+    tiles2 = [-(-27 * 64 * 40 // 2048), 27 * 1 * 2, 1, 1 * 1 * 1]
+    assert list(tab2['tile_begin']) == [0, tiles2[0], tiles2[0] + tiles2[1], sum(tiles2[:3])] and plan2.total_tiles == sum(tiles2)
+    assert list(tab2['tiles_b'][[1, 3]]) == [1, 1] and list(tab2['tchunks'][[1, 3]]) == [2, 1]
+
+
+def test_taps_major_arena_keeps_the_module_contract():
+    """ParamArena(taps_major=True): conv weights are stored [tap][Cout][Cin] but the module still sees the reference's shapes
+    and values (state_dict round trip), every tensor starts 16-byte aligned, ops.packed_alias finds the kernels' view of a
+    weight and of its gradient, and Adam-moment views follow the parameter's element order."""
+    from anatomask_b200 import ops
+    from anatomask_b200.trainer import build_model, ParamArena, dead_parameter_names, taps_major_weight_names
+    cfg = rp.CONFIGS['tiny']
+    model = build_model(base=cfg.base, input_size=cfg.input_size, device='cpu')
+    ref = build_model(base=cfg.base, input_size=cfg.input_size, device='cpu')
+    ref.load_state_dict(model.state_dict())
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    names = taps_major_weight_names(model)
+    assert names and all(n.endswith('.weight') for n in names)
+    assert not any('proj.weight' == n.split('dense_decoder.')[-1] for n in names)          # the 1-channel projection stays stock
+    arena = ParamArena(model, dead_parameter_names(model), with_grads=True, taps_major=True)
+    mods = dict(model.named_modules())
+    for n, p in model.named_parameters():
+        assert torch.equal(p.detach(), before[n]), n
+        o, k = arena.offsets[n]
+        assert o % 4 == 0, n
+        if n in names:
+            tr = isinstance(mods[n[:-len('.weight')]], torch.nn.ConvTranspose3d)
+            al = ops.packed_alias(p.detach(), tr)
+            assert al is not None and al.is_contiguous() and al.data_ptr() == arena.flat.data_ptr() + 4 * o, n
+            T = p.shape[2] * p.shape[3] * p.shape[4]
+            assert tuple(al.shape) == ((T, p.shape[1], p.shape[0]) if tr else (T, p.shape[0], p.shape[1]))
+            # element (tap t, out channel co, in channel ci) of the alias is the same number the module sees
+            co, ci, t = al.shape[1] - 1, al.shape[2] // 2, T // 2
+            w5 = p.detach().reshape(p.shape[0], p.shape[1], T)
+            assert float(al[t, co, ci]) == float(w5[ci, co, t] if tr else w5[co, ci, t])
+            if p.grad is not None:
+                assert ops.packed_alias(p.grad, tr).data_ptr() == arena.grad.data_ptr() + 4 * o
+        elif p.grad is not None:
+            assert p.grad.is_contiguous() and p.grad.data_ptr() == arena.grad.data_ptr() + 4 * o
+    # a state_dict written by the arena'd model loads into a stock model and back, bit for bit
+    ref.load_state_dict({k: v.clone() for k, v in model.state_dict().items()})
+    for k, v in ref.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    arena.flat.mul_(2)
+    model.load_state_dict(ref.state_dict())
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    # moment views: writing through the view of a parameter touches exactly that parameter's slots of the flat buffer
+    mom = torch.zeros_like(arena.grad)
+    vs = arena.views(mom)
+    n0 = sorted(names)[0]
+    vs[n0].fill_(1.0)
+    o, k = arena.offsets[n0]
+    assert float(mom.sum()) == k and float(mom[o:o + k].sum()) == k
 
 
 def test_augmentation_draws_follow_the_reference_order():
