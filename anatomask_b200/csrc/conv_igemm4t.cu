@@ -100,13 +100,12 @@ __global__ void __launch_bounds__(256, 1) igemm4t_kernel(const __grid_constant__
                     const uint32_t set = cc & 1u, ph = (cc >> 1) & 1u;
                     mbar_wait_u32(a_empty0 + set * 8u, ph ^ 1u, 51);
                     if (elect_one()) {
+                        const uint32_t bar = a_full0 + set * 8u;            // one barrier per plane set
+                        mbar_expect_tx_u32(bar, (uint32_t)NP * P.plane_tx);
 #pragma unroll
-                        for (int pl = 0; pl < NP; ++pl) {
-                            const uint32_t bar = a_full0 + (set * NP + (uint32_t)pl) * 8u;
-                            mbar_expect_tx_u32(bar, P.plane_tx);
+                        for (int pl = 0; pl < NP; ++pl)
                             tma_load_5d_u32(a_ring_u32 + (set * NP + (uint32_t)pl) * V4T_SLOT, &P.a_map, bar, (int)(kc * 32),
                                             c.x0 - 1, c.y0 - 1, c.z0 - 1 + pl, c.n);
-                        }
                     }
                     __syncwarp();
                 }
@@ -143,7 +142,9 @@ __global__ void __launch_bounds__(256, 1) igemm4t_kernel(const __grid_constant__
         const uint32_t id1 = P.idesc[0], id3 = P.idesc[2];
         const uint32_t blk16 = P.blk_bytes >> 4;
         uint32_t cc = 0, b_slot = 0, b_phase = 0, iter = 0;
+        uint32_t b_ready = 0, a_ready = 0;      // look-ahead polls of the next slab / plane set (see conv_igemm4.cu)
         for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+#pragma unroll
             for (int q = 0; q < 4; ++q, ++iter) {
                 const uint32_t acc = iter & 1u;
                 mbar_wait_u32(smem_u32(&tempty[acc]), ((iter >> 1) & 1u) ^ 1u, 53);
@@ -152,15 +153,21 @@ __global__ void __launch_bounds__(256, 1) igemm4t_kernel(const __grid_constant__
                 for (uint32_t kc = 0; kc < kchunks; ++kc, ++cc) {
                     const uint32_t set = cc & 1u, aph = (cc >> 1) & 1u;
                     const uint32_t a_set = a_ring_u32 + set * NP * V4T_SLOT;
-#pragma unroll 1
-                    for (int t4 = 0; t4 < 4; ++t4) {
-                        mbar_wait_u32(b_full0 + b_slot * 8u, b_phase, 55);
-                        if (t4 == 0) {
 #pragma unroll
-                            for (int pl = 0; pl < NP; ++pl) mbar_wait_u32(a_full0 + (set * NP + (uint32_t)pl) * 8u, aph, 54);
-                        }
+                    for (int t4 = 0; t4 < 4; ++t4) {
+                        if (!b_ready) mbar_wait_u32(b_full0 + b_slot * 8u, b_phase, 55);
+                        if (t4 == 0 && !a_ready) mbar_wait_u32(a_full0 + set * 8u, aph, 54);
                         tc_fence_after();
-                        const uint32_t a_lo = lo_const | (((a_set + (uint32_t)P.row_off[q][t4]) & 0x3FFFFu) >> 4);
+                        {
+                            const uint32_t nslot = b_slot + 1 == B_SLOTS ? 0u : b_slot + 1;
+                            b_ready = mbar_test_wait_u32(b_full0 + nslot * 8u, b_slot + 1 == B_SLOTS ? b_phase ^ 1u : b_phase);
+                            if (t4 == 3) a_ready = mbar_test_wait_u32(a_full0 + ((cc + 1) & 1u) * 8u, ((cc + 1) >> 1) & 1u);
+                        }
+                        // window start (dy + 1, dx + 1) inside a plane of PW = 10 columns: an immediate once q and t4 are unrolled
+                        // (parity 0 reads offsets {0, -1}, parity 1 reads {+1, 0}: row_off in igemm4t_conv)
+                        const int wy = ((q >> 1) ? ((t4 >> 1) ? 0 : 1) : ((t4 >> 1) ? -1 : 0)) + 1;
+                        const int wx = ((q & 1) ? ((t4 & 1) ? 0 : 1) : ((t4 & 1) ? -1 : 0)) + 1;
+                        const uint32_t a_lo = lo_const | (((a_set + (uint32_t)((wy * 10 + wx) * 64)) & 0x3FFFFu) >> 4);
                         const uint32_t b_lo = lo_const | (((b_ring_u32 + b_slot * b_bytes) & 0x3FFFFu) >> 4);
                         const bool first = (kc | (uint32_t)t4) == 0u;
                         if (elect_one()) {
