@@ -68,10 +68,14 @@ int amb_pack_weight(const float* src, void* dst, int T, int A, int B, long st, l
 int amb_unpack_wgrad(const float* src, float* dst, int T, int A, int B, long st, long sa, long sb, void* stream);
 /* All conv weights of a step in ONE launch (the reference's nn.Conv3d / nn.ConvTranspose3d read their fp32 `weight`
  * parameters in every forward — P/encoder3D.py:13, P/decoder3D.py:18-22, P/spark3D.py:82; here the bf16
- * operand copies are refreshed once per step).  A job packs one tensor whose taps are innermost (st == 1):
- * b_fast = 1: src[(a*B + b)*T + t], b_fast = 0: src[(b*A + a)*T + t]; tiles are 4x64 (b_fast) or 16x16 (a, b) positions
- * x 32 taps; tile_begin = first block of the job, tiles_b / tchunks = tiles along b / tap chunks.  The table lives in
- * device memory. */
+ * operand copies are refreshed once per step).  Job kinds (`b_fast`):
+ *   1 / 0  stock parameter layout, taps innermost (st == 1): src[(a*B + b)*T + t] / src[(b*A + a)*T + t]; tiles are 4x64
+ *          (kind 1) or 16x16 (a, b) positions x 32 taps, tiles_b / tchunks = tiles along b / tap chunks
+ *   2      taps-major source in dst order, src[(t*A + a)*B + b] (the engine's parameter arena): plain fp32 -> bf16
+ *          conversion, one block per 2048 elements (tiles_b / tchunks unused)
+ *   3      taps-major source with a and b swapped, src[(t*B + b)*A + a] (the input-gradient operand of an arena weight):
+ *          per-tap transpose, blocks of 32 a x 64 b, tiles_b / tchunks = tiles along b / along a
+ * tile_begin = first block of the job.  The table lives in device memory. */
 typedef struct amb_pack_job {
     const float* src;
     void* dst;
