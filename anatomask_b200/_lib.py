@@ -100,6 +100,20 @@ def load() -> C.CDLL:
             raise RuntimeError(
                 f'{LIB_PATH} is missing: build it with `python -m anatomask_b200.build` (nvcc, sm_100a). '
                 'anatomask_b200 has no CPU or non-B200 fallback.')
+        if os.environ.get('AMB_LIB_PATH') is None:
+            # a library older than its sources measures (and tests) something else than the tree says: say so loudly;
+            # AMB_STRICT_LIB=1 turns the warning into an error
+            try:
+                from . import build as _b
+                if os.path.isdir(_b.CSRC) and _b.built_hash() != _b.source_hash():
+                    msg = (f'{LIB_PATH} was not built from the sources in {_b.CSRC} (source hash differs from the build stamp): '
+                           'run `python -m anatomask_b200.build`')
+                    if os.environ.get('AMB_STRICT_LIB') == '1':
+                        raise RuntimeError(msg)
+                    import sys
+                    print('[anatomask_b200] WARNING: ' + msg, file=sys.stderr)
+            except OSError:
+                pass
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError here = header/library mismatch

@@ -12,12 +12,33 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '-Wno-deprecated-gpu-targets']
 
 
+STAMP = LIB + '.src-sha256'
+
+
+def source_hash() -> str:
+    """sha256 over every file the library is compiled from (csrc/ + the C header) and the compiler flags."""
+    import hashlib
+    h = hashlib.sha256(' '.join(NVCC_FLAGS + SOURCES).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, '..', 'include', 'anatomask_b200.h')]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def built_hash() -> str:
+    try:
+        with open(STAMP) as f:
+            return f.read().strip()
+    except OSError:
+        return ''
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, '..', 'include', 'anatomask_b200.h')]
-    return any(os.path.getmtime(d) > t for d in deps)
+    """By content, not by mtime: a `git checkout` of a source file after the last build must trigger a rebuild, and the copy
+    of the tree on a GPU box (fresh mtimes) must not."""
+    return not os.path.exists(LIB) or built_hash() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -42,6 +63,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError('nvcc failed')
     cmd = [nvcc, '-shared', '-o', LIB, *objs, '-cudart', 'static', '-Wno-deprecated-gpu-targets']
     subprocess.check_call(cmd)
+    with open(STAMP, 'w') as f:
+        f.write(source_hash() + '\n')
     return LIB
 
 

@@ -11,6 +11,14 @@ from oracle import reference_port as rp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def test_library_is_built_from_the_sources_in_the_tree():
+    """The build stamp (sha256 of csrc/ + header + flags) equals the hash of the sources: a stale library would make every GPU
+    number describe another tree.  Rebuilds first if needed (nvcc cross-compiles sm_100a without a GPU)."""
+    from anatomask_b200 import build as b
+    b.build(force=False)
+    assert os.path.exists(b.LIB) and b.built_hash() == b.source_hash() and not b.needs_build()
+
+
 def test_library_exports_every_declared_symbol():
     from anatomask_b200 import _lib
     lib = _lib.load()
