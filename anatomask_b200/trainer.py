@@ -203,6 +203,7 @@ class PretrainEngine:
         self._static_inp = None
         self._stage = None                   # (copy stream, device buffer) of stage_input()
         self._stage_ready = self._stage_consumed = None
+        self._stage_pending = False
         self._static_out = None
 
     # ---- pieces ---------------------------------------------------------------------------------------------
@@ -355,7 +356,9 @@ class PretrainEngine:
         self.teacher.mask_rng = 'device'
         self.teacher.rng_counter = self.step_counter
         self._set_hyper(epoch)
+        staged = self._staged_begin(inp)
         out = self._device_step(inp, epoch)
+        self._staged_end(staged)                     # eager steps read the batch until their last kernel
         self.t += 1
         return out
 
@@ -448,6 +451,9 @@ class PretrainEngine:
             self._stage = (torch.cuda.Stream(dev), torch.empty(host.shape, dtype=torch.float32, device=dev))
             self._stage_consumed = None
         cs, buf = self._stage
+        if self._stage_pending:
+            raise RuntimeError('stage_input: the batch staged before has not been handed to a step yet (one staging buffer: '
+                               'stage, step, stage, step, ...)')
         if self._stage_consumed is not None:
             cs.wait_event(self._stage_consumed)          # the previous batch has been copied out of the buffer
         else:
@@ -456,16 +462,27 @@ class PretrainEngine:
             buf.copy_(host, non_blocking=True)
             self._stage_ready = torch.cuda.Event()
             self._stage_ready.record(cs)
+        self._stage_pending = True
         return buf
 
-    def _consume_input(self, inp: torch.Tensor):
+    def _staged_begin(self, inp: torch.Tensor) -> bool:
+        """A step is about to read `inp`: if it is the staging buffer, wait for its copy."""
         staged = self._stage is not None and inp is self._stage[1]
         if staged:
             torch.cuda.current_stream().wait_event(self._stage_ready)
-        self._static_inp.copy_(inp, non_blocking=True)
+        return staged
+
+    def _staged_end(self, staged: bool):
+        """The step's last read of the staging buffer has been enqueued: the next stage_input() may overwrite it after this."""
         if staged:
             self._stage_consumed = torch.cuda.Event()
             self._stage_consumed.record()
+            self._stage_pending = False
+
+    def _consume_input(self, inp: torch.Tensor):
+        staged = self._staged_begin(inp)
+        self._static_inp.copy_(inp, non_blocking=True)
+        self._staged_end(staged)
 
     # ---- steps ----------------------------------------------------------------------------------------------
     def spark_step(self, inp: torch.Tensor, active: Optional[torch.Tensor] = None, epoch: int = 0) -> torch.Tensor:
@@ -483,6 +500,7 @@ class PretrainEngine:
         # counter left attached would freeze the random fill of generate_mask at one stream position
         self.teacher.rng_counter = None
         B = inp.shape[0]
+        staged = self._staged_begin(inp)
         if mask1 is None:
             mask1 = self.random_mask(B, inp.device)
         with torch.no_grad(), ops.lean_zero():
@@ -492,4 +510,5 @@ class PretrainEngine:
         loss = self._student_fwd_bwd(inp, mask)
         self._optimise(lr_at_epoch(epoch, self.lr, max_epochs=self.epochs))
         self.ema_update(ema_decay_at_epoch(epoch, self.epochs))
+        self._staged_end(staged)
         return loss, mask, recon

@@ -372,6 +372,18 @@ def check_staged_input(name='S64', batch=2, seed=1, steps=5):
             losses.append(float(loss))
         out[mode] = (losses, same)
     d = max(abs(a - b) / abs(b) for a, b in zip(out['staged'][0], out['plain'][0]))
+    # the last engine still holds a staged batch: staging another one before a step took it over must fail loudly, and an
+    # eager step (which reads the staging buffer until its last kernel) must accept it and free it
+    try:
+        eng.stage_input(hosts[0])
+        raise AssertionError('stage_input twice without a step did not raise')
+    except RuntimeError:
+        pass
+    loss_e, _, _ = eng.device_step(nxt, 500)
+    assert np.isfinite(float(loss_e))
+    nxt = eng.stage_input(hosts[1])
+    loss_s, _, _ = eng.step(nxt, epoch=500)
+    assert np.isfinite(float(loss_s))
     print('RESULT staged_input', name, json.dumps({'plain': out['plain'][0], 'staged': out['staged'][0], 'rel': d}))
     assert all(out['plain'][1]) and all(out['staged'][1]), out
     assert d < 5e-3, d
